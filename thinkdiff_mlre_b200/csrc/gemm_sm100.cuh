@@ -1,0 +1,364 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> smem ring -> tcgen05.mma (accumulators in TMEM)
+// -> tcgen05.ld epilogue, with the aligner's elementwise / reduction work fused into the epilogue.
+//
+//   D[M,N] = A[M,K] * B[N,K]^T          (logical; fp32 accumulate)
+//
+// Each operand is either K-major (stored [rows, K], K contiguous -- activations in the forward pass, nn.Linear
+// weights) or MN-major (stored [K, rows], rows contiguous -- what the backward pass has: dW = dY^T X contracts
+// over the token dimension of two row-major activations, dX = dY W contracts over W's row index). The tensor
+// core reads both through the 128-byte-swizzled canonical layouts, so no transposed copies are ever written.
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue
+// (one TMEM lane quarter each). CTAS=2 runs a CTA pair on one 256-row tile (tcgen05 cta_group::2): each CTA
+// stages its own 128 rows of A and half of B, the leader issues the MMAs, both run their own epilogue.
+//
+// Reference semantics being fused (thinkdiff/models/mllama_vllm_t5_embed_decoder_2.py:58-63, under the bf16
+// autocast of thinkdiff/tasks/base_task.py:237): Linear -> GELU(erf) -> Linear -> T5LayerNorm, each Linear/GELU
+// output rounded to bf16, the norm statistics taken in fp32 from the bf16-rounded Linear2 output.
+#pragma once
+#include "ptx_sm100.cuh"
+
+namespace td {
+
+enum EpiKind : int {
+  EPI_BF16 = 0,       // out0 = bf16(acc + bias?)
+  EPI_BIAS_GELU = 1,  // out0 = h0 = bf16(acc + bias); out1 = bf16(gelu(h0))
+  EPI_BIAS_SSQ = 2,   // out0 = h2 = bf16(acc + bias); red0[n_blk][row] = sum_cols h2^2
+  EPI_DGELU = 3,      // t = bf16(acc); out0 = bf16(t * gelu'(aux0)); red0[m_slab][col] = sum_rows out0
+  EPI_F32 = 4,        // out0(fp32) = alpha * acc   (splits > 1: red.add into a zeroed out0)
+};
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks;  // in units of tile (BLOCK_M * CTAS, BLOCK_N, BLOCK_K)
+  int splits, k_blocks_per_split;
+  void* out0;
+  void* out1;
+  const void* aux0;
+  const __nv_bfloat16* bias;
+  float* red0;
+  long long ld_out;  // elements
+  float alpha;
+};
+
+constexpr int kBlockM = 128;  // rows per CTA (TMEM lanes)
+constexpr int kBlockN = 256;  // accumulator columns (two stages fill the 512-column TMEM)
+constexpr int kBlockK = 64;   // 64 bf16 = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kAccStages = 2;
+
+template <int CTAS>
+struct GemmSmem {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;           // 16 KB
+  static constexpr int kBBytes = (kBlockN / CTAS) * kBlockK * 2;  // 32 KB or 16 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (CTAS == 1) ? 4 : 6;
+  static constexpr int kBarrierBytes = 1024;
+  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // +1024 alignment slack
+};
+
+// ------------------------------------------------------------------------------------------ epilogues
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int row0, int n0, int n_blk,
+                                              int m_slab, int quarter, int lane) {
+  const int row = row0 + quarter * 32 + lane;
+  const bool row_ok = row < p.M;
+  const uint32_t taddr = tmem_acc + (uint32_t(quarter * 32) << 16);
+  float ssq = 0.f;
+
+#pragma unroll 1
+  for (int c = 0; c < kBlockN / 32; ++c) {
+    const int col0 = n0 + c * 32;
+    if (col0 >= p.N) break;  // N % 32 == 0 is enforced on the host
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    tmem_ld_wait();
+
+    if constexpr (EPI == EPI_F32) {
+      float* out = reinterpret_cast<float*>(p.out0) + (long long)row * p.ld_out + col0;
+      if (row_ok) {
+        if (p.splits == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(p.alpha * __uint_as_float(v[j]), p.alpha * __uint_as_float(v[j + 1]),
+                                   p.alpha * __uint_as_float(v[j + 2]), p.alpha * __uint_as_float(v[j + 3]));
+            *reinterpret_cast<float4*>(out + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + j),
+                         "f"(p.alpha * __uint_as_float(v[j])), "f"(p.alpha * __uint_as_float(v[j + 1])),
+                         "f"(p.alpha * __uint_as_float(v[j + 2])), "f"(p.alpha * __uint_as_float(v[j + 3]))
+                         : "memory");
+          }
+        }
+      }
+    } else {
+      // bias (bf16, same 32 columns for every thread of the warp -> broadcast loads)
+      float b[32];
+      if constexpr (EPI == EPI_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_SSQ) {
+        if (p.bias != nullptr) {
+          const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u = __ldg(bp + q);
+            b[q * 8 + 0] = bf16lo(u.x); b[q * 8 + 1] = bf16hi(u.x);
+            b[q * 8 + 2] = bf16lo(u.y); b[q * 8 + 3] = bf16hi(u.y);
+            b[q * 8 + 4] = bf16lo(u.z); b[q * 8 + 5] = bf16hi(u.z);
+            b[q * 8 + 6] = bf16lo(u.w); b[q * 8 + 7] = bf16hi(u.w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) b[j] = 0.f;
+        }
+      }
+      float h[32];  // first output, already rounded to bf16 precision
+      if constexpr (EPI == EPI_DGELU) {
+        // gelu'(h0) on the saved pre-activation; dh1 is rounded to bf16 first, as autograd materialises it.
+        uint4 a[4];
+        if (row_ok) {
+          const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux0) +
+                                                           (long long)row * p.ld_out + col0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) a[q] = __ldg(ap + q);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) a[q] = make_uint4(0, 0, 0, 0);
+        }
+        const uint32_t* aw = reinterpret_cast<const uint32_t*>(a);
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float x0 = bf16lo(aw[j >> 1]), x1 = bf16hi(aw[j >> 1]);
+          const float t0 = bf16_round(__uint_as_float(v[j])), t1 = bf16_round(__uint_as_float(v[j + 1]));
+          h[j] = row_ok ? bf16_round(t0 * gelu_erf_grad(x0)) : 0.f;
+          h[j + 1] = row_ok ? bf16_round(t1 * gelu_erf_grad(x1)) : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) h[j] = bf16_round(__uint_as_float(v[j]) + b[j]);
+      }
+
+      if (row_ok) {
+        uint4* o0 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out0) + (long long)row * p.ld_out + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          o0[q] = make_uint4(pack_bf16x2(h[q * 8 + 0], h[q * 8 + 1]), pack_bf16x2(h[q * 8 + 2], h[q * 8 + 3]),
+                             pack_bf16x2(h[q * 8 + 4], h[q * 8 + 5]), pack_bf16x2(h[q * 8 + 6], h[q * 8 + 7]));
+      }
+      if constexpr (EPI == EPI_BIAS_GELU) {
+        if (row_ok) {
+          uint4* o1 =
+              reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out1) + (long long)row * p.ld_out + col0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float g[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = gelu_erf(h[q * 8 + j]);
+            o1[q] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
+                               pack_bf16x2(g[6], g[7]));
+          }
+        }
+      }
+      if constexpr (EPI == EPI_BIAS_SSQ) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ssq = fmaf(h[j], h[j], ssq);
+      }
+      if constexpr (EPI == EPI_DGELU) {
+        // Column sums over this warp's 32 rows by a butterfly transpose-reduce: after the 5 rounds lane j
+        // holds sum over lanes of h[j]. 31 shuffles for 32 columns.
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < off; ++i) {
+            const float send = upper ? h[i] : h[i + off];
+            const float keep = upper ? h[i + off] : h[i];
+            h[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        p.red0[(long long)(m_slab * 4 + quarter) * p.N + col0 + lane] = h[0];
+      }
+    }
+  }
+  if constexpr (EPI == EPI_BIAS_SSQ) {
+    if (row_ok) p.red0[(long long)n_blk * p.M + row] = ssq;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+template <int CTAS, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+  using S = GemmSmem<CTAS>;
+  constexpr int kStages = S::kStages;
+  constexpr int kBRows = kBlockN / CTAS;  // B rows staged by one CTA
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint64_t* full_bar = bars;                               // [kStages]   TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;                    // [kStages]   MMA -> TMA
+  uint64_t* acc_full_bar = bars + 2 * kStages;             // [kAccStages] MMA -> epilogue
+  uint64_t* acc_empty_bar = bars + 2 * kStages + kAccStages;  // [kAccStages] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(&acc_full_bar[s], 1);
+      mbar_init(&acc_empty_bar[s], 128 * CTAS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<CTAS>(tmem_slot, 512);
+    tmem_relinquish<CTAS>();
+  }
+  tc_fence_before();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // persistent schedule: work unit = (tile, split); units are dealt round-robin to CTAs (or CTA pairs)
+  const int num_workers = gridDim.x / CTAS;
+  const int worker = blockIdx.x / CTAS;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int num_units = num_tiles * p.splits;
+  constexpr int kGroupM = 8;  // rasterise m-blocks in groups so that concurrently running tiles share operands in L2
+
+  auto unit_coords = [&](int unit, int& m_blk, int& n_blk, int& kb0, int& kb1) {
+    const int tile = unit % num_tiles;
+    const int split = unit / num_tiles;
+    const int group = tile / (kGroupM * p.num_n_blocks);
+    const int first_m = group * kGroupM;
+    const int gsize = min(kGroupM, p.num_m_blocks - first_m);
+    const int in_group = tile - group * kGroupM * p.num_n_blocks;
+    m_blk = first_m + in_group % gsize;
+    n_blk = in_group / gsize;
+    kb0 = split * p.k_blocks_per_split;
+    kb1 = min(p.num_k_blocks, kb0 + p.k_blocks_per_split);
+  };
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = worker; unit < num_units; unit += num_workers) {
+        int m_blk, n_blk, kb0, kb1;
+        unit_coords(unit, m_blk, n_blk, kb0, kb1);
+        const int a_row0 = m_blk * (kBlockM * CTAS) + cta_rank * kBlockM;
+        const int b_row0 = n_blk * kBlockN + cta_rank * kBRows;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes * CTAS);
+          const int k0 = kb * kBlockK;
+          if constexpr (!A_MN) {
+            if constexpr (CTAS == 1) tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, a_row0);
+            else tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], k0, a_row0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBlockM / 64; ++j) {
+              if constexpr (CTAS == 1) tma_load_2d(sa + j * (kBlockK * 128), &tmap_a, &full_bar[stage], a_row0 + j * 64, k0);
+              else tma_load_2d_pair(sa + j * (kBlockK * 128), &tmap_a, &full_bar[stage], a_row0 + j * 64, k0);
+            }
+          }
+          if constexpr (!B_MN) {
+            if constexpr (CTAS == 1) tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, b_row0);
+            else tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], k0, b_row0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBRows / 64; ++j) {
+              if constexpr (CTAS == 1) tma_load_2d(sb + j * (kBlockK * 128), &tmap_b, &full_bar[stage], b_row0 + j * 64, k0);
+              else tma_load_2d_pair(sb + j * (kBlockK * 128), &tmap_b, &full_bar[stage], b_row0 + j * 64, k0);
+            }
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CTAS, kBlockN, A_MN, B_MN);
+      // K-major SW128: rows 128 B apart, 8-row groups 1024 B apart (SBO); LBO unused.
+      // MN-major SW128: 64-element row chunks; next 8 k-rows 1024 B (SBO), next 64 MN elements one box (LBO).
+      constexpr uint32_t a_lbo = A_MN ? kBlockK * 128 : 16, b_lbo = B_MN ? kBlockK * 128 : 16;
+      constexpr uint32_t sbo = 1024;
+      constexpr uint32_t a_kstep = A_MN ? kUmmaK * 128 : kUmmaK * 2;  // bytes per UMMA_K step
+      constexpr uint32_t b_kstep = B_MN ? kUmmaK * 128 : kUmmaK * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int unit = worker; unit < num_units; unit += num_workers) {
+        int m_blk, n_blk, kb0, kb1;
+        unit_coords(unit, m_blk, n_blk, kb0, kb1);
+        mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kBlockN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t sb = sa + S::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, sbo);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, sbo);
+            umma_bf16<CTAS>(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit<CTAS>(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit<CTAS>(&acc_full_bar[acc]);  // accumulator complete -> epilogue(s)
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue warps (TMEM lane quarter = warp % 4)
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = worker; unit < num_units; unit += num_workers) {
+      int m_blk, n_blk, kb0, kb1;
+      unit_coords(unit, m_blk, n_blk, kb0, kb1);
+      mbar_wait(&acc_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int m_slab = m_blk * CTAS + cta_rank;
+      if (kb1 > kb0)
+        epilogue_tile<EPI>(p, tmem_base + acc * kBlockN, m_slab * kBlockM, n_blk * kBlockN, n_blk, m_slab, quarter, lane);
+      tc_fence_before();
+      if constexpr (CTAS == 1) mbar_arrive(&acc_empty_bar[acc]);
+      else mbar_arrive_cluster(&acc_empty_bar[acc], 0);
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  // teardown: everyone (both CTAs of a pair) must be done with TMEM and the barriers before it is freed
+  tc_fence_before();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<CTAS>(tmem_base, 512);
+  }
+}
+
+}  // namespace td
