@@ -1,0 +1,114 @@
+/* thinkdiff_b200.h -- C ABI of the B200-native ThinkDiff aligner hot path (libthinkdiff_b200.so).
+ *
+ * The reference (avi22bhattacharya/ThinkDiff-mlre) is 100 % Python and has no FFI of its own: the hot path is the
+ * `mm_projector` nn.Module built by `build_vision_projector` and the ops either side of it. Each entry point below
+ * names the reference code it replaces (paths relative to the reference root). The host side that binds these
+ * symbols is thinkdiff_mlre_b200/_lib.py (ctypes); INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions: plain pointers and sizes only; every pointer is a DEVICE pointer unless marked [host]; the caller owns
+ * all buffers (outputs, saved activations, workspaces); every call is asynchronous on `stream` (a cudaStream_t);
+ * return value 0 = ok, negative = error, text via td_last_error() (thread-local). No exceptions cross the ABI.
+ * bf16 tensors are row-major, 16-byte aligned, with feature dimensions that are multiples of 64.
+ * There is no CPU fallback: a device that is not sm_100 makes every call fail with TD_ERR_UNSUPPORTED.
+ */
+#ifndef THINKDIFF_B200_H
+#define THINKDIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* td_stream_t; /* cudaStream_t */
+
+enum { TD_DTYPE_F32 = 0, TD_DTYPE_BF16 = 1 };
+enum { TD_OK_ = 0, TD_ERR_ARG_ = -1, TD_ERR_UNSUPPORTED_ = -2, TD_ERR_DRIVER_ = -3 };
+/* td_aligner_bwd phases (bit mask): the split lets the caller start the all-reduce of the Linear2 gradients
+ * while the Linear1 gradients are still being computed (DDP bucket overlap, thinkdiff/runners/runner_base.py:88-92). */
+enum { TD_BWD_PHASE_NORM_W2 = 1, TD_BWD_PHASE_GELU_W1 = 2, TD_BWD_PHASE_ALL = 3 };
+
+const char* td_last_error(void);
+int32_t td_version(void);
+/* 0 when the current CUDA device can run this library (compute capability 10.x), else TD_ERR_UNSUPPORTED. */
+int32_t td_device_check(void);
+
+/* Per-launch device timing for benchmarks: while enabled, every kernel launch of the library is bracketed by CUDA
+ * events on its stream. td_profile_report fills `buf` [host] with "tag,launches,total_ms,total_work\n" lines, where
+ * work = algorithmic FLOPs for gemm_* tags and algorithmic bytes for the row kernels. Enabling clears old records. */
+int32_t td_profile_enable(int32_t on);
+int32_t td_profile_report(char* buf /*[host]*/, int32_t buflen);
+
+/* ---- (1) ragged pack / pad / mask ------------------------------------------------------------------------
+ * Replaces the collater's pad/stack/mask loop, thinkdiff/datasets/datasets/llava_instruct_dataset_mllama_embed_2.py
+ * :101-131 (random split), :132-162 (fixed max), :78-99 (input embeds), and the padded H2D copy of
+ * thinkdiff/datasets/data_utils.py:83-96. Source = all samples' full embeddings back to back, `row_bytes` per row;
+ * sample i keeps rows [src_row_start[i], src_row_start[i] + len_i). Outputs are bit-exact copies. */
+int32_t td_cu_seqlens(const int32_t* lens, int32_t B, int32_t* cu_seqlens /*[B+1]*/, td_stream_t stream);
+int32_t td_pack_varlen(const void* src, const int64_t* src_row_start /*[B]*/, const int32_t* cu_seqlens /*[B+1]*/,
+                       int32_t B, int64_t total_rows /* = cu_seqlens[B], known to the host */, int64_t row_bytes,
+                       void* dst_packed /*[total_rows, row_bytes]*/, td_stream_t stream);
+/* Reference layout: zero-padded [B, L_max, row_bytes] + int64 mask [B, L_max] (mask may be NULL). With
+ * src = a packed buffer and src_row_start[i] = cu_seqlens[i] this is the inverse of td_pack_varlen. */
+int32_t td_pack_padded(const void* src, const int64_t* src_row_start, const int32_t* cu_seqlens, int32_t B, int32_t L_max,
+                       int64_t row_bytes, void* dst_padded, int64_t* mask, td_stream_t stream);
+
+/* ---- parameters: fp32 master -> bf16 compute copy (what autocast does per call, base_task.py:237) ---------- */
+int32_t td_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, td_stream_t stream);
+
+/* ---- (2) aligner = Linear -> GELU(erf) -> Linear -> T5LayerNorm ---------------------------------------------
+ * Replaces `self.mm_projector(x)` (thinkdiff/models/mllama_vllm_t5_embed_decoder_2.py:585, :761, :998, :1115;
+ * thinkdiff/models/blip_vision_t5_decoder.py:414, :641) for the module built at ...embed_decoder_2.py:58-63.
+ *   x [M, Din] bf16 (rows = tokens; pass the packed buffer), W1 [D, Din], b1 [D], W2 [D, D], b2 [D] bf16, g [D] fp32.
+ *   Saved for backward (may be NULL for inference, except h2): h0 = Linear1 out, h1 = GELU out, h2 = Linear2 out
+ *   (all bf16 [M, D]), rstd fp32 [M].  y [M, D]: fp32 (training rule) or bf16 (pure-bf16 inference rule). */
+int64_t td_aligner_fwd_workspace_bytes(int64_t M, int32_t Din, int32_t D);
+int32_t td_aligner_fwd(const void* x, int64_t M, int32_t Din, int32_t D, const void* W1, const void* b1, const void* W2,
+                       const void* b2, const float* g, float eps, void* h0, void* h1, void* h2, float* rstd, void* y,
+                       int32_t y_dtype, void* workspace, int64_t workspace_bytes, td_stream_t stream);
+/* Backward of the above for an upstream gradient dy [M, D] (fp32 or bf16). Replaces autograd through the Sequential
+ * (triggered at thinkdiff/tasks/base_task.py:241-244). Writes (not accumulates) fp32 gradients scaled by grad_scale:
+ * dW1 [D, Din], db1 [D], dW2 [D, D], db2 [D], dg [D]. No dx (the features do not require grad). */
+int64_t td_aligner_bwd_workspace_bytes(int64_t M, int32_t Din, int32_t D);
+int32_t td_aligner_bwd(const void* dy, int32_t dy_dtype, const void* x, const void* h0, const void* h1, const void* h2,
+                       const float* rstd, const void* W2, const float* g, int64_t M, int32_t Din, int32_t D,
+                       float grad_scale, float* dW1, float* db1, float* dW2, float* db2, float* dg, void* workspace,
+                       int64_t workspace_bytes, int32_t phases, td_stream_t stream);
+
+/* Standalone T5LayerNorm forward / backward (transformers modeling_t5.py T5LayerNorm, imported at
+ * ...embed_decoder_2.py:24). x bf16 [M, D]; y fp32 or bf16; dW/db are fp32 [D]; db = column sums of dx (may be NULL). */
+int32_t td_rmsnorm_fwd(const void* x, const float* g, float eps, int64_t M, int32_t D, void* y, int32_t y_dtype,
+                       float* rstd, td_stream_t stream);
+int64_t td_rmsnorm_bwd_workspace_bytes(int64_t M, int32_t D);
+int32_t td_rmsnorm_bwd(const void* dy, int32_t dy_dtype, const void* x, const float* rstd, const float* g, int64_t M,
+                       int32_t D, void* dx_bf16, float* dg, float* dxsum, void* workspace, int64_t workspace_bytes,
+                       td_stream_t stream);
+
+/* Plain bf16 linear  out[M, N] = x[M, K] . W[N, K]^T (+ bias)  -- nn.Linear under autocast (F.linear). */
+int32_t td_linear_bf16(const void* x, int64_t M, int32_t K, const void* W, int32_t N, const void* bias, void* out,
+                       td_stream_t stream);
+/* Generic entry to the tcgen05 GEMM for tests: D[M,N] (fp32) = alpha * A.B^T with either operand K-major
+ * ([rows, K]) or MN-major ([K, rows]); cta_pair selects cta_group::2; splits = 0 lets the library choose. */
+int32_t td_gemm_bf16_f32out(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb,
+                            int32_t b_mn_major, int64_t M, int32_t N, int64_t K, float alpha, float* out,
+                            int32_t cta_pair, int32_t splits, td_stream_t stream);
+
+/* ---- (3) masked losses, forward + gradient in one pass -----------------------------------------------------
+ * Cross entropy replaces `CrossEntropyLoss(ignore_index=-100)(lm_logits.view(-1, V), labels.view(-1))`
+ * (thinkdiff/models/mllama_vllm_t5_embed_decoder_2.py:241-246; blip_vision_t5_decoder.py:222-227).
+ * Masked MSE is the north-star's added loss (absent from the reference): mean over valid rows x D of (y - t)^2.
+ * loss: fp32 scalar on the device. Gradients are multiplied by grad_scale (GradScaler, base_task.py:241). */
+int64_t td_loss_workspace_bytes(int64_t rows);
+int32_t td_masked_mse_fwd_bwd(const void* y, int32_t y_dtype, const void* target, int32_t target_dtype,
+                              const int64_t* row_mask /* NULL = all rows valid; else != 0 is valid */, int64_t M,
+                              int32_t D, float grad_scale, float* loss, void* dy /* y_dtype, may be NULL */,
+                              void* workspace, int64_t workspace_bytes, td_stream_t stream);
+int32_t td_masked_ce_fwd_bwd(const void* logits, int32_t logits_dtype, const int64_t* labels /* -100 = ignore */,
+                             int64_t R, int32_t V, float grad_scale, float* loss,
+                             void* dlogits /* logits_dtype, may be NULL */, void* workspace, int64_t workspace_bytes,
+                             td_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THINKDIFF_B200_H */

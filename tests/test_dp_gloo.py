@@ -1,0 +1,94 @@
+"""World-size-2 data-parallel logic on CPU (gloo): sharding + flat gradient buckets + pre-scaled SUM all-reduce must
+equal DDP's semantics -- the mean over ranks of each rank's own mean-loss gradients (runner_base.py:88-92) -- computed
+here by the oracle in one process. The CUDA kernels are not involved (no GPU here); gradients come from the oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import aligner_ref
+from thinkdiff_mlre_b200.aligner import DataParallelState, GradBuckets
+from thinkdiff_mlre_b200.sharding import shard_bounds
+
+DIN, D, SEQS = 64, 128, 5
+NAMES = ("dW1", "db1", "dW2", "db2", "dg")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _global_batch():
+    rng = np.random.RandomState(42)
+    lens = [3, 9, 4, 7, 2]  # ragged: the two shards hold different token counts
+    xs = [torch.from_numpy(rng.standard_normal((n, DIN)).astype(np.float32)) for n in lens]
+    ts = [torch.from_numpy(rng.standard_normal((n, D)).astype(np.float32)) for n in lens]
+    return xs, ts
+
+
+def _shard_grads(xs, ts, params):
+    x, t = torch.cat(xs), torch.cat(ts)
+    fwd = aligner_ref.aligner_fwd_bwd_manual(x, params, regime="fp32")
+    dy = 2.0 * (fwd["y"] - t) / t.numel()  # this rank's OWN mean loss
+    out = aligner_ref.aligner_fwd_bwd_manual(x, params, dy=dy, regime="fp32")
+    return [out[n] for n in NAMES]
+
+
+def _worker(rank, world, port, overlap, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        params = aligner_ref.init_params_numpy(DIN, D, seed=3)
+        xs, ts = _global_batch()
+        lo, hi = shard_bounds(SEQS, world, rank)
+        grads = _shard_grads(xs[lo:hi], ts[lo:hi], params)
+        dp = DataParallelState(None, overlap=overlap)
+        gb = GradBuckets(DIN, D, "cpu")
+        for dst, src in zip(gb.in_parameter_order(), grads):
+            dst.copy_(src / dp.world)  # the kernels write gradients pre-scaled by 1/world
+        works = [dp.all_reduce_async(gb.linear2), dp.all_reduce_async(gb.linear1)]
+        for w in works:
+            w.wait()
+        if rank == 0:
+            ret.put([g.clone().numpy() for g in gb.in_parameter_order()])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_two_rank_gradient_mean_matches_oracle(overlap):
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, overlap, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = ret.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    params = aligner_ref.init_params_numpy(DIN, D, seed=3)
+    xs, ts = _global_batch()
+    per_rank = [_shard_grads(xs[slice(*shard_bounds(SEQS, world, r))], ts[slice(*shard_bounds(SEQS, world, r))], params) for r in range(world)]
+    for i, name in enumerate(NAMES):
+        want = sum(g[i] for g in per_rank) / world
+        np.testing.assert_allclose(got[i], want.numpy(), rtol=1e-5, atol=1e-8, err_msg=name)
+    # DDP's mean-of-means is NOT the global token mean when shards are ragged -- make sure we kept DDP's
+    glob = _shard_grads(xs, ts, params)
+    assert np.abs(got[2] - glob[2].numpy()).max() > 1e-6
+
+
+def test_bucket_views_alias_flat_storage():
+    gb = GradBuckets(DIN, D, "cpu")
+    gb.linear2.zero_(), gb.linear1.zero_()
+    gb.dW2.fill_(1), gb.db2.fill_(2), gb.dg.fill_(3), gb.dW1.fill_(4), gb.db1.fill_(5)
+    assert gb.linear2.numel() == D * D + 2 * D and gb.linear1.numel() == D * DIN + D
+    assert float(gb.linear2.sum()) == D * D + 2 * D + 3 * D and float(gb.linear1.sum()) == 4 * D * DIN + 5 * D
+    assert [t.shape for t in gb.in_parameter_order()] == [(D, DIN), (D,), (D, D), (D,), (D,)]

@@ -1,0 +1,233 @@
+"""Drop-in replacement for the reference's ``mm_projector`` (the ThinkDiff aligner).
+
+Reference interface mirrored here (paths relative to the reference root):
+  * ``build_vision_projector(config)``  thinkdiff/models/mllama_vllm_t5_embed_decoder_2.py:41-79
+    (duplicated in blip_vision_t5_decoder.py:31-61 and mllama_vllm_generate_1.py:53-83): ``config`` carries
+    ``mm_projector_type``, ``mm_hidden_size``, ``hidden_size``; the result is bound to ``self.mm_projector`` (:435).
+  * call sites ``self.mm_projector(x)``  ...embed_decoder_2.py:585 (train), :761/:998/:1115 (inference),
+    blip_vision_t5_decoder.py:414/:641: ``x[..., Din] -> y[..., D]``.
+
+``ThinkDiffAligner`` IS an ``nn.Sequential`` of the same four children (Linear, GELU, Linear, T5LayerNorm), so
+``state_dict`` keys (``0.weight 0.bias 2.weight 2.bias 3.weight``), ``named_parameters`` (the optimiser's weight-decay
+split, runners/runner_base.py:104-111), ``.modules()`` scans for ``T5LayerNorm`` (...embed_decoder_2.py:697-700),
+``.to()`` and DDP all behave as with the reference object. Only ``forward`` differs: it never calls the children, it
+runs the fused sm_100a kernels (two tcgen05 GEMMs with bias/GELU/sum-of-squares epilogues + one normalise pass; backward:
+one norm-backward pass + three tcgen05 GEMMs) through the C ABI. There is no fallback path.
+
+Numerical regimes:
+  * fp32 parameters under ``torch.autocast('cuda', dtype=torch.bfloat16)`` (training, base_task.py:237): bf16 GEMM
+    inputs, fp32 accumulate, bf16 h0/h1/h2, fp32 norm, **fp32 output**, fp32 gradients.
+  * bf16 parameters (``model.to(torch.bfloat16)``, scripts/test/test_blip_vision_t5_decoder_flux_text.py:104):
+    **bf16 output**, normalised value rounded to bf16 before the weight multiply (T5LayerNorm rule).
+  * fp32 parameters without autocast (BASELINE config 1): fp32 semantics, computed on the tensor cores by
+    error-compensated bf16x3 splitting (see ``fp32_mode``).
+"""
+from __future__ import annotations
+
+import re
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+
+EPS = 1e-6
+FUSED_TYPE = "mlp2x_gelu_t5_norm"
+
+
+def _t5_layer_norm_cls():
+    """The reference builds transformers' T5LayerNorm; subclass it when available so isinstance scans keep working."""
+    try:
+        from transformers.models.t5.modeling_t5 import T5LayerNorm  # noqa: WPS433
+
+        return T5LayerNorm
+    except Exception:  # transformers missing: a structurally identical holder (weight, variance_epsilon)
+        class T5LayerNorm(nn.Module):
+            def __init__(self, hidden_size, eps=EPS):
+                super().__init__()
+                self.weight = nn.Parameter(torch.ones(hidden_size))
+                self.variance_epsilon = eps
+
+        return T5LayerNorm
+
+
+class DataParallelState:
+    """Gradient all-reduce plan for the aligner (replaces DDP's reducer for this module, runner_base.py:88-92).
+
+    Two flat fp32 buckets in gradient-ready order -- {dW2, db2, dg} then {dW1, db1} -- are all-reduced (SUM of
+    gradients pre-scaled by 1/world = DDP's mean of per-rank means) on the process group's NCCL stream while the
+    remaining backward GEMMs run on the compute stream.
+    """
+
+    def __init__(self, group=None, overlap: bool = True):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.overlap = overlap
+
+    def all_reduce_async(self, flat):
+        return self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+
+class GradBuckets:
+    """The aligner's five gradients laid out as two flat fp32 all-reduce buckets, in gradient-ready order:
+    ``linear2 = [dW2 | db2 | dg]`` (ready after the first backward GEMM) and ``linear1 = [dW1 | db1]``.
+    The parameter gradients handed to autograd are views into the buckets."""
+
+    def __init__(self, din: int, d: int, device):
+        self.linear2 = torch.empty(d * d + 2 * d, dtype=torch.float32, device=device)
+        self.linear1 = torch.empty(d * din + d, dtype=torch.float32, device=device)
+        self.dW2, self.db2, self.dg = self.linear2[: d * d].view(d, d), self.linear2[d * d : d * d + d], self.linear2[d * d + d :]
+        self.dW1, self.db1 = self.linear1[: d * din].view(d, din), self.linear1[d * din :]
+
+    def in_parameter_order(self):
+        return self.dW1, self.db1, self.dW2, self.db2, self.dg
+
+
+class _AlignerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d, W1, b1, W2, b2, g, module, out_bf16):
+        # (grad mode is off inside Function.forward; this path is only taken when some parameter needs a gradient)
+        W1b, b1b, W2b, b2b = module._bf16_params()
+        gf = g.detach() if g.dtype == torch.float32 else g.detach().float()
+        y, (h0, h1, h2, rstd) = ops.aligner_fwd(x2d, W1b, b1b, W2b, b2b, gf, module.eps, out_bf16, True)
+        ctx.save_for_backward(x2d, h0, h1, h2, rstd, W2b, gf)
+        ctx.module = module
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, h0, h1, h2, rstd, W2b, gf = ctx.saved_tensors
+        module = ctx.module
+        M, Din = x2d.shape
+        D = W2b.shape[0]
+        dev = x2d.device
+        dp = module._dp
+        scale = 1.0 / dp.world if dp is not None else 1.0
+        if dy.dtype not in (torch.float32, torch.bfloat16):
+            dy = dy.float()
+        bwd = ops.AlignerBackward(x2d, (h0, h1, h2, rstd), W2b, gf, dy.contiguous(), grad_scale=scale)
+        gb = GradBuckets(Din, D, dev)
+        bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg)
+        works = []
+        if dp is not None and dp.world > 1 and dp.overlap:
+            works.append(dp.all_reduce_async(gb.linear2))  # rides NVLink while the next two GEMMs run
+        bwd.gelu_and_linear1(gb.dW1, gb.db1)
+        if dp is not None and dp.world > 1:
+            if not dp.overlap:
+                works.append(dp.all_reduce_async(gb.linear2))
+            works.append(dp.all_reduce_async(gb.linear1))
+            for w in works:
+                w.wait()  # stream-level wait: the compute stream orders after the NCCL stream, the host does not block
+        return (None, *gb.in_parameter_order(), None, None)
+
+
+class ThinkDiffAligner(nn.Sequential):
+    """``mlp2x_gelu_t5_norm`` aligner running on hand-written sm_100a kernels. See the module docstring."""
+
+    def __init__(self, mm_hidden_size: int, hidden_size: int, eps: float = EPS):
+        norm = _t5_layer_norm_cls()(hidden_size, eps)
+        super().__init__(nn.Linear(mm_hidden_size, hidden_size), nn.GELU(), nn.Linear(hidden_size, hidden_size), norm)
+        if mm_hidden_size % 64 or hidden_size % 64 or hidden_size > 4096:
+            raise ValueError(
+                f"ThinkDiffAligner needs mm_hidden_size ({mm_hidden_size}) and hidden_size ({hidden_size}) to be multiples of 64 "
+                "and hidden_size <= 4096 (TMA boxes / one norm row per CTA); there is no fallback path"
+            )
+        self.mm_hidden_size, self.hidden_size, self.eps = mm_hidden_size, hidden_size, eps
+        self._cache_key = None
+        self._cache = None
+        self._dp: DataParallelState | None = None
+        self.fp32_mode = "bf16x3"
+
+    # -- reference-compatible config property (IdentityMap has one; harmless here)
+    @property
+    def config(self):
+        return {"mm_projector_type": FUSED_TYPE}
+
+    # -- data parallel (replaces DDP for this module)
+    def enable_data_parallel(self, group=None, overlap: bool = True):
+        self._dp = DataParallelState(group, overlap)
+        return self
+
+    def disable_data_parallel(self):
+        self._dp = None
+        return self
+
+    def _bf16_params(self):
+        """bf16 compute copies of the Linear parameters, re-cast only when a parameter changed (optimizer step, load)."""
+        ps = (self[0].weight, self[0].bias, self[2].weight, self[2].bias)
+        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
+        if key != self._cache_key:
+            with torch.no_grad():
+                self._cache = tuple(p.detach() if p.dtype == torch.bfloat16 else ops.cast_to_bf16(p.detach().contiguous()) for p in ps)
+            self._cache_key = key
+        return self._cache
+
+    def _regime(self, x):
+        wdt = self[0].weight.dtype
+        if wdt == torch.bfloat16:
+            return "bf16_infer"
+        if wdt != torch.float32:
+            raise TypeError(f"aligner parameters must be float32 or bfloat16, got {wdt}")
+        if torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+            return "bf16_autocast"
+        if x.dtype == torch.bfloat16:
+            # reference: F.linear(bf16 x, fp32 W) raises a dtype error outside autocast
+            raise TypeError("bfloat16 features with float32 parameters need torch.autocast('cuda', dtype=torch.bfloat16)")
+        return "fp32"
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("ThinkDiffAligner runs on sm_100 CUDA devices only; there is no CPU fallback")
+        if x.shape[-1] != self.mm_hidden_size:
+            raise ValueError(f"expected last dim {self.mm_hidden_size}, got {tuple(x.shape)}")
+        if x.requires_grad:
+            raise NotImplementedError("no dx path: the reference never differentiates the aligner w.r.t. its input features")
+        regime = self._regime(x)
+        lead = x.shape[:-1]
+        x2d = x.reshape(-1, self.mm_hidden_size)
+        if regime == "fp32":
+            from .fp32_path import aligner_fp32
+
+            y = aligner_fp32(self, x2d.float().contiguous())
+            return y.reshape(*lead, self.hidden_size)
+        x2d = x2d.to(torch.bfloat16).contiguous()
+        w1, b1, w2, b2, g = self[0].weight, self[0].bias, self[2].weight, self[2].bias, self[3].weight
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in (w1, b1, w2, b2, g))
+        with torch.autocast("cuda", enabled=False):
+            if need_grad:
+                y = _AlignerFn.apply(x2d, w1, b1, w2, b2, g, self, regime == "bf16_infer")
+            else:  # inference: nothing is saved, h0 is never written
+                W1b, b1b, W2b, b2b = self._bf16_params()
+                gf = g.detach() if g.dtype == torch.float32 else g.detach().float()
+                y, _ = ops.aligner_fwd(x2d, W1b, b1b, W2b, b2b, gf, self.eps, regime == "bf16_infer", False)
+        return y.reshape(*lead, self.hidden_size)
+
+    def forward_packed(self, x_packed: torch.Tensor, cu_seqlens: torch.Tensor | None = None) -> torch.Tensor:
+        """Ragged entry point: ``x_packed[M, Din]`` (rows of all sequences back to back, ``cu_seqlens`` int32 [B+1]).
+
+        The aligner is token-wise, so the packed rows are projected directly -- pad rows are never computed, unlike the
+        reference which projects the zero-padded ``[B, L_max, Din]`` batch (...embed_decoder_2.py:585)."""
+        if x_packed.dim() != 2:
+            raise ValueError("x_packed must be [M, Din]")
+        if cu_seqlens is not None and int(cu_seqlens.numel()) < 1:
+            raise ValueError("cu_seqlens must have B+1 entries")
+        return self.forward(x_packed)
+
+
+def build_vision_projector(config):
+    """Same contract as the reference builder (...embed_decoder_2.py:41-79). ``mlp2x_gelu_t5_norm`` -- the type every
+    shipped config uses (configs/*.yaml ``mm_projector_type``) -- returns the fused B200 module; the other valid type
+    strings are recognised and rejected explicitly (no silent PyTorch fallback); unknown strings raise the reference's error."""
+    projector_type = getattr(config, "mm_projector_type", "linear")
+    if projector_type == FUSED_TYPE:
+        return ThinkDiffAligner(config.mm_hidden_size, config.hidden_size)
+    known = projector_type in ("linear", "identity") or re.match(r"^mlp(\d+)x_gelu(_t5_norm|_rms_norm|_norm)?$", projector_type)
+    if known:
+        raise NotImplementedError(
+            f"mm_projector_type={projector_type!r} has no B200 kernel path; only {FUSED_TYPE!r} (used by every shipped config) is built"
+        )
+    raise ValueError(f"Unknown projector type: {projector_type}")

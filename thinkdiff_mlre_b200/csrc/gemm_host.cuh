@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "gemm_sm100.cuh"
 
@@ -26,6 +27,29 @@ inline char* last_error_buf() {
   } while (0)
 
 enum : int { TD_OK = 0, TD_ERR_ARG = -1, TD_ERR_UNSUPPORTED = -2, TD_ERR_DRIVER = -3 };
+
+// ---- optional per-launch timing: when enabled (td_profile_enable) every kernel launch of the library is bracketed
+// by a pair of CUDA events on the launch stream; td_profile_report() sums them per tag. Off by default (zero cost).
+struct ProfRecord { const char* tag; cudaEvent_t e0, e1; double work; };
+struct Profiler {
+  bool on = false;
+  std::vector<ProfRecord> recs;
+  static Profiler& get() { static Profiler p; return p; }
+};
+struct ProfScope {
+  cudaStream_t st; int idx = -1;
+  // `work` = algorithmic FLOPs (GEMMs) or bytes (row kernels) of this launch, for the roofline report
+  ProfScope(const char* tag, double work, cudaStream_t s) : st(s) {
+    Profiler& p = Profiler::get();
+    if (!p.on) return;
+    ProfRecord r{tag, nullptr, nullptr, work};
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+    p.recs.push_back(r);
+    idx = int(p.recs.size()) - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(Profiler::get().recs[idx].e1, st); }
+};
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -75,8 +99,11 @@ inline int device_sm_count() {
   static int sms = 0;
   if (!sms) {
     int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+      cudaGetLastError();
+      return 148;  // no device visible (size queries on a build box): assume a full B200
+    }
   }
   return sms;
 }
@@ -103,7 +130,7 @@ inline int choose_splits(int num_tiles, int num_k_blocks, int workers, int max_s
 }
 
 template <int CTAS, bool A_MN, bool B_MN, int EPI>
-int launch_gemm(GemmOperand a, GemmOperand b, GemmParams p, int splits, cudaStream_t stream) {
+int launch_gemm(GemmOperand a, GemmOperand b, GemmParams p, int splits, cudaStream_t stream, const char* tag = "gemm") {
   using S = GemmSmem<CTAS>;
   if (p.M <= 0 || p.N <= 0) return TD_OK;
   if (p.N % 32) TD_FAIL(TD_ERR_UNSUPPORTED, "GEMM N=%d must be a multiple of 32", p.N);
@@ -149,6 +176,7 @@ int launch_gemm(GemmOperand a, GemmOperand b, GemmParams p, int splits, cudaStre
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  ProfScope prof(tag, 2.0 * double(p.M) * double(p.N) * double(p.K), stream);
   TD_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
   return TD_OK;
 }

@@ -140,7 +140,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
         for (int j = 0; j < 32; ++j) h[j] = bf16_round(__uint_as_float(v[j]) + b[j]);
       }
 
-      if (row_ok) {
+      if (row_ok && p.out0 != nullptr) {  // inference skips saving the pre-activation
         uint4* o0 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out0) + (long long)row * p.ld_out + col0);
 #pragma unroll
         for (int q = 0; q < 4; ++q)

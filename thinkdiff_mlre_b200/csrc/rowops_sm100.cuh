@@ -1,0 +1,537 @@
+// HBM-bound kernels of the aligner hot path: ragged pack / pad / mask, fp32->bf16 parameter casts, T5 RMSNorm
+// forward and backward, masked MSE and masked cross-entropy (forward + gradient in one pass), and the small
+// partial-sum finishers. All of them are byte movers with warp-shuffle reductions: 128-bit global accesses,
+// grids sized from the SM count, no shared-memory tiling beyond the CE row stage.
+//
+// Reference semantics:
+//   pack/pad/mask  thinkdiff/datasets/datasets/llava_instruct_dataset_mllama_embed_2.py:101-162
+//   T5LayerNorm    transformers modeling_t5.py (imported at thinkdiff/models/mllama_vllm_t5_embed_decoder_2.py:24)
+//   cross entropy  thinkdiff/models/mllama_vllm_t5_embed_decoder_2.py:241-246
+#pragma once
+#include "ptx_sm100.cuh"
+
+namespace td {
+
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------ cu_seqlens
+// Exclusive scan of B lengths into int32 cu_seqlens[B+1] (one block; B is a batch size, at most a few thousand).
+__global__ void cu_seqlens_kernel(const int* __restrict__ lens, int B, int* __restrict__ cu) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) { carry = 0; cu[0] = 0; }
+  __syncthreads();
+  for (int base = 0; base < B; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    int v = i < B ? lens[i] : 0;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int t = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      warp_tot[lane] = t;  // inclusive over warps
+    }
+    __syncthreads();
+    const int before = carry + (w ? warp_tot[w - 1] : 0);
+    if (i < B) cu[i + 1] = before + x;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += warp_tot[(blockDim.x >> 5) - 1];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ pack / pad / mask
+// One warp moves one destination row per iteration with 128-bit accesses, 8 loads in flight per lane.
+//   PADDED = false: dst row r of the packed buffer [M, row] <- sample i = upper_bound(cu, r) - 1, row j = r - cu[i]
+//   PADDED = true : dst row r of [B, Lmax, row] <- sample i = r / Lmax, row j = r % Lmax if j < len_i else zeros;
+//                   mask[r] = (j < len_i) as int64 (reference mask dtype, ...embed_2.py:118,128)
+// Source row = src_row_start[i] + j in the flat source (the un-truncated per-sample embeddings back to back).
+template <bool PADDED>
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const uint4* __restrict__ src, const long long* __restrict__ src_row_start,
+                 const int* __restrict__ cu, int B, long long dst_rows, int Lmax, int vec_per_row,
+                 uint4* __restrict__ dst, long long* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = warp0; r < dst_rows; r += nwarps) {
+    int i, j;
+    bool valid = true;
+    if constexpr (PADDED) {
+      i = int(r / Lmax);
+      j = int(r - (long long)i * Lmax);
+      valid = j < (cu[i + 1] - cu[i]);
+      if (mask != nullptr && lane == 0) mask[r] = valid ? 1ll : 0ll;
+    } else {
+      int lo = 0, hi = B;  // largest i with cu[i] <= r
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((long long)__ldg(cu + mid) <= r) lo = mid; else hi = mid;
+      }
+      i = lo;
+      j = int(r - (long long)__ldg(cu + i));
+    }
+    uint4* d = dst + r * vec_per_row;
+    if (valid) {
+      const uint4* s = src + (__ldg(src_row_start + i) + j) * vec_per_row;
+      for (int v0 = 0; v0 < vec_per_row; v0 += 256) {
+        uint4 t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int v = v0 + u * 32 + lane;
+          if (v < vec_per_row) t[u] = ld_stream(s + v);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int v = v0 + u * 32 + lane;
+          if (v < vec_per_row) st_stream(d + v, t[u]);
+        }
+      }
+    } else {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      for (int v = lane; v < vec_per_row; v += 32) st_stream(d + v, z);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ casts
+__global__ void __launch_bounds__(256)
+cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long n8 = n >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    reinterpret_cast<uint4*>(dst)[i] =
+        make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+  }
+  for (long long i = (n8 << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// ------------------------------------------------------------------------------------------ T5 RMSNorm forward
+// One warp per row. h2 is the bf16 output of Linear2; the variance is taken in fp32 over the bf16 values
+// (either summed here, or from the per-N-tile partials the GEMM2 epilogue wrote: ssq_part[P][M]).
+//   OUT_BF16 = false: y = g * (h2 * rstd) in fp32            (training: fp32 norm weight)
+//   OUT_BF16 = true : y = bf16(g) * bf16(h2 * rstd) -> bf16  (pure-bf16 inference, rounding before the multiply)
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(256)
+rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restrict__ ssq_part, int P,
+                   const float* __restrict__ g, float eps, int M, int D, void* __restrict__ y_out,
+                   float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const int warp0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int nvec = D >> 3;  // uint4 of 8 bf16
+  for (int row = warp0; row < M; row += nwarps) {
+    const uint4* hp = reinterpret_cast<const uint4*>(h2 + (long long)row * D);
+    float ssq = 0.f;
+    if (P > 0) {
+      for (int p = lane; p < P; p += 32) ssq += ssq_part[(long long)p * M + row];
+    } else {
+      for (int v = lane; v < nvec; v += 32) {
+        const uint4 u = __ldg(hp + v);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float a = bf16lo(w[q]), b = bf16hi(w[q]);
+          ssq = fmaf(a, a, ssq);
+          ssq = fmaf(b, b, ssq);
+        }
+      }
+    }
+    ssq = warp_sum(ssq);
+    const float rstd = rsqrtf(ssq / float(D) + eps);
+    if (lane == 0 && rstd_out != nullptr) rstd_out[row] = rstd;
+    for (int v = lane; v < nvec; v += 32) {
+      const uint4 u = ld_stream(hp + v);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + 2 * v);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(g) + 2 * v + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float o[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        o[2 * q] = bf16lo(w[q]) * rstd;
+        o[2 * q + 1] = bf16hi(w[q]) * rstd;
+      }
+      if constexpr (OUT_BF16) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = bf16_round(gg[q]) * bf16_round(o[q]);
+        st_stream(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y_out) + (long long)row * D) + v,
+                  make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                             pack_bf16x2(o[6], o[7])));
+      } else {
+        uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<float*>(y_out) + (long long)row * D) + 2 * v;
+        st_stream(yp, make_uint4(__float_as_uint(gg[0] * o[0]), __float_as_uint(gg[1] * o[1]),
+                                 __float_as_uint(gg[2] * o[2]), __float_as_uint(gg[3] * o[3])));
+        st_stream(yp + 1, make_uint4(__float_as_uint(gg[4] * o[4]), __float_as_uint(gg[5] * o[5]),
+                                     __float_as_uint(gg[6] * o[6]), __float_as_uint(gg[7] * o[7])));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ T5 RMSNorm backward
+// Thread t of a 512-thread CTA owns columns [8t, 8t+8); the CTA walks its slab of rows R at a time:
+//   ghat = g * dy;  s_r = sum_D(ghat * h2)   (block reduction, R rows at once)
+//   dh2  = bf16( rstd * ghat - h2 * rstd^3 * s_r / D )
+//   dg_part[cta][col] += dy * h2 * rstd;  db2_part[cta][col] += dh2
+// Column sums stay in registers and are written once per CTA (deterministic two-level reduction).
+constexpr int kNormBwdThreads = 512;
+constexpr int kNormBwdRows = 4;
+
+template <bool DY_BF16>
+__global__ void __launch_bounds__(kNormBwdThreads)
+rmsnorm_bwd_kernel(const void* __restrict__ dy_in, const __nv_bfloat16* __restrict__ h2,
+                   const float* __restrict__ rstd_in, const float* __restrict__ g, int M, int D, int rows_per_cta,
+                   __nv_bfloat16* __restrict__ dh2, float* __restrict__ dg_part, float* __restrict__ db2_part) {
+  constexpr int R = kNormBwdRows;
+  __shared__ float red[R][kNormBwdThreads / 32];
+  __shared__ float tot[R];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const bool col_ok = t * 8 < D;
+  const int row_begin = blockIdx.x * rows_per_cta;
+  const int row_end = min(M, row_begin + rows_per_cta);
+  float gg[8], adg[8], adb[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { gg[q] = col_ok ? g[t * 8 + q] : 0.f; adg[q] = 0.f; adb[q] = 0.f; }
+  const float inv_d = 1.0f / float(D);
+
+  for (int r0 = row_begin; r0 < row_end; r0 += R) {
+    float dyv[R][8], hv[R][8], part[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = r0 + r;
+      const bool ok = col_ok && row < row_end;
+      uint4 hu = make_uint4(0, 0, 0, 0);
+      if (ok) hu = ld_stream(reinterpret_cast<const uint4*>(h2 + (long long)row * D) + t);
+      const uint32_t hw[4] = {hu.x, hu.y, hu.z, hu.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { hv[r][2 * q] = bf16lo(hw[q]); hv[r][2 * q + 1] = bf16hi(hw[q]); }
+      if constexpr (DY_BF16) {
+        uint4 du = make_uint4(0, 0, 0, 0);
+        if (ok) du = ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(dy_in) + (long long)row * D) + t);
+        const uint32_t dw[4] = {du.x, du.y, du.z, du.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { dyv[r][2 * q] = bf16lo(dw[q]); dyv[r][2 * q + 1] = bf16hi(dw[q]); }
+      } else {
+        uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+        if (ok) {
+          const uint4* dp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(dy_in) + (long long)row * D) + 2 * t;
+          d0 = ld_stream(dp);
+          d1 = ld_stream(dp + 1);
+        }
+        dyv[r][0] = __uint_as_float(d0.x); dyv[r][1] = __uint_as_float(d0.y);
+        dyv[r][2] = __uint_as_float(d0.z); dyv[r][3] = __uint_as_float(d0.w);
+        dyv[r][4] = __uint_as_float(d1.x); dyv[r][5] = __uint_as_float(d1.y);
+        dyv[r][6] = __uint_as_float(d1.z); dyv[r][7] = __uint_as_float(d1.w);
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s = fmaf(gg[q] * dyv[r][q], hv[r][q], s);
+      part[r] = warp_sum(s);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) red[r][w] = part[r];
+    }
+    __syncthreads();
+    if (w < R) {
+      float v = lane < kNormBwdThreads / 32 ? red[w][lane] : 0.f;
+      v = warp_sum(v);
+      if (lane == 0) tot[w] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = r0 + r;
+      if (row < row_end && col_ok) {
+        const float rstd = __ldg(rstd_in + row);
+        const float c = tot[r] * inv_d * rstd * rstd * rstd;
+        float o[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          o[q] = bf16_round(rstd * gg[q] * dyv[r][q] - hv[r][q] * c);
+          adb[q] += o[q];
+          adg[q] = fmaf(dyv[r][q] * hv[r][q], rstd, adg[q]);
+        }
+        st_stream(reinterpret_cast<uint4*>(dh2 + (long long)row * D) + t,
+                  make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                             pack_bf16x2(o[6], o[7])));
+      }
+    }
+    // `tot`/`red` are rewritten only after the next iteration's first __syncthreads(), which every thread
+    // reaches after finishing its reads above.
+  }
+  if (col_ok) {
+    float4* pg = reinterpret_cast<float4*>(dg_part + (long long)blockIdx.x * D) + 2 * t;
+    float4* pb = reinterpret_cast<float4*>(db2_part + (long long)blockIdx.x * D) + 2 * t;
+    pg[0] = make_float4(adg[0], adg[1], adg[2], adg[3]);
+    pg[1] = make_float4(adg[4], adg[5], adg[6], adg[7]);
+    pb[0] = make_float4(adb[0], adb[1], adb[2], adb[3]);
+    pb[1] = make_float4(adb[4], adb[5], adb[6], adb[7]);
+  }
+}
+
+// out[n] = scale * sum_p part[p][n]   (fixed order -> deterministic)
+__global__ void __launch_bounds__(256)
+colsum_finish_kernel(const float* __restrict__ part, int P, int N, float scale, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int p = 0; p < P; ++p) acc += part[(long long)p * N + n];
+  out[n] = scale * acc;
+}
+
+// ------------------------------------------------------------------------------------------ masked MSE
+// loss = sum_valid (y - t)^2 / (n_valid * D);  dy = 2 (y - t) * grad_scale / (n_valid * D) on valid rows, else 0.
+// meta[0] = n_valid (float, written by count_valid_kernel or the host), partial sums -> loss_part[grid].
+__global__ void count_valid_kernel(const long long* __restrict__ mask, long long n, int ignore_mode,
+                                   float* __restrict__ meta) {
+  // ignore_mode 0: mask != 0 is valid (attention-mask convention); 1: label != -100 is valid (CE convention)
+  __shared__ int wsum[32];
+  if (mask == nullptr) {  // no mask: every row counts
+    if (threadIdx.x == 0) meta[0] = float(n);
+    return;
+  }
+  int c = 0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const long long v = mask[i];
+    c += ignore_mode ? (v != -100) : (v != 0);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) tot += wsum[i];
+    meta[0] = float(tot);
+  }
+}
+
+template <bool Y_BF16, bool T_BF16>
+__global__ void __launch_bounds__(256)
+masked_mse_kernel(const void* __restrict__ y_in, const void* __restrict__ t_in, const long long* __restrict__ mask,
+                  int M, int D, const float* __restrict__ meta, float grad_scale, void* __restrict__ dy_out,
+                  float* __restrict__ loss_part) {
+  __shared__ float wsum[8];
+  const int lane = threadIdx.x & 31;
+  const int warp0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int nvec = D >> 3;
+  const float n_valid = meta[0];
+  const float gs = 2.0f * grad_scale / (n_valid * float(D));
+  float acc = 0.f;
+  for (int row = warp0; row < M; row += nwarps) {
+    const bool valid = mask == nullptr || __ldg(mask + row) != 0;
+    for (int v = lane; v < nvec; v += 32) {
+      float yv[8], tv[8];
+      if (valid) {
+        if constexpr (Y_BF16) {
+          const uint4 u = ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(y_in) + (long long)row * D) + v);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { yv[2 * q] = bf16lo(w[q]); yv[2 * q + 1] = bf16hi(w[q]); }
+        } else {
+          const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(y_in) + (long long)row * D) + 2 * v;
+          const uint4 a = ld_stream(p), b = ld_stream(p + 1);
+          yv[0] = __uint_as_float(a.x); yv[1] = __uint_as_float(a.y); yv[2] = __uint_as_float(a.z); yv[3] = __uint_as_float(a.w);
+          yv[4] = __uint_as_float(b.x); yv[5] = __uint_as_float(b.y); yv[6] = __uint_as_float(b.z); yv[7] = __uint_as_float(b.w);
+        }
+        if constexpr (T_BF16) {
+          const uint4 u = ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(t_in) + (long long)row * D) + v);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { tv[2 * q] = bf16lo(w[q]); tv[2 * q + 1] = bf16hi(w[q]); }
+        } else {
+          const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(t_in) + (long long)row * D) + 2 * v;
+          const uint4 a = ld_stream(p), b = ld_stream(p + 1);
+          tv[0] = __uint_as_float(a.x); tv[1] = __uint_as_float(a.y); tv[2] = __uint_as_float(a.z); tv[3] = __uint_as_float(a.w);
+          tv[4] = __uint_as_float(b.x); tv[5] = __uint_as_float(b.y); tv[6] = __uint_as_float(b.z); tv[7] = __uint_as_float(b.w);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { yv[q] = 0.f; tv[q] = 0.f; }
+      }
+      float d[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { d[q] = yv[q] - tv[q]; acc = fmaf(d[q], d[q], acc); d[q] = valid ? d[q] * gs : 0.f; }
+      if (dy_out != nullptr) {
+        if constexpr (Y_BF16) {
+          st_stream(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dy_out) + (long long)row * D) + v,
+                    make_uint4(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7])));
+        } else {
+          uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<float*>(dy_out) + (long long)row * D) + 2 * v;
+          st_stream(p, make_uint4(__float_as_uint(d[0]), __float_as_uint(d[1]), __float_as_uint(d[2]), __float_as_uint(d[3])));
+          st_stream(p + 1, make_uint4(__float_as_uint(d[4]), __float_as_uint(d[5]), __float_as_uint(d[6]), __float_as_uint(d[7])));
+        }
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) tot += wsum[i];
+    loss_part[blockIdx.x] = tot;
+  }
+}
+
+// loss = sum(part[0..P)) * (use_nd ? 1 / (n_valid * D) : 1 / n_valid); NaN when n_valid == 0 (as torch)
+__global__ void loss_finish_kernel(const float* __restrict__ part, int P, const float* __restrict__ meta, float d_or_1,
+                                   float* __restrict__ loss) {
+  __shared__ float wsum[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) acc += part[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) tot += wsum[i];
+    loss[0] = tot / (meta[0] * d_or_1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ masked cross-entropy
+// One CTA per logits row; the row (V values) is staged once in shared memory as fp32, so HBM sees one read of the
+// logits and one write of dlogits: loss_row = logsumexp(z) - z[label]; dz = (softmax(z) - onehot) * grad_scale / n_valid.
+// Rows with label == -100 write zeros (ignore_index, ...embed_decoder_2.py:243) and contribute nothing.
+constexpr int kCeThreads = 512;
+
+template <bool Z_BF16>
+__global__ void __launch_bounds__(kCeThreads)
+masked_ce_kernel(const void* __restrict__ z_in, const long long* __restrict__ labels, int V, const float* __restrict__ meta,
+                 float grad_scale, void* __restrict__ dz_out, float* __restrict__ row_loss) {
+  extern __shared__ float zs[];  // V floats
+  __shared__ float red[kCeThreads / 32];
+  __shared__ float bcast;
+  const int row = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const long long label = labels[row];
+  const bool valid = label != -100;
+  const int nvec = V >> 3;  // V % 8 == 0 enforced on the host
+  if (!valid) {
+    if (dz_out != nullptr) {
+      const uint4 z4 = make_uint4(0, 0, 0, 0);
+      if constexpr (Z_BF16) {
+        uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dz_out) + (long long)row * V);
+        for (int v = t; v < nvec; v += kCeThreads) st_stream(d + v, z4);
+      } else {
+        uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<float*>(dz_out) + (long long)row * V);
+        for (int v = t; v < 2 * nvec; v += kCeThreads) st_stream(d + v, z4);
+      }
+    }
+    if (t == 0) row_loss[row] = 0.f;
+    return;
+  }
+  // pass 1: stage + max
+  float mx = -INFINITY;
+  for (int v = t; v < nvec; v += kCeThreads) {
+    float x[8];
+    if constexpr (Z_BF16) {
+      const uint4 u = ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(z_in) + (long long)row * V) + v);
+      const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { x[2 * q] = bf16lo(ww[q]); x[2 * q + 1] = bf16hi(ww[q]); }
+    } else {
+      const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(z_in) + (long long)row * V) + 2 * v;
+      const uint4 a = ld_stream(p), b = ld_stream(p + 1);
+      x[0] = __uint_as_float(a.x); x[1] = __uint_as_float(a.y); x[2] = __uint_as_float(a.z); x[3] = __uint_as_float(a.w);
+      x[4] = __uint_as_float(b.x); x[5] = __uint_as_float(b.y); x[6] = __uint_as_float(b.z); x[7] = __uint_as_float(b.w);
+    }
+    float4* s = reinterpret_cast<float4*>(zs) + 2 * v;
+    s[0] = make_float4(x[0], x[1], x[2], x[3]);
+    s[1] = make_float4(x[4], x[5], x[6], x[7]);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mx = fmaxf(mx, x[q]);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[w] = mx;
+  __syncthreads();
+  if (w == 0) {
+    float v = lane < kCeThreads / 32 ? red[lane] : -INFINITY;
+    v = warp_max(v);
+    if (lane == 0) bcast = v;
+  }
+  __syncthreads();
+  mx = bcast;
+  // pass 2: sum of exp (from smem)
+  float sum = 0.f;
+  for (int v = t; v < 2 * nvec; v += kCeThreads) {
+    const float4 x = reinterpret_cast<const float4*>(zs)[v];
+    sum += __expf(x.x - mx) + __expf(x.y - mx) + __expf(x.z - mx) + __expf(x.w - mx);
+  }
+  sum = warp_sum(sum);
+  __syncthreads();  // everyone has read bcast
+  if (lane == 0) red[w] = sum;
+  __syncthreads();
+  if (w == 0) {
+    float v = lane < kCeThreads / 32 ? red[lane] : 0.f;
+    v = warp_sum(v);
+    if (lane == 0) bcast = v;
+  }
+  __syncthreads();
+  sum = bcast;
+  if (t == 0) row_loss[row] = (label >= 0 && label < V) ? (logf(sum) + mx) - zs[label] : __int_as_float(0x7fc00000);
+  if (dz_out == nullptr) return;
+  // pass 3: gradient
+  const float inv_sum = 1.0f / sum;
+  const float gs = grad_scale / meta[0];
+  for (int v = t; v < nvec; v += kCeThreads) {
+    const float4 a = reinterpret_cast<const float4*>(zs)[2 * v], b = reinterpret_cast<const float4*>(zs)[2 * v + 1];
+    float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const int c0 = v * 8;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float p = __expf(x[q] - mx) * inv_sum;
+      if (c0 + q == label) p -= 1.0f;
+      x[q] = p * gs;
+    }
+    if constexpr (Z_BF16) {
+      st_stream(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dz_out) + (long long)row * V) + v,
+                make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7])));
+    } else {
+      uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<float*>(dz_out) + (long long)row * V) + 2 * v;
+      st_stream(p, make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3])));
+      st_stream(p + 1, make_uint4(__float_as_uint(x[4]), __float_as_uint(x[5]), __float_as_uint(x[6]), __float_as_uint(x[7])));
+    }
+  }
+}
+
+}  // namespace td

@@ -1,0 +1,470 @@
+// C ABI of libthinkdiff_b200.so (declared in include/thinkdiff_b200.h): argument checking, workspace carving and
+// kernel launches for the ThinkDiff aligner hot path on sm_100a. No torch types, no global mutable state beyond
+// cached device attributes; every launch goes to the caller's stream.
+#include "thinkdiff_b200.h"
+
+#include "gemm_host.cuh"
+#include "rowops_sm100.cuh"
+
+using namespace td;
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<uint8_t*>(p)) {}
+  template <class T>
+  T* take(size_t n) {
+    T* r = reinterpret_cast<T*>(base + off);
+    off = align_up(off + n * sizeof(T), 256);
+    return r;
+  }
+};
+
+int check_device() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+      TD_FAIL(TD_ERR_UNSUPPORTED, "no usable CUDA device");
+    ok = (major == 10) ? 1 : 0;
+  }
+  if (!ok) TD_FAIL(TD_ERR_UNSUPPORTED, "libthinkdiff_b200 needs an sm_100 (B200) device; there is no fallback path");
+  return TD_OK;
+}
+#define TD_DEVICE_OR_RETURN()      \
+  do {                             \
+    int _rc = check_device();      \
+    if (_rc) return _rc;           \
+  } while (0)
+
+inline int grid_for_rows(long long rows, int rows_per_block, int blocks_per_sm) {
+  const long long want = (rows + rows_per_block - 1) / rows_per_block;
+  const long long cap = (long long)device_sm_count() * blocks_per_sm;
+  return int(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+inline int norm_bwd_grid(long long M, int* rows_per_cta) {
+  // one slab of rows per CTA, a multiple of the R rows it walks at a time
+  int ctas = device_sm_count() * 2;
+  long long rpc = (M + ctas - 1) / ctas;
+  rpc = (rpc + kNormBwdRows - 1) / kNormBwdRows * kNormBwdRows;
+  if (rpc < kNormBwdRows) rpc = kNormBwdRows;
+  *rows_per_cta = int(rpc);
+  return int((M + rpc - 1) / rpc);
+}
+
+inline bool dims_ok(int Din, int D) { return Din > 0 && D > 0 && Din % 64 == 0 && D % 64 == 0 && D <= 8 * kNormBwdThreads; }
+
+}  // namespace
+
+extern "C" {
+
+const char* td_last_error(void) { return last_error_buf(); }
+int32_t td_version(void) { return 100; }
+int32_t td_device_check(void) { return check_device(); }
+
+// ------------------------------------------------------------------------------------------------ profiling
+int32_t td_profile_enable(int32_t on) {
+  Profiler& p = Profiler::get();
+  for (auto& r : p.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  p.recs.clear();
+  p.on = on != 0;
+  return TD_OK;
+}
+
+// Writes "tag,launches,total_ms,total_work\n" lines (work = FLOPs for gemm_* tags, algorithmic bytes otherwise).
+int32_t td_profile_report(char* buf, int32_t buflen) {
+  Profiler& p = Profiler::get();
+  struct Agg { const char* tag; int n; double ms, work; };
+  std::vector<Agg> agg;
+  for (auto& r : p.recs) {
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) TD_FAIL(TD_ERR_DRIVER, "td_profile_report: event sync failed");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    size_t i = 0;
+    for (; i < agg.size(); ++i) if (!strcmp(agg[i].tag, r.tag)) break;
+    if (i == agg.size()) agg.push_back({r.tag, 0, 0.0, 0.0});
+    agg[i].n++; agg[i].ms += ms; agg[i].work += r.work;
+  }
+  int off = 0;
+  for (auto& a : agg) {
+    int w = snprintf(buf + off, buflen > off ? buflen - off : 0, "%s,%d,%.6f,%.6e\n", a.tag, a.n, a.ms, a.work);
+    if (w < 0 || off + w >= buflen) TD_FAIL(TD_ERR_ARG, "td_profile_report: buffer too small");
+    off += w;
+  }
+  if (buflen > 0) buf[off < buflen ? off : buflen - 1] = 0;
+  return TD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ pack
+int32_t td_cu_seqlens(const int32_t* lens, int32_t B, int32_t* cu, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (B < 0 || !cu || (B > 0 && !lens)) TD_FAIL(TD_ERR_ARG, "td_cu_seqlens: bad arguments");
+  cu_seqlens_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lens, B, cu);
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+int32_t td_pack_varlen(const void* src, const int64_t* src_row_start, const int32_t* cu, int32_t B, int64_t total_rows,
+                       int64_t row_bytes, void* dst, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (B < 0 || total_rows < 0 || row_bytes <= 0 || row_bytes % 16)
+    TD_FAIL(TD_ERR_ARG, "td_pack_varlen: row_bytes=%lld must be a positive multiple of 16", (long long)row_bytes);
+  if (total_rows == 0 || B == 0) return TD_OK;
+  if (!src || !src_row_start || !cu || !dst) TD_FAIL(TD_ERR_ARG, "td_pack_varlen: null pointer");
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15)
+    TD_FAIL(TD_ERR_ARG, "td_pack_varlen: buffers must be 16-byte aligned");
+  const int grid = grid_for_rows(total_rows, 8, 8);
+  {
+    ProfScope prof("pack_varlen", 2.0 * double(total_rows) * double(row_bytes), (cudaStream_t)stream);
+    pack_rows_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint4*>(src), reinterpret_cast<const long long*>(src_row_start), cu, B, total_rows, 0,
+        int(row_bytes / 16), static_cast<uint4*>(dst), nullptr);
+  }
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+int32_t td_pack_padded(const void* src, const int64_t* src_row_start, const int32_t* cu, int32_t B, int32_t L_max,
+                       int64_t row_bytes, void* dst, int64_t* mask, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (B < 0 || L_max < 0 || row_bytes <= 0 || row_bytes % 16)
+    TD_FAIL(TD_ERR_ARG, "td_pack_padded: row_bytes=%lld must be a positive multiple of 16", (long long)row_bytes);
+  if (B == 0 || L_max == 0) return TD_OK;
+  if (!src_row_start || !cu || !dst) TD_FAIL(TD_ERR_ARG, "td_pack_padded: null pointer");
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15)
+    TD_FAIL(TD_ERR_ARG, "td_pack_padded: buffers must be 16-byte aligned");
+  const long long rows = (long long)B * L_max;
+  const int grid = grid_for_rows(rows, 8, 8);
+  {
+    ProfScope prof("pack_padded", 2.0 * double(rows) * double(row_bytes), (cudaStream_t)stream);
+    pack_rows_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint4*>(src), reinterpret_cast<const long long*>(src_row_start), cu, B, rows, L_max,
+        int(row_bytes / 16), static_cast<uint4*>(dst), reinterpret_cast<long long*>(mask));
+  }
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ casts
+int32_t td_cast_f32_to_bf16(const float* src, void* dst, int64_t n, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (n < 0) TD_FAIL(TD_ERR_ARG, "td_cast_f32_to_bf16: n < 0");
+  if (n == 0) return TD_OK;
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15)
+    TD_FAIL(TD_ERR_ARG, "td_cast_f32_to_bf16: buffers must be 16-byte aligned");
+  const int grid = grid_for_rows((n + 7) / 8, 256, 8);
+  {
+    ProfScope prof("cast_f32_to_bf16", 6.0 * double(n), (cudaStream_t)stream);
+    cast_f32_to_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+  }
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ norm
+int32_t td_rmsnorm_fwd(const void* x, const float* g, float eps, int64_t M, int32_t D, void* y, int32_t y_dtype,
+                       float* rstd, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (M < 0 || D <= 0 || D % 8) TD_FAIL(TD_ERR_ARG, "td_rmsnorm_fwd: D=%d must be a positive multiple of 8", D);
+  if (M == 0) return TD_OK;
+  const int grid = grid_for_rows(M, 8, 8);
+  if (y_dtype == TD_DTYPE_BF16)
+    rmsnorm_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(x), nullptr, 0, g,
+                                                                    eps, int(M), D, y, rstd);
+  else
+    rmsnorm_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(x), nullptr, 0,
+                                                                     g, eps, int(M), D, y, rstd);
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+int64_t td_rmsnorm_bwd_workspace_bytes(int64_t M, int32_t D) {
+  int rpc;
+  const int grid = norm_bwd_grid(M > 0 ? M : 1, &rpc);
+  return (int64_t)(2 * align_up(sizeof(float) * (size_t)grid * D, 256));
+}
+
+static int rmsnorm_bwd_impl(const void* dy, int32_t dy_dtype, const __nv_bfloat16* x, const float* rstd, const float* g,
+                            int64_t M, int32_t D, __nv_bfloat16* dx, float* dg, float* dxsum, float scale, void* ws,
+                            cudaStream_t st) {
+  int rpc;
+  const int grid = norm_bwd_grid(M, &rpc);
+  Carver c(ws);
+  float* dg_part = c.take<float>((size_t)grid * D);
+  float* db_part = c.take<float>((size_t)grid * D);
+  {
+  ProfScope prof("rmsnorm_bwd", double(M) * D * (dy_dtype == TD_DTYPE_BF16 ? 6.0 : 8.0), st);
+  if (dy_dtype == TD_DTYPE_BF16)
+    rmsnorm_bwd_kernel<true><<<grid, kNormBwdThreads, 0, st>>>(dy, x, rstd, g, int(M), D, rpc, dx, dg_part, db_part);
+  else
+    rmsnorm_bwd_kernel<false><<<grid, kNormBwdThreads, 0, st>>>(dy, x, rstd, g, int(M), D, rpc, dx, dg_part, db_part);
+  }
+  TD_CUDA(cudaGetLastError());
+  if (dg) colsum_finish_kernel<<<(D + 255) / 256, 256, 0, st>>>(dg_part, grid, D, scale, dg);
+  if (dxsum) colsum_finish_kernel<<<(D + 255) / 256, 256, 0, st>>>(db_part, grid, D, scale, dxsum);
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+int32_t td_rmsnorm_bwd(const void* dy, int32_t dy_dtype, const void* x, const float* rstd, const float* g, int64_t M,
+                       int32_t D, void* dx, float* dg, float* dxsum, void* ws, int64_t ws_bytes, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (M < 0 || D <= 0 || D % 8 || D > 8 * kNormBwdThreads)
+    TD_FAIL(TD_ERR_UNSUPPORTED, "td_rmsnorm_bwd: D=%d must be a multiple of 8 and <= %d", D, 8 * kNormBwdThreads);
+  if (M == 0) {
+    if (dg) TD_CUDA(cudaMemsetAsync(dg, 0, sizeof(float) * D, (cudaStream_t)stream));
+    if (dxsum) TD_CUDA(cudaMemsetAsync(dxsum, 0, sizeof(float) * D, (cudaStream_t)stream));
+    return TD_OK;
+  }
+  if (ws_bytes < td_rmsnorm_bwd_workspace_bytes(M, D)) TD_FAIL(TD_ERR_ARG, "td_rmsnorm_bwd: workspace too small");
+  return rmsnorm_bwd_impl(dy, dy_dtype, static_cast<const __nv_bfloat16*>(x), rstd, g, M, D,
+                          static_cast<__nv_bfloat16*>(dx), dg, dxsum, 1.0f, ws, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM entries
+int32_t td_linear_bf16(const void* x, int64_t M, int32_t K, const void* W, int32_t N, const void* bias, void* out,
+                       td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (M < 0 || K <= 0 || N <= 0 || K % 8 || N % 32) TD_FAIL(TD_ERR_UNSUPPORTED, "td_linear_bf16: need K %% 8 == 0, N %% 32 == 0");
+  if (M == 0) return TD_OK;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = int(M); p.N = N; p.K = K;
+  p.out0 = out; p.ld_out = N; p.bias = static_cast<const __nv_bfloat16*>(bias); p.alpha = 1.f;
+  return launch_gemm<2, false, false, EPI_BF16>({x, K, false}, {W, K, false}, p, 1, (cudaStream_t)stream);
+}
+
+int32_t td_gemm_bf16_f32out(const void* A, int64_t lda, int32_t a_mn, const void* B, int64_t ldb, int32_t b_mn, int64_t M,
+                            int32_t N, int64_t K, float alpha, float* out, int32_t cta_pair, int32_t splits,
+                            td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (M <= 0 || N <= 0 || K <= 0) TD_FAIL(TD_ERR_ARG, "td_gemm_bf16_f32out: empty problem");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = int(M); p.N = N; p.K = int(K);
+  p.out0 = out; p.ld_out = N; p.alpha = alpha;
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmOperand a{A, lda, a_mn != 0}, b{B, ldb, b_mn != 0};
+  const int sel = (cta_pair ? 4 : 0) | (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
+  switch (sel) {
+    case 0: return launch_gemm<1, false, false, EPI_F32>(a, b, p, splits, st);
+    case 1: return launch_gemm<1, false, true, EPI_F32>(a, b, p, splits, st);
+    case 2: return launch_gemm<1, true, false, EPI_F32>(a, b, p, splits, st);
+    case 3: return launch_gemm<1, true, true, EPI_F32>(a, b, p, splits, st);
+    case 4: return launch_gemm<2, false, false, EPI_F32>(a, b, p, splits, st);
+    case 5: return launch_gemm<2, false, true, EPI_F32>(a, b, p, splits, st);
+    case 6: return launch_gemm<2, true, false, EPI_F32>(a, b, p, splits, st);
+    default: return launch_gemm<2, true, true, EPI_F32>(a, b, p, splits, st);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ aligner forward
+int64_t td_aligner_fwd_workspace_bytes(int64_t M, int32_t Din, int32_t D) {
+  (void)Din;
+  const size_t nblk = (size_t)(D + kBlockN - 1) / kBlockN;
+  return (int64_t)align_up(sizeof(float) * nblk * (size_t)(M > 0 ? M : 1), 256);
+}
+
+int32_t td_aligner_fwd(const void* x, int64_t M, int32_t Din, int32_t D, const void* W1, const void* b1, const void* W2,
+                       const void* b2, const float* g, float eps, void* h0, void* h1, void* h2, float* rstd, void* y,
+                       int32_t y_dtype, void* ws, int64_t ws_bytes, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (!dims_ok(Din, D)) TD_FAIL(TD_ERR_UNSUPPORTED, "td_aligner_fwd: Din=%d, D=%d must be multiples of 64 (D <= 4096)", Din, D);
+  if (M < 0 || M > 0x7fffffffll / D) TD_FAIL(TD_ERR_ARG, "td_aligner_fwd: M=%lld out of range", (long long)M);
+  if (M == 0) return TD_OK;
+  if (!x || !W1 || !W2 || !g || !h1 || !h2 || !y) TD_FAIL(TD_ERR_ARG, "td_aligner_fwd: null pointer");
+  if (ws_bytes < td_aligner_fwd_workspace_bytes(M, Din, D)) TD_FAIL(TD_ERR_ARG, "td_aligner_fwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ssq_part = static_cast<float*>(ws);
+  const int nblk = (D + kBlockN - 1) / kBlockN;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = int(M); p.N = D; p.K = Din; p.ld_out = D; p.alpha = 1.f;
+  p.out0 = h0; p.out1 = h1; p.bias = static_cast<const __nv_bfloat16*>(b1);
+  int rc = launch_gemm<2, false, false, EPI_BIAS_GELU>({x, Din, false}, {W1, Din, false}, p, 1, st, "gemm_fwd1_bias_gelu");
+  if (rc) return rc;
+
+  memset(&p, 0, sizeof(p));
+  p.M = int(M); p.N = D; p.K = D; p.ld_out = D; p.alpha = 1.f;
+  p.out0 = h2; p.bias = static_cast<const __nv_bfloat16*>(b2); p.red0 = ssq_part;
+  rc = launch_gemm<2, false, false, EPI_BIAS_SSQ>({h1, D, false}, {W2, D, false}, p, 1, st, "gemm_fwd2_bias_ssq");
+  if (rc) return rc;
+
+  const int grid = grid_for_rows(M, 8, 8);
+  ProfScope prof("rmsnorm_fwd", double(M) * D * (y_dtype == TD_DTYPE_BF16 ? 4.0 : 6.0), st);
+  if (y_dtype == TD_DTYPE_BF16)
+    rmsnorm_fwd_kernel<true><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(h2), ssq_part, nblk, g, eps, int(M),
+                                                   D, y, rstd);
+  else
+    rmsnorm_fwd_kernel<false><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(h2), ssq_part, nblk, g, eps, int(M),
+                                                    D, y, rstd);
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ aligner backward
+namespace {
+struct BwdWorkspace {
+  __nv_bfloat16* dh2;
+  __nv_bfloat16* dh0;
+  void* norm_ws;
+  float* db1_part;
+  int db1_rows;
+  size_t bytes;
+};
+BwdWorkspace carve_bwd(void* ws, int64_t M, int32_t D) {
+  Carver c(ws);
+  BwdWorkspace w;
+  const size_t m = (size_t)(M > 0 ? M : 1);
+  w.dh2 = c.take<__nv_bfloat16>(m * D);
+  w.dh0 = c.take<__nv_bfloat16>(m * D);
+  w.norm_ws = c.take<uint8_t>((size_t)td_rmsnorm_bwd_workspace_bytes((int64_t)m, D));
+  w.db1_rows = int((m + kBlockM - 1) / kBlockM + 1) * 4;  // one partial row per 32-row warp slab (+1 pair padding)
+  w.db1_part = c.take<float>((size_t)w.db1_rows * D);
+  w.bytes = c.off;
+  return w;
+}
+}  // namespace
+
+int64_t td_aligner_bwd_workspace_bytes(int64_t M, int32_t Din, int32_t D) {
+  (void)Din;
+  return (int64_t)carve_bwd(nullptr, M, D).bytes;
+}
+
+int32_t td_aligner_bwd(const void* dy, int32_t dy_dtype, const void* x, const void* h0, const void* h1, const void* h2,
+                       const float* rstd, const void* W2, const float* g, int64_t M, int32_t Din, int32_t D,
+                       float grad_scale, float* dW1, float* db1, float* dW2, float* db2, float* dg, void* ws,
+                       int64_t ws_bytes, int32_t phases, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (!dims_ok(Din, D)) TD_FAIL(TD_ERR_UNSUPPORTED, "td_aligner_bwd: Din=%d, D=%d must be multiples of 64 (D <= 4096)", Din, D);
+  if (M < 0 || M > 0x7fffffffll / D) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd: M=%lld out of range", (long long)M);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M == 0) {  // empty shard: gradients are exact zeros
+    if (phases & TD_BWD_PHASE_NORM_W2) {
+      TD_CUDA(cudaMemsetAsync(dW2, 0, sizeof(float) * (size_t)D * D, st));
+      TD_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * D, st));
+      TD_CUDA(cudaMemsetAsync(dg, 0, sizeof(float) * D, st));
+    }
+    if (phases & TD_BWD_PHASE_GELU_W1) {
+      TD_CUDA(cudaMemsetAsync(dW1, 0, sizeof(float) * (size_t)D * Din, st));
+      TD_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * D, st));
+    }
+    return TD_OK;
+  }
+  if (ws_bytes < td_aligner_bwd_workspace_bytes(M, Din, D)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd: workspace too small");
+  BwdWorkspace w = carve_bwd(ws, M, D);
+  GemmParams p;
+
+  if (phases & TD_BWD_PHASE_NORM_W2) {
+    if (!dy || !h1 || !h2 || !rstd || !g || !dW2 || !db2 || !dg) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd: null pointer (phase 1)");
+    // T5LayerNorm backward -> dh2 (bf16), dg, db2
+    int rc = rmsnorm_bwd_impl(dy, dy_dtype, static_cast<const __nv_bfloat16*>(h2), rstd, g, M, D, w.dh2, dg, db2, grad_scale,
+                              w.norm_ws, st);
+    if (rc) return rc;
+    // dW2[D, D] = dh2^T . h1  (contraction over tokens; both operands MN-major)
+    memset(&p, 0, sizeof(p));
+    p.M = D; p.N = D; p.K = int(M); p.ld_out = D; p.alpha = grad_scale; p.out0 = dW2;
+    rc = launch_gemm<2, true, true, EPI_F32>({w.dh2, D, true}, {h1, D, true}, p, 0, st, "gemm_dW2");
+    if (rc) return rc;
+  }
+  if (phases & TD_BWD_PHASE_GELU_W1) {
+    if (!x || !h0 || !W2 || !dW1 || !db1) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd: null pointer (phase 2)");
+    // dh0 = bf16( bf16(dh2 . W2) * gelu'(h0) ), plus per-slab column sums for db1
+    memset(&p, 0, sizeof(p));
+    p.M = int(M); p.N = D; p.K = D; p.ld_out = D; p.alpha = 1.f;
+    p.out0 = w.dh0; p.aux0 = h0; p.red0 = w.db1_part;
+    int rc = launch_gemm<2, false, true, EPI_DGELU>({w.dh2, D, false}, {W2, D, true}, p, 1, st, "gemm_dh0_dgelu");
+    if (rc) return rc;
+    const int slabs = int((M + 2 * kBlockM - 1) / (2 * kBlockM)) * 2 * 4;  // pair tiles: 2 slabs x 4 warps each
+    colsum_finish_kernel<<<(D + 255) / 256, 256, 0, st>>>(w.db1_part, slabs, D, grad_scale, db1);
+    TD_CUDA(cudaGetLastError());
+    // dW1[D, Din] = dh0^T . x
+    memset(&p, 0, sizeof(p));
+    p.M = D; p.N = Din; p.K = int(M); p.ld_out = Din; p.alpha = grad_scale; p.out0 = dW1;
+    rc = launch_gemm<2, true, true, EPI_F32>({w.dh0, D, true}, {x, Din, true}, p, 0, st, "gemm_dW1");
+    if (rc) return rc;
+  }
+  return TD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ losses
+int64_t td_loss_workspace_bytes(int64_t rows) {
+  const size_t parts = (size_t)device_sm_count() * 8 + 8;
+  return (int64_t)(align_up(sizeof(float) * 8, 256) + align_up(sizeof(float) * parts, 256) +
+                   align_up(sizeof(float) * (size_t)(rows > 0 ? rows : 1), 256));
+}
+
+int32_t td_masked_mse_fwd_bwd(const void* y, int32_t y_dtype, const void* t, int32_t t_dtype, const int64_t* row_mask,
+                              int64_t M, int32_t D, float grad_scale, float* loss, void* dy, void* ws, int64_t ws_bytes,
+                              td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (M < 0 || D <= 0 || D % 8) TD_FAIL(TD_ERR_ARG, "td_masked_mse_fwd_bwd: D=%d must be a positive multiple of 8", D);
+  if (!loss) TD_FAIL(TD_ERR_ARG, "td_masked_mse_fwd_bwd: loss pointer is null");
+  if (ws_bytes < td_loss_workspace_bytes(M)) TD_FAIL(TD_ERR_ARG, "td_masked_mse_fwd_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver c(ws);
+  float* meta = c.take<float>(8);
+  float* part = c.take<float>((size_t)device_sm_count() * 8 + 8);
+  count_valid_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const long long*>(row_mask), M, 0, meta);
+  int grid = 1;
+  if (M > 0) {
+    grid = grid_for_rows(M, 8, 8);
+    const long long* mk = reinterpret_cast<const long long*>(row_mask);
+    const int sel = (y_dtype == TD_DTYPE_BF16 ? 2 : 0) | (t_dtype == TD_DTYPE_BF16 ? 1 : 0);
+    ProfScope prof("masked_mse", double(M) * D * ((y_dtype == TD_DTYPE_BF16 ? 2.0 : 4.0) * (dy ? 2.0 : 1.0) + (t_dtype == TD_DTYPE_BF16 ? 2.0 : 4.0)), st);
+    switch (sel) {
+      case 0: masked_mse_kernel<false, false><<<grid, 256, 0, st>>>(y, t, mk, int(M), D, meta, grad_scale, dy, part); break;
+      case 1: masked_mse_kernel<false, true><<<grid, 256, 0, st>>>(y, t, mk, int(M), D, meta, grad_scale, dy, part); break;
+      case 2: masked_mse_kernel<true, false><<<grid, 256, 0, st>>>(y, t, mk, int(M), D, meta, grad_scale, dy, part); break;
+      default: masked_mse_kernel<true, true><<<grid, 256, 0, st>>>(y, t, mk, int(M), D, meta, grad_scale, dy, part); break;
+    }
+  } else {
+    TD_CUDA(cudaMemsetAsync(part, 0, sizeof(float), st));
+  }
+  loss_finish_kernel<<<1, 256, 0, st>>>(part, grid, meta, float(D), loss);
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+int32_t td_masked_ce_fwd_bwd(const void* logits, int32_t dtype, const int64_t* labels, int64_t R, int32_t V,
+                             float grad_scale, float* loss, void* dlogits, void* ws, int64_t ws_bytes,
+                             td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (R < 0 || V <= 0 || V % 8) TD_FAIL(TD_ERR_ARG, "td_masked_ce_fwd_bwd: V=%d must be a positive multiple of 8", V);
+  if ((size_t)V * sizeof(float) > 200 * 1024) TD_FAIL(TD_ERR_UNSUPPORTED, "td_masked_ce_fwd_bwd: V=%d does not fit the smem row stage", V);
+  if (!loss || (R > 0 && (!logits || !labels))) TD_FAIL(TD_ERR_ARG, "td_masked_ce_fwd_bwd: null pointer");
+  if (ws_bytes < td_loss_workspace_bytes(R)) TD_FAIL(TD_ERR_ARG, "td_masked_ce_fwd_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver c(ws);
+  float* meta = c.take<float>(8);
+  (void)c.take<float>((size_t)device_sm_count() * 8 + 8);
+  float* row_loss = c.take<float>((size_t)(R > 0 ? R : 1));
+  count_valid_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const long long*>(labels), R, 1, meta);
+  if (R > 0) {
+    const size_t smem = (size_t)V * sizeof(float);
+    ProfScope prof("masked_ce", double(R) * V * (dtype == TD_DTYPE_BF16 ? 2.0 : 4.0) * (dlogits ? 2.0 : 1.0), st);
+    static bool attr_done[2] = {false, false};
+    if (dtype == TD_DTYPE_BF16) {
+      if (!attr_done[1]) { TD_CUDA(cudaFuncSetAttribute(masked_ce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done[1] = true; }
+      masked_ce_kernel<true><<<int(R), kCeThreads, smem, st>>>(logits, reinterpret_cast<const long long*>(labels), V, meta, grad_scale, dlogits, row_loss);
+    } else {
+      if (!attr_done[0]) { TD_CUDA(cudaFuncSetAttribute(masked_ce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done[0] = true; }
+      masked_ce_kernel<false><<<int(R), kCeThreads, smem, st>>>(logits, reinterpret_cast<const long long*>(labels), V, meta, grad_scale, dlogits, row_loss);
+    }
+    TD_CUDA(cudaGetLastError());
+  } else {
+    TD_CUDA(cudaMemsetAsync(row_loss, 0, sizeof(float), st));
+  }
+  loss_finish_kernel<<<1, 256, 0, st>>>(row_loss, int(R), meta, 1.0f, loss);
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,226 @@
+"""Functional wrappers: torch tensors in, C-ABI calls out. torch is used for device memory and streams only.
+
+Every function checks shapes/dtypes on the host, allocates outputs through the caching allocator (so stream
+semantics hold) and launches on ``torch.cuda.current_stream()``.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("thinkdiff_mlre_b200 runs on CUDA tensors only (no CPU fallback)")
+
+
+def _contig(t, name):
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+# ------------------------------------------------------------------------------------------------ pack
+def cu_seqlens(lens: torch.Tensor) -> torch.Tensor:
+    """int32 lens[B] (device) -> int32 cu_seqlens[B+1] (device)."""
+    _need_cuda(lens)
+    lens = _contig(lens.to(torch.int32), "lens")
+    cu = torch.empty(lens.numel() + 1, dtype=torch.int32, device=lens.device)
+    L.launch_count += 1
+    L.check(L.lib().td_cu_seqlens(L.ptr(lens), lens.numel(), L.ptr(cu), L.stream_ptr()), "td_cu_seqlens")
+    return cu
+
+
+def pack_varlen(flat: torch.Tensor, src_row_start: torch.Tensor, cu: torch.Tensor, total_rows: int) -> torch.Tensor:
+    """flat [R, C] (any dtype) -> packed [total_rows, C]: rows src_row_start[i] + [0, len_i) of each sample, back to back."""
+    _need_cuda(flat, src_row_start, cu)
+    _contig(flat, "flat")
+    if src_row_start.dtype != torch.int64 or cu.dtype != torch.int32:
+        raise TypeError("src_row_start must be int64 and cu_seqlens int32")
+    out = torch.empty((total_rows, flat.shape[1]), dtype=flat.dtype, device=flat.device)
+    row_bytes = flat.shape[1] * flat.element_size()
+    L.launch_count += 1
+    L.check(
+        L.lib().td_pack_varlen(L.ptr(flat), L.ptr(src_row_start), L.ptr(cu), cu.numel() - 1, total_rows, row_bytes,
+                               L.ptr(out), L.stream_ptr()),
+        "td_pack_varlen",
+    )
+    return out
+
+
+def pack_padded(flat: torch.Tensor, src_row_start: torch.Tensor, cu: torch.Tensor, l_max: int, want_mask: bool = True):
+    """Reference layout: zero-padded [B, l_max, C] and int64 mask [B, l_max]."""
+    _need_cuda(flat, src_row_start, cu)
+    _contig(flat, "flat")
+    B = cu.numel() - 1
+    out = torch.empty((B, l_max, flat.shape[1]), dtype=flat.dtype, device=flat.device)
+    mask = torch.empty((B, l_max), dtype=torch.int64, device=flat.device) if want_mask else None
+    row_bytes = flat.shape[1] * flat.element_size()
+    L.launch_count += 1
+    L.check(
+        L.lib().td_pack_padded(L.ptr(flat), L.ptr(src_row_start), L.ptr(cu), B, l_max, row_bytes, L.ptr(out), L.ptr(mask),
+                               L.stream_ptr()),
+        "td_pack_padded",
+    )
+    return out, mask
+
+
+# ------------------------------------------------------------------------------------------------ params
+def cast_to_bf16(src: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    _need_cuda(src)
+    if src.dtype != torch.float32:
+        raise TypeError("cast_to_bf16 expects float32")
+    _contig(src, "src")
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    L.launch_count += 1
+    L.check(L.lib().td_cast_f32_to_bf16(L.ptr(src), L.ptr(out), src.numel(), L.stream_ptr()), "td_cast_f32_to_bf16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ aligner
+def aligner_fwd(x, W1, b1, W2, b2, g, eps: float, out_bf16: bool, save_for_backward: bool):
+    """x [M, Din] bf16; W/b bf16; g fp32 -> y [M, D] (fp32, or bf16 when out_bf16), saved = (h0, h1, h2, rstd)."""
+    _need_cuda(x, W1, W2, g)
+    M, Din = x.shape
+    D = W1.shape[0]
+    for t, n in ((x, "x"), (W1, "W1"), (W2, "W2")):
+        if t.dtype != torch.bfloat16:
+            raise TypeError(f"{n} must be bfloat16")
+        _contig(t, n)
+    if g.dtype != torch.float32:
+        raise TypeError("norm weight must be float32 at the ABI")
+    dev = x.device
+    h0 = torch.empty((M, D), dtype=torch.bfloat16, device=dev) if save_for_backward else None
+    h1 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+    h2 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+    rstd = torch.empty((M,), dtype=torch.float32, device=dev)
+    y = torch.empty((M, D), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
+    ws_bytes = L.lib().td_aligner_fwd_workspace_bytes(M, Din, D)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    L.launch_count += 3
+    L.check(
+        L.lib().td_aligner_fwd(L.ptr(x), M, Din, D, L.ptr(W1), L.ptr(b1), L.ptr(W2), L.ptr(b2), L.ptr(g), eps, L.ptr(h0),
+                               L.ptr(h1), L.ptr(h2), L.ptr(rstd), L.ptr(y), L.BF16 if out_bf16 else L.F32, L.ptr(ws),
+                               ws_bytes, L.stream_ptr()),
+        "td_aligner_fwd",
+    )
+    return y, (h0, h1, h2, rstd)
+
+
+class AlignerBackward:
+    """Two-phase aligner backward writing into caller-chosen gradient buffers (so buckets can be flat)."""
+
+    def __init__(self, x, saved, W2, g, dy, grad_scale: float = 1.0):
+        self.x, (self.h0, self.h1, self.h2, self.rstd), self.W2, self.g = x, saved, W2, g
+        self.dy = _contig(dy, "dy")
+        self.M, self.Din = x.shape
+        self.D = W2.shape[0]
+        self.grad_scale = float(grad_scale)
+        ws_bytes = L.lib().td_aligner_bwd_workspace_bytes(self.M, self.Din, self.D)
+        self.ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+        self.ws_bytes = ws_bytes
+
+    def _call(self, phase, dW1, db1, dW2, db2, dg):
+        L.launch_count += 4 if phase == L.BWD_NORM_W2 else 3
+        L.check(
+            L.lib().td_aligner_bwd(L.ptr(self.dy), L.dtype_code(self.dy), L.ptr(self.x), L.ptr(self.h0), L.ptr(self.h1),
+                                   L.ptr(self.h2), L.ptr(self.rstd), L.ptr(self.W2), L.ptr(self.g), self.M, self.Din,
+                                   self.D, self.grad_scale, L.ptr(dW1), L.ptr(db1), L.ptr(dW2), L.ptr(db2), L.ptr(dg),
+                                   L.ptr(self.ws), self.ws_bytes, phase, L.stream_ptr()),
+            "td_aligner_bwd",
+        )
+
+    def norm_and_linear2(self, dW2, db2, dg):
+        self._call(L.BWD_NORM_W2, None, None, dW2, db2, dg)
+
+    def gelu_and_linear1(self, dW1, db1):
+        self._call(L.BWD_GELU_W1, dW1, db1, None, None, None)
+
+
+def rmsnorm_fwd(x: torch.Tensor, g: torch.Tensor, eps: float = 1e-6, out_bf16: bool = False):
+    _need_cuda(x, g)
+    M, D = x.shape
+    y = torch.empty((M, D), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+    rstd = torch.empty((M,), dtype=torch.float32, device=x.device)
+    L.launch_count += 1
+    L.check(L.lib().td_rmsnorm_fwd(L.ptr(_contig(x, "x")), L.ptr(g), eps, M, D, L.ptr(y), L.BF16 if out_bf16 else L.F32,
+                                   L.ptr(rstd), L.stream_ptr()), "td_rmsnorm_fwd")
+    return y, rstd
+
+
+def rmsnorm_bwd(dy, x, rstd, g):
+    _need_cuda(dy, x, rstd, g)
+    M, D = x.shape
+    dx = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
+    dg = torch.empty((D,), dtype=torch.float32, device=x.device)
+    dxsum = torch.empty((D,), dtype=torch.float32, device=x.device)
+    ws_bytes = L.lib().td_rmsnorm_bwd_workspace_bytes(M, D)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+    L.launch_count += 3
+    L.check(L.lib().td_rmsnorm_bwd(L.ptr(_contig(dy, "dy")), L.dtype_code(dy), L.ptr(x), L.ptr(rstd), L.ptr(g), M, D,
+                                   L.ptr(dx), L.ptr(dg), L.ptr(dxsum), L.ptr(ws), ws_bytes, L.stream_ptr()), "td_rmsnorm_bwd")
+    return dx, dg, dxsum
+
+
+def linear_bf16(x, W, bias=None):
+    _need_cuda(x, W)
+    M, K = x.shape
+    N = W.shape[0]
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    L.launch_count += 1
+    L.check(L.lib().td_linear_bf16(L.ptr(_contig(x, "x")), M, K, L.ptr(_contig(W, "W")), N, L.ptr(bias), L.ptr(out),
+                                   L.stream_ptr()), "td_linear_bf16")
+    return out
+
+
+def gemm_f32out(A, B, a_mn_major: bool, b_mn_major: bool, alpha: float = 1.0, cta_pair: bool = True, splits: int = 0):
+    """Test entry: D[M, N] fp32 = alpha * A.B^T; K-major operand = [rows, K], MN-major operand = [K, rows]."""
+    _need_cuda(A, B)
+    M, K = (A.shape[1], A.shape[0]) if a_mn_major else A.shape
+    N = B.shape[1] if b_mn_major else B.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    L.launch_count += 1
+    L.check(L.lib().td_gemm_bf16_f32out(L.ptr(_contig(A, "A")), A.stride(0), int(a_mn_major), L.ptr(_contig(B, "B")),
+                                        B.stride(0), int(b_mn_major), M, N, K, alpha, L.ptr(out), int(cta_pair), splits,
+                                        L.stream_ptr()), "td_gemm_bf16_f32out")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ losses
+def masked_mse_fwd_bwd(y, target, row_mask=None, grad_scale: float = 1.0, want_grad: bool = True):
+    """Returns (loss fp32 scalar tensor, dy or None). y, target [M, D] float32/bfloat16; row_mask int64 [M] or None."""
+    _need_cuda(y, target, row_mask)
+    M, D = y.shape
+    if target.shape != y.shape:
+        raise ValueError("target shape must match y")
+    if row_mask is not None and (row_mask.dtype != torch.int64 or row_mask.numel() != M):
+        raise TypeError("row_mask must be int64 [M]")
+    loss = torch.empty((), dtype=torch.float32, device=y.device)
+    dy = torch.empty_like(y) if want_grad else None
+    ws_bytes = L.lib().td_loss_workspace_bytes(M)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=y.device)
+    L.launch_count += 3
+    L.check(L.lib().td_masked_mse_fwd_bwd(L.ptr(_contig(y, "y")), L.dtype_code(y), L.ptr(_contig(target, "target")),
+                                          L.dtype_code(target), L.ptr(row_mask), M, D, grad_scale, L.ptr(loss), L.ptr(dy),
+                                          L.ptr(ws), ws_bytes, L.stream_ptr()), "td_masked_mse_fwd_bwd")
+    return loss, dy
+
+
+def masked_ce_fwd_bwd(logits, labels, grad_scale: float = 1.0, want_grad: bool = True):
+    """CrossEntropyLoss(ignore_index=-100) forward + dlogits. logits [R, V] float32/bfloat16, labels int64 [R]."""
+    _need_cuda(logits, labels)
+    R, V = logits.shape
+    if labels.dtype != torch.int64 or labels.numel() != R:
+        raise TypeError("labels must be int64 [R]")
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    dz = torch.empty_like(logits) if want_grad else None
+    ws_bytes = L.lib().td_loss_workspace_bytes(R)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=logits.device)
+    L.launch_count += 3
+    L.check(L.lib().td_masked_ce_fwd_bwd(L.ptr(_contig(logits, "logits")), L.dtype_code(logits), L.ptr(_contig(labels, "labels")),
+                                         R, V, grad_scale, L.ptr(loss), L.ptr(dz), L.ptr(ws), ws_bytes, L.stream_ptr()),
+            "td_masked_ce_fwd_bwd")
+    return loss, dz

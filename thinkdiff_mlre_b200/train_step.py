@@ -1,0 +1,84 @@
+"""The aligner training step, isolated: pack -> aligner forward -> masked loss -> backward (-> gradient all-reduce) -> AdamW.
+
+This is the hot part of the reference's ``BaseTask._train_inner_loop`` (thinkdiff/tasks/base_task.py:169-272) with the
+frozen T5 decoder excised: ``samples -> .cuda() -> autocast(bf16) forward -> loss -> backward ->
+optimizer.step -> zero_grad``. The optimizer is the reference's AdamW with its weight-decay split
+(thinkdiff/runners/runner_base.py:98-127); it stays a PyTorch (fused) optimizer -- plumbing, not the product.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .aligner import ThinkDiffAligner
+from .pack import FlatBatch, pack_device
+
+
+def reference_param_groups(module: torch.nn.Module, weight_decay: float = 0.05):
+    """The reference's weight-decay split (runner_base.py:104-119): no decay for ndim < 2 or names with bias/ln/bn."""
+    decay, no_decay = [], []
+    for n, p in module.named_parameters():
+        if not p.requires_grad:
+            continue
+        (no_decay if (p.ndim < 2 or "bias" in n or "ln" in n or "bn" in n) else decay).append(p)
+    return [{"params": decay, "weight_decay": weight_decay}, {"params": no_decay, "weight_decay": 0.0}]
+
+
+def make_reference_optimizer(module, lr: float = 1e-4, weight_decay: float = 0.05, beta2: float = 0.999):
+    return torch.optim.AdamW(reference_param_groups(module, weight_decay), lr=lr, weight_decay=weight_decay,
+                             betas=(0.9, beta2), fused=True)
+
+
+def synthetic_lvlm_batch(num_seqs: int, max_len: int, din: int, d: int, seed: int, pin: bool = True,
+                         with_target: bool = True) -> FlatBatch:
+    """BASELINE config-2 style ragged batch: kept length ``len_i ~ U{1..max_len}`` (the injected
+    split point), source length ``L_i = len_i + 1 + (i mod 32)``, bf16 N(0,1) features ``[sum L_i, din]`` and, for the
+    MSE loss, bf16 N(0,1) targets ``[sum L_i, d]`` in the same ragged source layout. Host tensors (pinned)."""
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(1, max_len + 1, (num_seqs,), generator=g, dtype=torch.int32)
+    full = lens.to(torch.int64) + 1 + (torch.arange(num_seqs) % 32)
+    start = torch.zeros(num_seqs, dtype=torch.int64)
+    start[1:] = torch.cumsum(full[:-1], 0)
+    rows = int(full.sum())
+    flat = torch.randn((rows, din), generator=g, dtype=torch.float32).to(torch.bfloat16)
+    extras = {}
+    if with_target:
+        extras["flat_target"] = torch.randn((rows, d), generator=g, dtype=torch.float32).to(torch.bfloat16)
+    if pin and torch.cuda.is_available():
+        flat = flat.pin_memory()
+        if with_target:
+            extras["flat_target"] = extras["flat_target"].pin_memory()
+    return FlatBatch(flat, start, lens, int(lens.max()), extras)
+
+
+class AlignerTrainStep:
+    """One data-parallel training step of the aligner against T5-space targets (masked MSE)."""
+
+    def __init__(self, aligner: ThinkDiffAligner, optimizer=None, loss_scale: float = 1.0):
+        self.aligner = aligner
+        self.optimizer = optimizer
+        self.loss_scale = float(loss_scale)  # GradScaler-style static scale (backward is linear in it)
+
+    def step_device(self, flat, src_row_start, lens_dev, total_rows: int, l_max: int, flat_target) -> torch.Tensor:
+        """Inputs already resident in HBM. Returns the (unscaled) loss as a device scalar; nothing syncs the host."""
+        packed = pack_device(flat, src_row_start, lens_dev, total_rows, l_max)
+        target = ops.pack_varlen(flat_target, src_row_start, packed.cu_seqlens, total_rows)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = self.aligner.forward_packed(packed.x, packed.cu_seqlens)
+        loss, dy = ops.masked_mse_fwd_bwd(y, target, None, self.loss_scale)
+        y.backward(dy)
+        if self.optimizer is not None:
+            if self.loss_scale != 1.0:
+                for group in self.optimizer.param_groups:
+                    torch._foreach_mul_([p.grad for p in group["params"] if p.grad is not None], 1.0 / self.loss_scale)
+            self.optimizer.step()
+            self.optimizer.zero_grad(set_to_none=True)
+        return loss
+
+    def step_host(self, batch: FlatBatch, device="cuda") -> torch.Tensor:
+        """Inputs in (pinned) host memory: async H2D of the flat features/targets, then ``step_device``."""
+        flat = batch.flat.to(device, non_blocking=True)
+        tgt = batch.extras["flat_target"].to(device, non_blocking=True)
+        start = batch.src_row_start.to(device, non_blocking=True)
+        lens = batch.lens.to(device, non_blocking=True)
+        return self.step_device(flat, start, lens, batch.total_rows, batch.l_max, tgt)
