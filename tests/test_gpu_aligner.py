@@ -309,3 +309,27 @@ def test_standalone_rmsnorm_fwd_bwd():
     y16, _ = ops.rmsnorm_fwd(x.cuda(), gw.cuda(), out_bf16=True)
     ref16 = norm.to(torch.bfloat16)(x)
     assert y16.dtype == torch.bfloat16 and rel(y16, ref16.float()) < 5e-3
+
+
+def test_weights_are_recast_after_a_fused_optimizer_step():
+    """torch's fused AdamW updates parameters without bumping Tensor._version: the bf16 compute copies must not go stale."""
+    from oracle import aligner_ref
+
+    m, _ = make_module(192, 512, seed=12)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-2, fused=True)
+    x = torch.randn(64, 192, device="cuda").to(torch.bfloat16)
+    t = torch.randn(64, 512, device="cuda")
+    for _ in range(3):
+        run_train(m, x, t)
+        opt.step()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = m(x)
+    params = {k: v.detach().float().cpu() for k, v in m.state_dict().items()}
+    ref = aligner_ref.aligner_fwd_bwd_manual(x.float().cpu(), params, regime="bf16")
+    assert rel(y, ref["y"]) < 5e-3
+    m.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y1 = m(x)
+        m[0].weight.mul_(2.0)  # in-place edit bumps the version: the eval cache must notice
+        y2 = m(x)
+    assert torch.equal(y1, y.detach()) and not torch.equal(y1, y2)

@@ -156,11 +156,15 @@ class ThinkDiffAligner(nn.Sequential):
         self._dp = None
         return self
 
-    def _bf16_params(self):
-        """bf16 compute copies of the Linear parameters, re-cast only when a parameter changed (optimizer step, load)."""
+    def _bf16_params(self, allow_cache: bool = False):
+        """bf16 compute copies of the Linear parameters.
+
+        Training casts on every forward, exactly as autocast does (fused optimizers update parameters without bumping
+        ``Tensor._version``, so a version-keyed cache would go stale). Only ``eval()`` + ``no_grad`` inference reuses the
+        copies, keyed on (data_ptr, version) so that ``load_state_dict`` / ``.to()`` still invalidate them."""
         ps = (self[0].weight, self[0].bias, self[2].weight, self[2].bias)
         key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
-        if key != self._cache_key:
+        if not allow_cache or key != self._cache_key:
             with torch.no_grad():
                 self._cache = tuple(p.detach() if p.dtype == torch.bfloat16 else ops.cast_to_bf16(p.detach().contiguous()) for p in ps)
             self._cache_key = key
@@ -201,7 +205,7 @@ class ThinkDiffAligner(nn.Sequential):
             if need_grad:
                 y = _AlignerFn.apply(x2d, w1, b1, w2, b2, g, self, regime == "bf16_infer")
             else:  # inference: nothing is saved, h0 is never written
-                W1b, b1b, W2b, b2b = self._bf16_params()
+                W1b, b1b, W2b, b2b = self._bf16_params(allow_cache=not self.training)
                 gf = g.detach() if g.dtype == torch.float32 else g.detach().float()
                 y, _ = ops.aligner_fwd(x2d, W1b, b1b, W2b, b2b, gf, self.eps, regime == "bf16_infer", False)
         return y.reshape(*lead, self.hidden_size)

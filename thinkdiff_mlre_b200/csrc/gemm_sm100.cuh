@@ -8,8 +8,8 @@
 // over the token dimension of two row-major activations, dX = dY W contracts over W's row index). The tensor
 // core reads both through the 128-byte-swizzled canonical layouts, so no transposed copies are ever written.
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue
-// (one TMEM lane quarter each). CTAS=2 runs a CTA pair on one 256-row tile (tcgen05 cta_group::2): each CTA
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = epilogue
+// (TMEM lane quarter = warp % 4, two warps per quarter split the columns). CTAS=2 runs a CTA pair on one 256-row tile (tcgen05 cta_group::2): each CTA
 // stages its own 128 rows of A and half of B, the leader issues the MMAs, both run their own epilogue.
 //
 // Reference semantics being fused (thinkdiff/models/mllama_vllm_t5_embed_decoder_2.py:58-63, under the bf16
@@ -23,7 +23,7 @@ namespace td {
 enum EpiKind : int {
   EPI_BF16 = 0,       // out0 = bf16(acc + bias?)
   EPI_BIAS_GELU = 1,  // out0 = h0 = bf16(acc + bias); out1 = bf16(gelu(h0))
-  EPI_BIAS_SSQ = 2,   // out0 = h2 = bf16(acc + bias); red0[n_blk][row] = sum_cols h2^2
+  EPI_BIAS_SSQ = 2,   // out0 = h2 = bf16(acc + bias); red0[2 * n_blk + half][row] = sum over 128 cols of h2^2
   EPI_DGELU = 3,      // t = bf16(acc); out0 = bf16(t * gelu'(aux0)); red0[m_slab][col] = sum_rows out0
   EPI_F32 = 4,        // out0(fp32) = alpha * acc   (splits > 1: red.add into a zeroed out0)
 };
@@ -45,7 +45,7 @@ constexpr int kBlockM = 128;  // rows per CTA (TMEM lanes)
 constexpr int kBlockN = 256;  // accumulator columns (two stages fill the 512-column TMEM)
 constexpr int kBlockK = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kAccStages = 2;
 
 template <int CTAS>
@@ -59,24 +59,61 @@ struct GemmSmem {
 };
 
 // ------------------------------------------------------------------------------------------ epilogues
+// Eight epilogue warps: warp e (0..7) owns TMEM lane quarter (warp % 4) and column half e / 4 of the 256-column
+// accumulator, i.e. 32 rows x 128 columns, walked in 4 chunks of 32 columns. Thread = one output row.
+constexpr int kEpiWarps = 8;
+constexpr int kEpiColsPerWarp = kBlockN / (kEpiWarps / 4);  // 128
+constexpr int kEpiChunks = kEpiColsPerWarp / 32;            // 4
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int row0, int n0, int n_blk,
-                                              int m_slab, int quarter, int lane) {
+                                              int m_slab, int quarter, int half, int lane) {
   const int row = row0 + quarter * 32 + lane;
   const bool row_ok = row < p.M;
-  const uint32_t taddr = tmem_acc + (uint32_t(quarter * 32) << 16);
+  const int ncol0 = n0 + half * kEpiColsPerWarp;
+  const uint32_t taddr = tmem_acc + (uint32_t(quarter * 32) << 16) + half * kEpiColsPerWarp;
+  const long long row_off = (long long)row * p.ld_out;
   float ssq = 0.f;
 
+  // software prefetch of the saved pre-activation (EPI_DGELU): chunk c+1 is in flight while chunk c is computed
+  uint4 aux_next[4];
+  auto load_aux = [&](int c) {
+    const int col0 = ncol0 + c * 32;
+    if (row_ok && col0 < p.N) {
+      const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux0) + row_off + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) aux_next[q] = __ldg(ap + q);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) aux_next[q] = make_uint4(0, 0, 0, 0);
+    }
+  };
+  if constexpr (EPI == EPI_DGELU) load_aux(0);
+
 #pragma unroll 1
-  for (int c = 0; c < kBlockN / 32; ++c) {
-    const int col0 = n0 + c * 32;
+  for (int c = 0; c < kEpiChunks; ++c) {
+    const int col0 = ncol0 + c * 32;
     if (col0 >= p.N) break;  // N % 32 == 0 is enforced on the host
     uint32_t v[32];
     tmem_ld_32x32(taddr + c * 32, v);
+    uint4 aux[4];
+    if constexpr (EPI == EPI_DGELU) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) aux[q] = aux_next[q];
+      if (c + 1 < kEpiChunks) load_aux(c + 1);
+    }
     tmem_ld_wait();
 
     if constexpr (EPI == EPI_F32) {
-      float* out = reinterpret_cast<float*>(p.out0) + (long long)row * p.ld_out + col0;
+      float* out = reinterpret_cast<float*>(p.out0) + row_off + col0;
       if (row_ok) {
         if (p.splits == 1) {
 #pragma unroll
@@ -95,95 +132,67 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
           }
         }
       }
+    } else if constexpr (EPI == EPI_DGELU) {
+      // dh0 = bf16( bf16(dh1) * gelu'(h0) ): dh1 is rounded to bf16 first, as autograd materialises it.
+      float colsum[32];
+      uint4* o0 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out0) + row_off + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float x[8], h[8];
+        unpack8(aux[q], x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = bf16_round(__uint_as_float(v[q * 8 + j]));
+          h[j] = row_ok ? bf16_round(t * gelu_grad_fast(x[j])) : 0.f;
+          colsum[q * 8 + j] = h[j];
+        }
+        if (row_ok) o0[q] = pack8(h);
+      }
+      // Column sums over this warp's 32 rows by a butterfly transpose-reduce: after the 5 rounds lane j holds
+      // the sum over lanes of colsum[j]. 31 shuffles for 32 columns.
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+          const float send = upper ? colsum[i] : colsum[i + off];
+          const float keep = upper ? colsum[i + off] : colsum[i];
+          colsum[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      p.red0[(long long)(m_slab * 4 + quarter) * p.N + col0 + lane] = colsum[0];
     } else {
       // bias (bf16, same 32 columns for every thread of the warp -> broadcast loads)
-      float b[32];
-      if constexpr (EPI == EPI_BF16 || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_SSQ) {
+      uint4* o0 = p.out0 ? reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out0) + row_off + col0) : nullptr;
+      uint4* o1 = nullptr;
+      if constexpr (EPI == EPI_BIAS_GELU) o1 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out1) + row_off + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float b[8], h[8];
         if (p.bias != nullptr) {
-          const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 u = __ldg(bp + q);
-            b[q * 8 + 0] = bf16lo(u.x); b[q * 8 + 1] = bf16hi(u.x);
-            b[q * 8 + 2] = bf16lo(u.y); b[q * 8 + 3] = bf16hi(u.y);
-            b[q * 8 + 4] = bf16lo(u.z); b[q * 8 + 5] = bf16hi(u.z);
-            b[q * 8 + 6] = bf16lo(u.w); b[q * 8 + 7] = bf16hi(u.w);
-          }
+          unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias + col0) + q), b);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) b[j] = 0.f;
+          for (int j = 0; j < 8; ++j) b[j] = 0.f;
         }
-      }
-      float h[32];  // first output, already rounded to bf16 precision
-      if constexpr (EPI == EPI_DGELU) {
-        // gelu'(h0) on the saved pre-activation; dh1 is rounded to bf16 first, as autograd materialises it.
-        uint4 a[4];
-        if (row_ok) {
-          const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux0) +
-                                                           (long long)row * p.ld_out + col0);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) a[q] = __ldg(ap + q);
-        } else {
+        for (int j = 0; j < 8; ++j) h[j] = bf16_round(__uint_as_float(v[q * 8 + j]) + b[j]);
+        if (row_ok && o0 != nullptr) o0[q] = pack8(h);  // inference skips saving the pre-activation
+        if constexpr (EPI == EPI_BIAS_GELU) {
+          float g[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) a[q] = make_uint4(0, 0, 0, 0);
+          for (int j = 0; j < 8; ++j) g[j] = gelu_fast(h[j]);
+          if (row_ok) o1[q] = pack8(g);
         }
-        const uint32_t* aw = reinterpret_cast<const uint32_t*>(a);
+        if constexpr (EPI == EPI_BIAS_SSQ) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float x0 = bf16lo(aw[j >> 1]), x1 = bf16hi(aw[j >> 1]);
-          const float t0 = bf16_round(__uint_as_float(v[j])), t1 = bf16_round(__uint_as_float(v[j + 1]));
-          h[j] = row_ok ? bf16_round(t0 * gelu_erf_grad(x0)) : 0.f;
-          h[j + 1] = row_ok ? bf16_round(t1 * gelu_erf_grad(x1)) : 0.f;
+          for (int j = 0; j < 8; ++j) ssq = fmaf(h[j], h[j], ssq);
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) h[j] = bf16_round(__uint_as_float(v[j]) + b[j]);
-      }
-
-      if (row_ok && p.out0 != nullptr) {  // inference skips saving the pre-activation
-        uint4* o0 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out0) + (long long)row * p.ld_out + col0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          o0[q] = make_uint4(pack_bf16x2(h[q * 8 + 0], h[q * 8 + 1]), pack_bf16x2(h[q * 8 + 2], h[q * 8 + 3]),
-                             pack_bf16x2(h[q * 8 + 4], h[q * 8 + 5]), pack_bf16x2(h[q * 8 + 6], h[q * 8 + 7]));
-      }
-      if constexpr (EPI == EPI_BIAS_GELU) {
-        if (row_ok) {
-          uint4* o1 =
-              reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out1) + (long long)row * p.ld_out + col0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float g[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] = gelu_erf(h[q * 8 + j]);
-            o1[q] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
-                               pack_bf16x2(g[6], g[7]));
-          }
-        }
-      }
-      if constexpr (EPI == EPI_BIAS_SSQ) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) ssq = fmaf(h[j], h[j], ssq);
-      }
-      if constexpr (EPI == EPI_DGELU) {
-        // Column sums over this warp's 32 rows by a butterfly transpose-reduce: after the 5 rounds lane j
-        // holds sum over lanes of h[j]. 31 shuffles for 32 columns.
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-          const bool upper = (lane & off) != 0;
-#pragma unroll
-          for (int i = 0; i < off; ++i) {
-            const float send = upper ? h[i] : h[i + off];
-            const float keep = upper ? h[i + off] : h[i];
-            h[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-          }
-        }
-        p.red0[(long long)(m_slab * 4 + quarter) * p.N + col0 + lane] = h[0];
       }
     }
   }
   if constexpr (EPI == EPI_BIAS_SSQ) {
-    if (row_ok) p.red0[(long long)n_blk * p.M + row] = ssq;
+    if (row_ok) p.red0[(long long)(n_blk * 2 + half) * p.M + row] = ssq;
   }
 }
 
@@ -219,7 +228,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&acc_full_bar[s], 1);
-      mbar_init(&acc_empty_bar[s], 128 * CTAS);
+      mbar_init(&acc_empty_bar[s], 32 * kEpiWarps * CTAS);
     }
     fence_mbar_init();
   }
@@ -335,6 +344,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else {
     // ===================================================== epilogue warps (TMEM lane quarter = warp % 4)
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int unit = worker; unit < num_units; unit += num_workers) {
@@ -344,7 +354,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const int m_slab = m_blk * CTAS + cta_rank;
       if (kb1 > kb0)
-        epilogue_tile<EPI>(p, tmem_base + acc * kBlockN, m_slab * kBlockM, n_blk * kBlockN, n_blk, m_slab, quarter, lane);
+        epilogue_tile<EPI>(p, tmem_base + acc * kBlockN, m_slab * kBlockM, n_blk * kBlockN, n_blk, m_slab, quarter, half, lane);
       tc_fence_before();
       if constexpr (CTAS == 1) mbar_arrive(&acc_empty_bar[acc]);
       else mbar_arrive_cluster(&acc_empty_bar[acc], 0);

@@ -267,8 +267,8 @@ int32_t td_gemm_bf16_f32out(const void* A, int64_t lda, int32_t a_mn, const void
 // ------------------------------------------------------------------------------------------------ aligner forward
 int64_t td_aligner_fwd_workspace_bytes(int64_t M, int32_t Din, int32_t D) {
   (void)Din;
-  const size_t nblk = (size_t)(D + kBlockN - 1) / kBlockN;
-  return (int64_t)align_up(sizeof(float) * nblk * (size_t)(M > 0 ? M : 1), 256);
+  const size_t nparts = 2 * ((size_t)(D + kBlockN - 1) / kBlockN);  // two column halves per N tile
+  return (int64_t)align_up(sizeof(float) * nparts * (size_t)(M > 0 ? M : 1), 256);
 }
 
 int32_t td_aligner_fwd(const void* x, int64_t M, int32_t Din, int32_t D, const void* W1, const void* b1, const void* W2,
@@ -282,7 +282,8 @@ int32_t td_aligner_fwd(const void* x, int64_t M, int32_t Din, int32_t D, const v
   if (ws_bytes < td_aligner_fwd_workspace_bytes(M, Din, D)) TD_FAIL(TD_ERR_ARG, "td_aligner_fwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   float* ssq_part = static_cast<float*>(ws);
-  const int nblk = (D + kBlockN - 1) / kBlockN;
+  // sum-of-squares partials: one per 128-column half tile that exists (the last N tile may be half empty)
+  const int nblk = (D + kEpiColsPerWarp - 1) / kEpiColsPerWarp;
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
