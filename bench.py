@@ -238,8 +238,10 @@ def main():
     clocks = ClockSampler(local)
     with clocks:
         e0.record()
+        t_host0 = time.perf_counter()
         for i in range(steps):
             loss = stepper.step_device(*resident[i % NUM_BATCHES])
+        host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / steps  # CPU time to enqueue one step (no sync inside)
         e1.record()
         sync_all()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -312,7 +314,7 @@ def main():
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_peak": step_tflops / peaks["bf16_tflops_sustained"],
             "step_frac_of_nominal_2250": step_tflops / 2250.0, "tokens_per_step": tokens / steps, "final_loss": final_loss,
-            "kernels": kernels,
+            "host_enqueue_ms_per_step": host_enqueue_ms, "kernels": kernels,
         }
         if args.profile_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)

@@ -14,9 +14,11 @@ namespace td {
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
+  // not volatile, no memory clobber: a read-only (.nc) load is a pure function of its address, so the compiler is
+  // free to hoist and batch these ahead of the streaming stores
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+      : "l"(p));
   return r;
 }
 __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
@@ -78,11 +80,23 @@ __global__ void cu_seqlens_kernel(const int* __restrict__ lens, int B, int* __re
 //   PADDED = true : dst row r of [B, Lmax, row] <- sample i = r / Lmax, row j = r % Lmax if j < len_i else zeros;
 //                   mask[r] = (j < len_i) as int64 (reference mask dtype, ...embed_2.py:118,128)
 // Source row = src_row_start[i] + j in the flat source (the un-truncated per-sample embeddings back to back).
+constexpr int kPackMaxStagedSeqs = 2048;  // cu_seqlens / src_row_start are staged in shared memory up to this batch size
+
 template <bool PADDED>
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const uint4* __restrict__ src, const long long* __restrict__ src_row_start,
                  const int* __restrict__ cu, int B, long long dst_rows, int Lmax, int vec_per_row,
                  uint4* __restrict__ dst, long long* __restrict__ mask) {
+  __shared__ int s_cu[kPackMaxStagedSeqs + 1];
+  __shared__ long long s_start[kPackMaxStagedSeqs];
+  const bool staged = B <= kPackMaxStagedSeqs;
+  if (staged) {
+    for (int i = threadIdx.x; i <= B; i += blockDim.x) s_cu[i] = cu[i];
+    for (int i = threadIdx.x; i < B; i += blockDim.x) s_start[i] = src_row_start[i];
+    __syncthreads();
+  }
+  const int* cu_t = staged ? s_cu : cu;
+  const long long* start_t = staged ? s_start : src_row_start;
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -92,20 +106,20 @@ pack_rows_kernel(const uint4* __restrict__ src, const long long* __restrict__ sr
     if constexpr (PADDED) {
       i = int(r / Lmax);
       j = int(r - (long long)i * Lmax);
-      valid = j < (cu[i + 1] - cu[i]);
+      valid = j < (cu_t[i + 1] - cu_t[i]);
       if (mask != nullptr && lane == 0) mask[r] = valid ? 1ll : 0ll;
     } else {
       int lo = 0, hi = B;  // largest i with cu[i] <= r
       while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if ((long long)__ldg(cu + mid) <= r) lo = mid; else hi = mid;
+        if ((long long)cu_t[mid] <= r) lo = mid; else hi = mid;
       }
       i = lo;
-      j = int(r - (long long)__ldg(cu + i));
+      j = int(r - (long long)cu_t[i]);
     }
     uint4* d = dst + r * vec_per_row;
     if (valid) {
-      const uint4* s = src + (__ldg(src_row_start + i) + j) * vec_per_row;
+      const uint4* s = src + (start_t[i] + j) * vec_per_row;
       for (int v0 = 0; v0 < vec_per_row; v0 += 256) {
         uint4 t[8];
 #pragma unroll
@@ -175,30 +189,39 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restrict
     ssq = warp_sum(ssq);
     const float rstd = rsqrtf(ssq / float(D) + eps);
     if (lane == 0 && rstd_out != nullptr) rstd_out[row] = rstd;
-    for (int v = lane; v < nvec; v += 32) {
-      const uint4 u = ld_stream(hp + v);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + 2 * v);
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(g) + 2 * v + 1);
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      float o[8];
+    constexpr int U = 4;  // 4 independent 16-byte loads in flight per lane
+    for (int v0 = lane; v0 < nvec; v0 += 32 * U) {
+      uint4 hu[U];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        o[2 * q] = bf16lo(w[q]) * rstd;
-        o[2 * q + 1] = bf16hi(w[q]) * rstd;
-      }
-      if constexpr (OUT_BF16) {
+      for (int k = 0; k < U; ++k)
+        if (v0 + 32 * k < nvec) hu[k] = ld_stream(hp + v0 + 32 * k);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) o[q] = bf16_round(gg[q]) * bf16_round(o[q]);
-        st_stream(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y_out) + (long long)row * D) + v,
-                  make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                             pack_bf16x2(o[6], o[7])));
-      } else {
-        uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<float*>(y_out) + (long long)row * D) + 2 * v;
-        st_stream(yp, make_uint4(__float_as_uint(gg[0] * o[0]), __float_as_uint(gg[1] * o[1]),
-                                 __float_as_uint(gg[2] * o[2]), __float_as_uint(gg[3] * o[3])));
-        st_stream(yp + 1, make_uint4(__float_as_uint(gg[4] * o[4]), __float_as_uint(gg[5] * o[5]),
-                                     __float_as_uint(gg[6] * o[6]), __float_as_uint(gg[7] * o[7])));
+      for (int k = 0; k < U; ++k) {
+        const int v = v0 + 32 * k;
+        if (v >= nvec) break;
+        const uint32_t w[4] = {hu[k].x, hu[k].y, hu[k].z, hu[k].w};
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + 2 * v);
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(g) + 2 * v + 1);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        float o[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          o[2 * q] = bf16lo(w[q]) * rstd;
+          o[2 * q + 1] = bf16hi(w[q]) * rstd;
+        }
+        if constexpr (OUT_BF16) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) o[q] = bf16_round(gg[q]) * bf16_round(o[q]);
+          st_stream(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y_out) + (long long)row * D) + v,
+                    make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                               pack_bf16x2(o[6], o[7])));
+        } else {
+          uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<float*>(y_out) + (long long)row * D) + 2 * v;
+          st_stream(yp, make_uint4(__float_as_uint(gg[0] * o[0]), __float_as_uint(gg[1] * o[1]),
+                                   __float_as_uint(gg[2] * o[2]), __float_as_uint(gg[3] * o[3])));
+          st_stream(yp + 1, make_uint4(__float_as_uint(gg[4] * o[4]), __float_as_uint(gg[5] * o[5]),
+                                       __float_as_uint(gg[6] * o[6]), __float_as_uint(gg[7] * o[7])));
+        }
       }
     }
   }
@@ -306,14 +329,36 @@ rmsnorm_bwd_kernel(const void* __restrict__ dy_in, const __nv_bfloat16* __restri
   }
 }
 
-// out[n] = scale * sum_p part[p][n]   (fixed order -> deterministic)
+// out[n] = scale * sum_p part[p][n]   (fixed order -> deterministic). One CTA per 32 columns; warp w adds rows
+// p = w, w + 8, ... (4 independent loads in flight), then the 8 warp sums are combined in warp order.
+// blockIdx.y selects one of up to two (part, out) pairs so that dg and db2 finish in one launch.
 __global__ void __launch_bounds__(256)
-colsum_finish_kernel(const float* __restrict__ part, int P, int N, float scale, float* __restrict__ out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float acc = 0.f;
-  for (int p = 0; p < P; ++p) acc += part[(long long)p * N + n];
-  out[n] = scale * acc;
+colsum_finish_kernel(const float* __restrict__ part0, float* __restrict__ out0, const float* __restrict__ part1,
+                     float* __restrict__ out1, int P, int N, float scale) {
+  __shared__ float red[8][33];
+  const float* part = blockIdx.y ? part1 : part0;
+  float* out = blockIdx.y ? out1 : out0;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (col < N) {
+    int p = w;
+    for (; p + 24 < P; p += 32) {
+      a0 += part[(long long)p * N + col];
+      a1 += part[(long long)(p + 8) * N + col];
+      a2 += part[(long long)(p + 16) * N + col];
+      a3 += part[(long long)(p + 24) * N + col];
+    }
+    for (; p < P; p += 8) a0 += part[(long long)p * N + col];
+  }
+  red[w][lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (w == 0 && col < N) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += red[i][lane];
+    out[col] = scale * acc;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ masked MSE
@@ -358,6 +403,7 @@ masked_mse_kernel(const void* __restrict__ y_in, const void* __restrict__ t_in, 
   float acc = 0.f;
   for (int row = warp0; row < M; row += nwarps) {
     const bool valid = mask == nullptr || __ldg(mask + row) != 0;
+#pragma unroll 2
     for (int v = lane; v < nvec; v += 32) {
       float yv[8], tv[8];
       if (valid) {

@@ -206,8 +206,12 @@ static int rmsnorm_bwd_impl(const void* dy, int32_t dy_dtype, const __nv_bfloat1
     rmsnorm_bwd_kernel<false><<<grid, kNormBwdThreads, 0, st>>>(dy, x, rstd, g, int(M), D, rpc, dx, dg_part, db_part);
   }
   TD_CUDA(cudaGetLastError());
-  if (dg) colsum_finish_kernel<<<(D + 255) / 256, 256, 0, st>>>(dg_part, grid, D, scale, dg);
-  if (dxsum) colsum_finish_kernel<<<(D + 255) / 256, 256, 0, st>>>(db_part, grid, D, scale, dxsum);
+  if (dg && dxsum)
+    colsum_finish_kernel<<<dim3((D + 31) / 32, 2), 256, 0, st>>>(dg_part, dg, db_part, dxsum, grid, D, scale);
+  else if (dg)
+    colsum_finish_kernel<<<dim3((D + 31) / 32, 1), 256, 0, st>>>(dg_part, dg, nullptr, nullptr, grid, D, scale);
+  else if (dxsum)
+    colsum_finish_kernel<<<dim3((D + 31) / 32, 1), 256, 0, st>>>(db_part, dxsum, nullptr, nullptr, grid, D, scale);
   TD_CUDA(cudaGetLastError());
   return TD_OK;
 }
@@ -384,7 +388,7 @@ int32_t td_aligner_bwd(const void* dy, int32_t dy_dtype, const void* x, const vo
     int rc = launch_gemm<2, false, true, EPI_DGELU>({w.dh2, D, false}, {W2, D, true}, p, 1, st, "gemm_dh0_dgelu");
     if (rc) return rc;
     const int slabs = int((M + 2 * kBlockM - 1) / (2 * kBlockM)) * 2 * 4;  // pair tiles: 2 slabs x 4 warps each
-    colsum_finish_kernel<<<(D + 255) / 256, 256, 0, st>>>(w.db1_part, slabs, D, grad_scale, db1);
+    colsum_finish_kernel<<<dim3((D + 31) / 32, 1), 256, 0, st>>>(w.db1_part, db1, nullptr, nullptr, slabs, D, grad_scale);
     TD_CUDA(cudaGetLastError());
     // dW1[D, Din] = dh0^T . x
     memset(&p, 0, sizeof(p));
