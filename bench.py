@@ -141,7 +141,7 @@ def cpu_reference_run(steps: int, warmup: int, max_tokens: int = 2048):
             "ms_per_step": dt / steps * 1e3, "tokens_per_step": tokens}
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -153,7 +153,7 @@ def run_reference_arm(args):
             "config": workload_config(args.gpus),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(n):
@@ -175,8 +175,19 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after backward instead of overlapped")
     ap.add_argument("--profile-out", default="", help="write the per-kernel table (JSON) here")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON); anything a library prints there meanwhile (e.g. NCCL's version
+    # banner) is diverted to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -320,7 +331,7 @@ def main():
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
             with open(args.profile_out, "w") as f:
                 json.dump({"kernels": kernels, "kernel_ms_per_step": total_ms, "ms_per_step": ms / steps, "peaks": peaks}, f, indent=1)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -1,0 +1,91 @@
+"""Multi-GPU (NCCL) data-parallel parity: world-size-2 run of the real kernels with the built-in bucketed all-reduce
+(overlapped and not) must equal the mean of the per-shard oracle gradients (DDP semantics). Skipped with < 2 GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DIN, D, SEQS = 192, 512, 6
+NAMES = ("dW1", "db1", "dW2", "db2", "dg")
+KEYS = ("0.weight", "0.bias", "2.weight", "2.bias", "3.weight")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _batch():
+    rng = np.random.RandomState(7)
+    lens = [40, 7, 130, 64, 1, 99]
+    xs = [torch.from_numpy(rng.standard_normal((n, DIN)).astype(np.float32)).to(torch.bfloat16) for n in lens]
+    ts = [torch.from_numpy(rng.standard_normal((n, D)).astype(np.float32)) for n in lens]
+    return xs, ts
+
+
+def _worker(rank, world, port, overlap, ret):
+    import torch.distributed as dist
+
+    import thinkdiff_mlre_b200 as td
+    from oracle import aligner_ref
+    from thinkdiff_mlre_b200.sharding import shard_bounds
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        m = td.ThinkDiffAligner(DIN, D).cuda()
+        m.load_state_dict(aligner_ref.init_params_numpy(DIN, D, seed=3))
+        m.enable_data_parallel(overlap=overlap)
+        xs, ts = _batch()
+        lo, hi = shard_bounds(SEQS, world, rank)
+        x, t = torch.cat(xs[lo:hi]).cuda(), torch.cat(ts[lo:hi]).cuda()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = m.forward_packed(x)
+        loss, dy = td.ops.masked_mse_fwd_bwd(y, t)  # this rank's OWN mean loss
+        y.backward(dy)
+        torch.cuda.synchronize()
+        if rank == 0:
+            ret.put([p.grad.float().cpu().numpy() for p in m.parameters()])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_two_gpu_bucketed_allreduce_equals_oracle_mean(overlap):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    from oracle import aligner_ref
+    from thinkdiff_mlre_b200.sharding import shard_bounds
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, overlap, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = ret.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    params = aligner_ref.init_params_numpy(DIN, D, seed=3)
+    xs, ts = _batch()
+    want = None
+    for r in range(world):
+        lo, hi = shard_bounds(SEQS, world, r)
+        x, t = torch.cat(xs[lo:hi]).float(), torch.cat(ts[lo:hi])
+        fwd = aligner_ref.aligner_fwd_bwd_manual(x, params, regime="bf16")
+        out = aligner_ref.aligner_fwd_bwd_manual(x, params, dy=2 * (fwd["y"] - t) / t.numel(), regime="bf16")
+        g = [out[n] / world for n in NAMES]
+        want = g if want is None else [a + b for a, b in zip(want, g)]
+    for a, b, n in zip(got, want, NAMES):
+        err = np.linalg.norm(a - b.numpy()) / np.linalg.norm(b.numpy())
+        assert err < 2e-2, (n, err)
