@@ -75,6 +75,22 @@ int32_t td_aligner_bwd(const void* dy, int32_t dy_dtype, const void* x, const vo
                        float grad_scale, float* dW1, float* db1, float* dW2, float* db2, float* dg, void* workspace,
                        int64_t workspace_bytes, int32_t phases, td_stream_t stream);
 
+/* Fused training path against T5 targets (masked MSE over all M packed rows): forward GEMMs, then ONE pass that forms
+ * y = T5LayerNorm(h2) in registers, accumulates sum (y - target)^2 and writes the norm backward of dy = 2 (y - target) / (M D)
+ * -- y and dy never touch HBM. Outputs for a UNIT upstream gradient: dh2 bf16 [M, D], dg_unit / db2_unit fp32 [D], and the
+ * loss (fp32 device scalar). td_aligner_bwd_dh2 finishes the backward, multiplying by grad_scale * (*grad_scale_ptr)
+ * (grad_scale_ptr: optional DEVICE scalar = the upstream gradient of the loss, e.g. GradScaler's scale; no host sync).
+ * Same gradients as td_aligner_fwd -> td_masked_mse_fwd_bwd -> td_aligner_bwd (base_task.py:237-244 with an MSE loss). */
+int64_t td_aligner_mse_fwd_workspace_bytes(int64_t M, int32_t Din, int32_t D);
+int32_t td_aligner_mse_fwd(const void* x, int64_t M, int32_t Din, int32_t D, const void* W1, const void* b1, const void* W2,
+                           const void* b2, const float* g, float eps, const void* target, int32_t target_dtype, void* h0,
+                           void* h1, void* dh2, float* dg_unit, float* db2_unit, float* loss, void* workspace,
+                           int64_t workspace_bytes, td_stream_t stream);
+int32_t td_aligner_bwd_dh2(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
+                           const float* dg_unit, const float* db2_unit, int64_t M, int32_t Din, int32_t D, float grad_scale,
+                           const float* grad_scale_ptr, float* dW1, float* db1, float* dW2, float* db2, float* dg,
+                           void* workspace, int64_t workspace_bytes, int32_t phases, td_stream_t stream);
+
 /* Standalone T5LayerNorm forward / backward (transformers modeling_t5.py T5LayerNorm, imported at
  * ...embed_decoder_2.py:24). x bf16 [M, D]; y fp32 or bf16; dW/db are fp32 [D]; db = column sums of dx (may be NULL). */
 int32_t td_rmsnorm_fwd(const void* x, const float* g, float eps, int64_t M, int32_t D, void* y, int32_t y_dtype,

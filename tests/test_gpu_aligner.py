@@ -333,3 +333,33 @@ def test_weights_are_recast_after_a_fused_optimizer_step():
         m[0].weight.mul_(2.0)  # in-place edit bumps the version: the eval cache must notice
         y2 = m(x)
     assert torch.equal(y1, y.detach()) and not torch.equal(y1, y2)
+
+
+@pytest.mark.parametrize("M,tdt", [(1, torch.float32), (200, torch.bfloat16), (515, torch.float32)])
+def test_fused_mse_path_equals_module_boundary_path_and_oracle(M, tdt):
+    """aligner.mse_loss_packed (y / dy never in HBM) vs forward -> masked_mse -> backward, and vs the closed-form oracle;
+    the upstream scalar (GradScaler) is applied on the device."""
+    import thinkdiff_mlre_b200 as td
+    from oracle import aligner_ref
+
+    m, params = make_module(192, 512, seed=21)
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn((M, 192), generator=g).to(torch.bfloat16).cuda()
+    t = torch.randn((M, 512), generator=g).to(tdt).cuda()
+    # unfused, through the module boundary
+    y, loss_ref_path, grads_ref = run_train(m, x, t.float())
+    grads_ref = {k: v.clone() for k, v in grads_ref.items()}
+    # fused
+    m.zero_grad(set_to_none=True)
+    loss = m.mse_loss_packed(x, t)
+    scale = torch.tensor(1024.0, device="cuda")
+    (loss * scale).backward()
+    assert abs(float(loss) - float(loss_ref_path)) < 1e-5 * abs(float(loss_ref_path))
+    for k, p in m.named_parameters():
+        assert rel(p.grad / 1024.0, grads_ref[k].cpu()) < 2e-3, k  # same kernels bar the fused norm pass
+    fwd = aligner_ref.aligner_fwd_bwd_manual(x.float().cpu(), params, regime="bf16")
+    out = aligner_ref.aligner_fwd_bwd_manual(x.float().cpu(), params, dy=2 * (fwd["y"] - t.float().cpu()) / t.numel(), regime="bf16")
+    for k in PARAM_KEYS:
+        assert rel(dict(m.named_parameters())[k].grad / 1024.0, out[ORACLE_NAME[k]]) < BF16_RTOL, k
+    ref_loss = float(((fwd["y"] - t.float().cpu()) ** 2).mean())
+    assert abs(float(loss) - ref_loss) < 1e-3 * ref_loss

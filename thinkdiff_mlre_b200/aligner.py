@@ -111,18 +111,48 @@ class _AlignerFn(torch.autograd.Function):
             dy = dy.float()
         bwd = ops.AlignerBackward(x2d, (h0, h1, h2, rstd), W2b, gf, dy.contiguous(), grad_scale=scale)
         gb = GradBuckets(Din, D, dev)
-        bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg)
-        works = []
-        if dp is not None and dp.world > 1 and dp.overlap:
-            works.append(dp.all_reduce_async(gb.linear2))  # rides NVLink while the next two GEMMs run
-        bwd.gelu_and_linear1(gb.dW1, gb.db1)
-        if dp is not None and dp.world > 1:
-            if not dp.overlap:
-                works.append(dp.all_reduce_async(gb.linear2))
-            works.append(dp.all_reduce_async(gb.linear1))
-            for w in works:
-                w.wait()  # stream-level wait: the compute stream orders after the NCCL stream, the host does not block
+        _reduce_and_return(dp, gb, lambda: bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg), lambda: bwd.gelu_and_linear1(gb.dW1, gb.db1))
         return (None, *gb.in_parameter_order(), None, None)
+
+
+def _reduce_and_return(dp, gb, run_phase1, run_phase2):
+    """Shared backward schedule: phase 1 (Linear2 / norm gradients) -> start its all-reduce -> phase 2 (Linear1
+    gradients, overlapping the first all-reduce) -> all-reduce the second bucket -> stream-level waits."""
+    run_phase1()
+    works = []
+    if dp is not None and dp.world > 1 and dp.overlap:
+        works.append(dp.all_reduce_async(gb.linear2))  # rides NVLink while the next two GEMMs run
+    run_phase2()
+    if dp is not None and dp.world > 1:
+        if not dp.overlap:
+            works.append(dp.all_reduce_async(gb.linear2))
+        works.append(dp.all_reduce_async(gb.linear1))
+        for w in works:
+            w.wait()  # the compute stream orders after the NCCL stream; the host does not block
+
+
+class _AlignerMSEFn(torch.autograd.Function):
+    """loss = mean((aligner(x) - target)^2) with y / dy never materialised (td_aligner_mse_fwd / td_aligner_bwd_dh2)."""
+
+    @staticmethod
+    def forward(ctx, x2d, target, W1, b1, W2, b2, g, module):
+        W1b, b1b, W2b, b2b = module._bf16_params()
+        gf = g.detach() if g.dtype == torch.float32 else g.detach().float()
+        loss, saved = ops.aligner_mse_fwd(x2d, W1b, b1b, W2b, b2b, gf, module.eps, target)
+        ctx.save_for_backward(x2d, W2b, *saved)
+        ctx.module = module
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        x2d, W2b, h0, h1, dh2, dg_unit, db2_unit = ctx.saved_tensors
+        module = ctx.module
+        dp = module._dp
+        scale = 1.0 / dp.world if dp is not None else 1.0
+        bwd = ops.AlignerBackwardFromDh2(x2d, (h0, h1, dh2, dg_unit, db2_unit), W2b, grad_loss, grad_scale=scale)
+        gb = GradBuckets(x2d.shape[1], W2b.shape[0], x2d.device)
+        _reduce_and_return(dp, gb, lambda: bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg), lambda: bwd.gelu_and_linear1(gb.dW1, gb.db1))
+        return (None, None, *gb.in_parameter_order(), None)
 
 
 class ThinkDiffAligner(nn.Sequential):
@@ -209,6 +239,24 @@ class ThinkDiffAligner(nn.Sequential):
                 gf = g.detach() if g.dtype == torch.float32 else g.detach().float()
                 y, _ = ops.aligner_fwd(x2d, W1b, b1b, W2b, b2b, gf, self.eps, regime == "bf16_infer", False)
         return y.reshape(*lead, self.hidden_size)
+
+    def mse_loss_packed(self, x_packed: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """``F.mse_loss(self.forward_packed(x_packed).float(), target.float())`` as ONE fused training path: the norm
+        output y and its gradient are formed in registers, never written to HBM. Training regime only (fp32 parameters,
+        bf16 compute, as under ``torch.autocast('cuda', dtype=torch.bfloat16)``); differentiable w.r.t. the parameters and
+        compatible with a GradScaler (the upstream scalar is applied on the device inside the backward GEMM epilogues)."""
+        if self[0].weight.dtype != torch.float32:
+            raise TypeError("mse_loss_packed is the training path: parameters must be float32 masters")
+        if x_packed.dim() != 2 or x_packed.shape[1] != self.mm_hidden_size or x_packed.shape[0] == 0:
+            raise ValueError(f"x_packed must be [M > 0, {self.mm_hidden_size}], got {tuple(x_packed.shape)}")
+        if x_packed.requires_grad:
+            raise NotImplementedError("no dx path: the reference never differentiates the aligner w.r.t. its input features")
+        x2d = x_packed.to(torch.bfloat16).contiguous()
+        if target.dtype not in (torch.float32, torch.bfloat16):
+            target = target.float()
+        w1, b1, w2, b2, g = self[0].weight, self[0].bias, self[2].weight, self[2].bias, self[3].weight
+        with torch.autocast("cuda", enabled=False):
+            return _AlignerMSEFn.apply(x2d, target.contiguous(), w1, b1, w2, b2, g, self)
 
     def forward_packed(self, x_packed: torch.Tensor, cu_seqlens: torch.Tensor | None = None) -> torch.Tensor:
         """Ragged entry point: ``x_packed[M, Din]`` (rows of all sequences back to back, ``cu_seqlens`` int32 [B+1]).

@@ -24,7 +24,7 @@ enum EpiKind : int {
   EPI_BF16 = 0,       // out0 = bf16(acc + bias?)
   EPI_BIAS_GELU = 1,  // out0 = h0 = bf16(acc + bias); out1 = bf16(gelu(h0))
   EPI_BIAS_SSQ = 2,   // out0 = h2 = bf16(acc + bias); red0[2 * n_blk + half][row] = sum over 128 cols of h2^2
-  EPI_DGELU = 3,      // t = bf16(acc); out0 = bf16(t * gelu'(aux0)); red0[m_slab][col] = sum_rows out0
+  EPI_DGELU = 3,      // t = bf16(alpha * acc); out0 = bf16(t * gelu'(aux0)); red0[m_slab][col] = sum_rows out0
   EPI_F32 = 4,        // out0(fp32) = alpha * acc   (splits > 1: red.add into a zeroed out0)
 };
 
@@ -39,6 +39,7 @@ struct GemmParams {
   float* red0;
   long long ld_out;  // elements
   float alpha;
+  const float* alpha_ptr;  // optional device scalar multiplied into alpha (upstream loss gradient / GradScaler scale)
 };
 
 constexpr int kBlockM = 128;  // rows per CTA (TMEM lanes)
@@ -82,6 +83,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
   const uint32_t taddr = tmem_acc + (uint32_t(quarter * 32) << 16) + half * kEpiColsPerWarp;
   const long long row_off = (long long)row * p.ld_out;
   float ssq = 0.f;
+  float alpha = p.alpha;
+  if constexpr (EPI == EPI_F32 || EPI == EPI_DGELU) {
+    if (p.alpha_ptr != nullptr) alpha *= __ldg(p.alpha_ptr);
+  }
 
   // software prefetch of the saved pre-activation (EPI_DGELU): chunk c+1 is in flight while chunk c is computed
   uint4 aux_next[4];
@@ -118,16 +123,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
         if (p.splits == 1) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(p.alpha * __uint_as_float(v[j]), p.alpha * __uint_as_float(v[j + 1]),
-                                   p.alpha * __uint_as_float(v[j + 2]), p.alpha * __uint_as_float(v[j + 3]));
+            float4 o = make_float4(alpha * __uint_as_float(v[j]), alpha * __uint_as_float(v[j + 1]),
+                                   alpha * __uint_as_float(v[j + 2]), alpha * __uint_as_float(v[j + 3]));
             *reinterpret_cast<float4*>(out + j) = o;
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + j),
-                         "f"(p.alpha * __uint_as_float(v[j])), "f"(p.alpha * __uint_as_float(v[j + 1])),
-                         "f"(p.alpha * __uint_as_float(v[j + 2])), "f"(p.alpha * __uint_as_float(v[j + 3]))
+                         "f"(alpha * __uint_as_float(v[j])), "f"(alpha * __uint_as_float(v[j + 1])),
+                         "f"(alpha * __uint_as_float(v[j + 2])), "f"(alpha * __uint_as_float(v[j + 3]))
                          : "memory");
           }
         }
@@ -142,7 +147,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
         unpack8(aux[q], x);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float t = bf16_round(__uint_as_float(v[q * 8 + j]));
+          const float t = bf16_round(alpha * __uint_as_float(v[q * 8 + j]));
           h[j] = row_ok ? bf16_round(t * gelu_grad_fast(x[j])) : 0.f;
           colsum[q * 8 + j] = h[j];
         }

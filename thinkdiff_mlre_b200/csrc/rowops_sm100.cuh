@@ -329,12 +329,146 @@ rmsnorm_bwd_kernel(const void* __restrict__ dy_in, const __nv_bfloat16* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------ fused norm + MSE + norm-backward
+// rstd[row] = rsqrt(mean(h2^2) + eps) from the GEMM2 epilogue's per-half-tile partial sums ssq_part[P][M].
+__global__ void __launch_bounds__(256)
+rstd_from_partials_kernel(const float* __restrict__ ssq_part, int P, int M, int D, float eps, float* __restrict__ rstd) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  float ssq = 0.f;
+  for (int p = 0; p < P; ++p) ssq += ssq_part[(long long)p * M + row];
+  rstd[row] = rsqrtf(ssq / float(D) + eps);
+}
+
+// Training against T5 targets never needs y or dy in memory: with y = g * h2 * rstd,
+//   diff = y - t;  loss += diff^2;  dy = (2 / (M D)) diff;  then the T5LayerNorm backward of dy, all per row in registers.
+// Same CTA organisation as rmsnorm_bwd_kernel (thread = 8 columns, R rows per block reduction). dh2 / dg / db2 are written
+// for a unit upstream gradient; the backward GEMMs multiply by the (device-resident) upstream scalar.
+// HBM traffic per token: h2 8 KB + target 8 KB (bf16) read, dh2 8 KB written -- instead of the 96 KB of the three
+// separate passes (norm fwd 24 KB, MSE 40 KB, norm bwd 32 KB).
+template <bool T_BF16>
+__global__ void __launch_bounds__(kNormBwdThreads)
+norm_mse_bwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restrict__ rstd_in, const float* __restrict__ g,
+                    const void* __restrict__ t_in, int M, int D, int rows_per_cta, float dy_coef,
+                    __nv_bfloat16* __restrict__ dh2, float* __restrict__ dg_part, float* __restrict__ db2_part,
+                    float* __restrict__ loss_part) {
+  constexpr int R = kNormBwdRows;
+  __shared__ float red[R][kNormBwdThreads / 32];
+  __shared__ float tot[R];
+  __shared__ float lred[kNormBwdThreads / 32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const bool col_ok = t * 8 < D;
+  const int row_begin = blockIdx.x * rows_per_cta;
+  const int row_end = min(M, row_begin + rows_per_cta);
+  float gg[8], adg[8], adb[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { gg[q] = col_ok ? g[t * 8 + q] : 0.f; adg[q] = 0.f; adb[q] = 0.f; }
+  const float inv_d = 1.0f / float(D);
+  float loss_acc = 0.f;
+
+  for (int r0 = row_begin; r0 < row_end; r0 += R) {
+    float dyv[R][8], hv[R][8], part[R], rs[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = r0 + r;
+      const bool ok = col_ok && row < row_end;
+      uint4 hu = make_uint4(0, 0, 0, 0);
+      float tv[8];
+      if (ok) hu = ld_stream(reinterpret_cast<const uint4*>(h2 + (long long)row * D) + t);
+      if constexpr (T_BF16) {
+        uint4 tu = make_uint4(0, 0, 0, 0);
+        if (ok) tu = ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(t_in) + (long long)row * D) + t);
+        const uint32_t tw[4] = {tu.x, tu.y, tu.z, tu.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { tv[2 * q] = bf16lo(tw[q]); tv[2 * q + 1] = bf16hi(tw[q]); }
+      } else {
+        uint4 t0 = make_uint4(0, 0, 0, 0), t1 = t0;
+        if (ok) {
+          const uint4* tp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(t_in) + (long long)row * D) + 2 * t;
+          t0 = ld_stream(tp);
+          t1 = ld_stream(tp + 1);
+        }
+        tv[0] = __uint_as_float(t0.x); tv[1] = __uint_as_float(t0.y); tv[2] = __uint_as_float(t0.z); tv[3] = __uint_as_float(t0.w);
+        tv[4] = __uint_as_float(t1.x); tv[5] = __uint_as_float(t1.y); tv[6] = __uint_as_float(t1.z); tv[7] = __uint_as_float(t1.w);
+      }
+      rs[r] = (row < row_end) ? __ldg(rstd_in + row) : 0.f;
+      const uint32_t hw[4] = {hu.x, hu.y, hu.z, hu.w};
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { hv[r][2 * q] = bf16lo(hw[q]); hv[r][2 * q + 1] = bf16hi(hw[q]); }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float diff = ok ? gg[q] * (hv[r][q] * rs[r]) - tv[q] : 0.f;
+        loss_acc = fmaf(diff, diff, loss_acc);
+        dyv[r][q] = dy_coef * diff;
+        s = fmaf(gg[q] * dyv[r][q], hv[r][q], s);
+      }
+      part[r] = warp_sum(s);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) red[r][w] = part[r];
+    }
+    __syncthreads();
+    if (w < R) {
+      float v = lane < kNormBwdThreads / 32 ? red[w][lane] : 0.f;
+      v = warp_sum(v);
+      if (lane == 0) tot[w] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = r0 + r;
+      if (row < row_end && col_ok) {
+        const float rstd = rs[r];
+        const float c = tot[r] * inv_d * rstd * rstd * rstd;
+        float o[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          o[q] = bf16_round(rstd * gg[q] * dyv[r][q] - hv[r][q] * c);
+          adb[q] += o[q];
+          adg[q] = fmaf(dyv[r][q] * hv[r][q], rstd, adg[q]);
+        }
+        st_stream(reinterpret_cast<uint4*>(dh2 + (long long)row * D) + t,
+                  make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                             pack_bf16x2(o[6], o[7])));
+      }
+    }
+  }
+  if (col_ok) {
+    float4* pg = reinterpret_cast<float4*>(dg_part + (long long)blockIdx.x * D) + 2 * t;
+    float4* pb = reinterpret_cast<float4*>(db2_part + (long long)blockIdx.x * D) + 2 * t;
+    pg[0] = make_float4(adg[0], adg[1], adg[2], adg[3]);
+    pg[1] = make_float4(adg[4], adg[5], adg[6], adg[7]);
+    pb[0] = make_float4(adb[0], adb[1], adb[2], adb[3]);
+    pb[1] = make_float4(adb[4], adb[5], adb[6], adb[7]);
+  }
+  loss_acc = warp_sum(loss_acc);
+  if (lane == 0) lred[w] = loss_acc;
+  __syncthreads();
+  if (t == 0) {
+    float tot_loss = 0.f;
+    for (int i = 0; i < kNormBwdThreads / 32; ++i) tot_loss += lred[i];
+    loss_part[blockIdx.x] = tot_loss;
+  }
+}
+
+// out[i] = scale * (*scale_ptr) * in[i]   (applies the upstream loss gradient, resident on the device, to dg / db2)
+__global__ void scale_vec_kernel(const float* __restrict__ in0, float* __restrict__ out0, const float* __restrict__ in1,
+                                 float* __restrict__ out1, int n, float scale, const float* __restrict__ scale_ptr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float a = scale * (scale_ptr ? __ldg(scale_ptr) : 1.f);
+  out0[i] = a * in0[i];
+  if (in1 != nullptr) out1[i] = a * in1[i];
+}
+
 // out[n] = scale * sum_p part[p][n]   (fixed order -> deterministic). One CTA per 32 columns; warp w adds rows
 // p = w, w + 8, ... (4 independent loads in flight), then the 8 warp sums are combined in warp order.
 // blockIdx.y selects one of up to two (part, out) pairs so that dg and db2 finish in one launch.
 __global__ void __launch_bounds__(256)
 colsum_finish_kernel(const float* __restrict__ part0, float* __restrict__ out0, const float* __restrict__ part1,
-                     float* __restrict__ out1, int P, int N, float scale) {
+                     float* __restrict__ out1, int P, int N, float scale, const float* __restrict__ scale_ptr = nullptr) {
   __shared__ float red[8][33];
   const float* part = blockIdx.y ? part1 : part0;
   float* out = blockIdx.y ? out1 : out0;
@@ -357,7 +491,7 @@ colsum_finish_kernel(const float* __restrict__ part0, float* __restrict__ out0, 
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc += red[i][lane];
-    out[col] = scale * acc;
+    out[col] = scale * (scale_ptr ? __ldg(scale_ptr) : 1.f) * acc;
   }
 }
 

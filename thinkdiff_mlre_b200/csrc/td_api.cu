@@ -343,6 +343,53 @@ int64_t td_aligner_bwd_workspace_bytes(int64_t M, int32_t Din, int32_t D) {
   return (int64_t)carve_bwd(nullptr, M, D).bytes;
 }
 
+namespace {
+// Backward from dh2 (already in the workspace or caller-provided): dW2 GEMM | dh0 GEMM + db1 + dW1 GEMM.
+int bwd_from_dh2(const __nv_bfloat16* dh2, const void* x, const void* h0, const void* h1, const void* W2, int64_t M,
+                 int32_t Din, int32_t D, float scale, const float* scale_ptr, float* dW1, float* db1, float* dW2,
+                 BwdWorkspace& w, int32_t phases, cudaStream_t st) {
+  GemmParams p;
+  if (phases & TD_BWD_PHASE_NORM_W2) {
+    // dW2[D, D] = scale * dh2^T . h1  (contraction over tokens; both operands MN-major)
+    memset(&p, 0, sizeof(p));
+    p.M = D; p.N = D; p.K = int(M); p.ld_out = D; p.alpha = scale; p.alpha_ptr = scale_ptr; p.out0 = dW2;
+    int rc = launch_gemm<2, true, true, EPI_F32>({dh2, D, true}, {h1, D, true}, p, 0, st, "gemm_dW2");
+    if (rc) return rc;
+  }
+  if (phases & TD_BWD_PHASE_GELU_W1) {
+    // dh0 = bf16( bf16(scale_ptr * dh2 . W2) * gelu'(h0) ), plus per-slab column sums for db1
+    memset(&p, 0, sizeof(p));
+    p.M = int(M); p.N = D; p.K = D; p.ld_out = D; p.alpha = 1.f; p.alpha_ptr = scale_ptr;
+    p.out0 = w.dh0; p.aux0 = h0; p.red0 = w.db1_part;
+    int rc = launch_gemm<2, false, true, EPI_DGELU>({dh2, D, false}, {W2, D, true}, p, 1, st, "gemm_dh0_dgelu");
+    if (rc) return rc;
+    const int slabs = int((M + 2 * kBlockM - 1) / (2 * kBlockM)) * 2 * 4;  // pair tiles: 2 slabs x 4 warps each
+    colsum_finish_kernel<<<dim3((D + 31) / 32, 1), 256, 0, st>>>(w.db1_part, db1, nullptr, nullptr, slabs, D, scale);
+    TD_CUDA(cudaGetLastError());
+    // dW1[D, Din] = scale * dh0^T . x   (dh0 already carries the upstream scalar)
+    memset(&p, 0, sizeof(p));
+    p.M = D; p.N = Din; p.K = int(M); p.ld_out = Din; p.alpha = scale; p.out0 = dW1;
+    rc = launch_gemm<2, true, true, EPI_F32>({w.dh0, D, true}, {x, Din, true}, p, 0, st, "gemm_dW1");
+    if (rc) return rc;
+  }
+  return TD_OK;
+}
+
+int zero_grads(int32_t Din, int32_t D, float* dW1, float* db1, float* dW2, float* db2, float* dg, int32_t phases,
+               cudaStream_t st) {
+  if (phases & TD_BWD_PHASE_NORM_W2) {
+    TD_CUDA(cudaMemsetAsync(dW2, 0, sizeof(float) * (size_t)D * D, st));
+    TD_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * D, st));
+    TD_CUDA(cudaMemsetAsync(dg, 0, sizeof(float) * D, st));
+  }
+  if (phases & TD_BWD_PHASE_GELU_W1) {
+    TD_CUDA(cudaMemsetAsync(dW1, 0, sizeof(float) * (size_t)D * Din, st));
+    TD_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * D, st));
+  }
+  return TD_OK;
+}
+}  // namespace
+
 int32_t td_aligner_bwd(const void* dy, int32_t dy_dtype, const void* x, const void* h0, const void* h1, const void* h2,
                        const float* rstd, const void* W2, const float* g, int64_t M, int32_t Din, int32_t D,
                        float grad_scale, float* dW1, float* db1, float* dW2, float* db2, float* dg, void* ws,
@@ -351,52 +398,99 @@ int32_t td_aligner_bwd(const void* dy, int32_t dy_dtype, const void* x, const vo
   if (!dims_ok(Din, D)) TD_FAIL(TD_ERR_UNSUPPORTED, "td_aligner_bwd: Din=%d, D=%d must be multiples of 64 (D <= 4096)", Din, D);
   if (M < 0 || M > 0x7fffffffll / D) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd: M=%lld out of range", (long long)M);
   cudaStream_t st = (cudaStream_t)stream;
-  if (M == 0) {  // empty shard: gradients are exact zeros
-    if (phases & TD_BWD_PHASE_NORM_W2) {
-      TD_CUDA(cudaMemsetAsync(dW2, 0, sizeof(float) * (size_t)D * D, st));
-      TD_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * D, st));
-      TD_CUDA(cudaMemsetAsync(dg, 0, sizeof(float) * D, st));
-    }
-    if (phases & TD_BWD_PHASE_GELU_W1) {
-      TD_CUDA(cudaMemsetAsync(dW1, 0, sizeof(float) * (size_t)D * Din, st));
-      TD_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * D, st));
-    }
-    return TD_OK;
-  }
+  if (M == 0) return zero_grads(Din, D, dW1, db1, dW2, db2, dg, phases, st);  // empty shard: exact zeros
   if (ws_bytes < td_aligner_bwd_workspace_bytes(M, Din, D)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd: workspace too small");
   BwdWorkspace w = carve_bwd(ws, M, D);
-  GemmParams p;
-
   if (phases & TD_BWD_PHASE_NORM_W2) {
     if (!dy || !h1 || !h2 || !rstd || !g || !dW2 || !db2 || !dg) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd: null pointer (phase 1)");
     // T5LayerNorm backward -> dh2 (bf16), dg, db2
     int rc = rmsnorm_bwd_impl(dy, dy_dtype, static_cast<const __nv_bfloat16*>(h2), rstd, g, M, D, w.dh2, dg, db2, grad_scale,
                               w.norm_ws, st);
     if (rc) return rc;
-    // dW2[D, D] = dh2^T . h1  (contraction over tokens; both operands MN-major)
-    memset(&p, 0, sizeof(p));
-    p.M = D; p.N = D; p.K = int(M); p.ld_out = D; p.alpha = grad_scale; p.out0 = dW2;
-    rc = launch_gemm<2, true, true, EPI_F32>({w.dh2, D, true}, {h1, D, true}, p, 0, st, "gemm_dW2");
-    if (rc) return rc;
   }
-  if (phases & TD_BWD_PHASE_GELU_W1) {
-    if (!x || !h0 || !W2 || !dW1 || !db1) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd: null pointer (phase 2)");
-    // dh0 = bf16( bf16(dh2 . W2) * gelu'(h0) ), plus per-slab column sums for db1
-    memset(&p, 0, sizeof(p));
-    p.M = int(M); p.N = D; p.K = D; p.ld_out = D; p.alpha = 1.f;
-    p.out0 = w.dh0; p.aux0 = h0; p.red0 = w.db1_part;
-    int rc = launch_gemm<2, false, true, EPI_DGELU>({w.dh2, D, false}, {W2, D, true}, p, 1, st, "gemm_dh0_dgelu");
-    if (rc) return rc;
-    const int slabs = int((M + 2 * kBlockM - 1) / (2 * kBlockM)) * 2 * 4;  // pair tiles: 2 slabs x 4 warps each
-    colsum_finish_kernel<<<dim3((D + 31) / 32, 1), 256, 0, st>>>(w.db1_part, db1, nullptr, nullptr, slabs, D, grad_scale);
-    TD_CUDA(cudaGetLastError());
-    // dW1[D, Din] = dh0^T . x
-    memset(&p, 0, sizeof(p));
-    p.M = D; p.N = Din; p.K = int(M); p.ld_out = Din; p.alpha = grad_scale; p.out0 = dW1;
-    rc = launch_gemm<2, true, true, EPI_F32>({w.dh0, D, true}, {x, Din, true}, p, 0, st, "gemm_dW1");
-    if (rc) return rc;
+  if ((phases & TD_BWD_PHASE_GELU_W1) && (!x || !h0 || !W2 || !dW1 || !db1)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd: null pointer (phase 2)");
+  return bwd_from_dh2(w.dh2, x, h0, h1, W2, M, Din, D, grad_scale, nullptr, dW1, db1, dW2, w, phases, st);
+}
+
+// ------------------------------------------------------------------------------------------------ fused aligner + MSE
+int64_t td_aligner_mse_fwd_workspace_bytes(int64_t M, int32_t Din, int32_t D) {
+  const size_t m = (size_t)(M > 0 ? M : 1);
+  return td_aligner_fwd_workspace_bytes(M, Din, D) + (int64_t)align_up(sizeof(__nv_bfloat16) * m * D, 256) +
+         (int64_t)align_up(sizeof(float) * m, 256) + td_rmsnorm_bwd_workspace_bytes((int64_t)m, D) +
+         (int64_t)align_up(sizeof(float) * ((size_t)device_sm_count() * 2 + 8), 256) + 256;
+}
+
+int32_t td_aligner_mse_fwd(const void* x, int64_t M, int32_t Din, int32_t D, const void* W1, const void* b1,
+                           const void* W2, const void* b2, const float* g, float eps, const void* target,
+                           int32_t target_dtype, void* h0, void* h1, void* dh2, float* dg_unit, float* db2_unit,
+                           float* loss, void* ws, int64_t ws_bytes, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (!dims_ok(Din, D)) TD_FAIL(TD_ERR_UNSUPPORTED, "td_aligner_mse_fwd: Din=%d, D=%d must be multiples of 64 (D <= 4096)", Din, D);
+  if (M <= 0 || M > 0x7fffffffll / D) TD_FAIL(TD_ERR_ARG, "td_aligner_mse_fwd: M=%lld out of range (needs at least one token)", (long long)M);
+  if (!x || !W1 || !W2 || !g || !target || !h0 || !h1 || !dh2 || !dg_unit || !db2_unit || !loss)
+    TD_FAIL(TD_ERR_ARG, "td_aligner_mse_fwd: null pointer");
+  if (ws_bytes < td_aligner_mse_fwd_workspace_bytes(M, Din, D)) TD_FAIL(TD_ERR_ARG, "td_aligner_mse_fwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver c(ws);
+  const int nparts = (D + kEpiColsPerWarp - 1) / kEpiColsPerWarp;
+  float* ssq_part = c.take<float>((size_t)(2 * ((D + kBlockN - 1) / kBlockN)) * (size_t)M);
+  __nv_bfloat16* h2 = c.take<__nv_bfloat16>((size_t)M * D);
+  float* rstd = c.take<float>((size_t)M);
+  int rpc;
+  const int grid = norm_bwd_grid(M, &rpc);
+  float* dg_part = c.take<float>((size_t)grid * D);
+  float* db_part = c.take<float>((size_t)grid * D);
+  float* loss_part = c.take<float>((size_t)grid);
+  float* meta = c.take<float>(8);
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = int(M); p.N = D; p.K = Din; p.ld_out = D; p.alpha = 1.f;
+  p.out0 = h0; p.out1 = h1; p.bias = static_cast<const __nv_bfloat16*>(b1);
+  int rc = launch_gemm<2, false, false, EPI_BIAS_GELU>({x, Din, false}, {W1, Din, false}, p, 1, st, "gemm_fwd1_bias_gelu");
+  if (rc) return rc;
+  memset(&p, 0, sizeof(p));
+  p.M = int(M); p.N = D; p.K = D; p.ld_out = D; p.alpha = 1.f;
+  p.out0 = h2; p.bias = static_cast<const __nv_bfloat16*>(b2); p.red0 = ssq_part;
+  rc = launch_gemm<2, false, false, EPI_BIAS_SSQ>({h1, D, false}, {W2, D, false}, p, 1, st, "gemm_fwd2_bias_ssq");
+  if (rc) return rc;
+  rstd_from_partials_kernel<<<int((M + 255) / 256), 256, 0, st>>>(ssq_part, nparts, int(M), D, eps, rstd);
+  const float dy_coef = 2.0f / (float(M) * float(D));
+  {
+    ProfScope prof("norm_mse_bwd_fused", double(M) * D * (4.0 + (target_dtype == TD_DTYPE_BF16 ? 2.0 : 4.0)), st);
+    if (target_dtype == TD_DTYPE_BF16)
+      norm_mse_bwd_kernel<true><<<grid, kNormBwdThreads, 0, st>>>(h2, rstd, g, target, int(M), D, rpc, dy_coef,
+                                                                  static_cast<__nv_bfloat16*>(dh2), dg_part, db_part, loss_part);
+    else
+      norm_mse_bwd_kernel<false><<<grid, kNormBwdThreads, 0, st>>>(h2, rstd, g, target, int(M), D, rpc, dy_coef,
+                                                                   static_cast<__nv_bfloat16*>(dh2), dg_part, db_part, loss_part);
   }
+  TD_CUDA(cudaGetLastError());
+  colsum_finish_kernel<<<dim3((D + 31) / 32, 2), 256, 0, st>>>(dg_part, dg_unit, db_part, db2_unit, grid, D, 1.0f);
+  count_valid_kernel<<<1, 32, 0, st>>>(nullptr, M, 0, meta);  // meta[0] = M
+  loss_finish_kernel<<<1, 256, 0, st>>>(loss_part, grid, meta, float(D), loss);
+  TD_CUDA(cudaGetLastError());
   return TD_OK;
+}
+
+int32_t td_aligner_bwd_dh2(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
+                           const float* dg_unit, const float* db2_unit, int64_t M, int32_t Din, int32_t D,
+                           float grad_scale, const float* grad_scale_ptr, float* dW1, float* db1, float* dW2, float* db2,
+                           float* dg, void* ws, int64_t ws_bytes, int32_t phases, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (!dims_ok(Din, D)) TD_FAIL(TD_ERR_UNSUPPORTED, "td_aligner_bwd_dh2: Din=%d, D=%d must be multiples of 64 (D <= 4096)", Din, D);
+  if (M <= 0 || M > 0x7fffffffll / D) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: M=%lld out of range", (long long)M);
+  if (ws_bytes < td_aligner_bwd_workspace_bytes(M, Din, D)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  BwdWorkspace w = carve_bwd(ws, M, D);
+  if (phases & TD_BWD_PHASE_NORM_W2) {
+    if (!dh2 || !h1 || !dg_unit || !db2_unit || !dW2 || !db2 || !dg) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (phase 1)");
+    scale_vec_kernel<<<(D + 255) / 256, 256, 0, st>>>(dg_unit, dg, db2_unit, db2, D, grad_scale, grad_scale_ptr);
+    TD_CUDA(cudaGetLastError());
+  }
+  if ((phases & TD_BWD_PHASE_GELU_W1) && (!x || !h0 || !W2 || !dW1 || !db1)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (phase 2)");
+  return bwd_from_dh2(static_cast<const __nv_bfloat16*>(dh2), x, h0, h1, W2, M, Din, D, grad_scale, grad_scale_ptr, dW1, db1,
+                      dW2, w, phases, st);
 }
 
 // ------------------------------------------------------------------------------------------------ losses

@@ -140,6 +140,62 @@ class AlignerBackward:
         self._call(L.BWD_GELU_W1, dW1, db1, None, None, None)
 
 
+def aligner_mse_fwd(x, W1, b1, W2, b2, g, eps: float, target):
+    """Fused training forward against T5 targets: returns (loss, saved) with saved = (h0, h1, dh2, dg_unit, db2_unit),
+    where dh2 / dg_unit / db2_unit are the T5LayerNorm backward of the MSE gradient for a unit upstream gradient."""
+    _need_cuda(x, W1, W2, g, target)
+    M, Din = x.shape
+    D = W1.shape[0]
+    if target.shape != (M, D):
+        raise ValueError(f"target must be [{M}, {D}], got {tuple(target.shape)}")
+    dev = x.device
+    h0 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+    h1 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+    dh2 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+    dg_unit = torch.empty((D,), dtype=torch.float32, device=dev)
+    db2_unit = torch.empty((D,), dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    ws_bytes = L.lib().td_aligner_mse_fwd_workspace_bytes(M, Din, D)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    L.launch_count += 7
+    L.check(
+        L.lib().td_aligner_mse_fwd(L.ptr(_contig(x, "x")), M, Din, D, L.ptr(W1), L.ptr(b1), L.ptr(W2), L.ptr(b2), L.ptr(g), eps,
+                                   L.ptr(_contig(target, "target")), L.dtype_code(target), L.ptr(h0), L.ptr(h1), L.ptr(dh2),
+                                   L.ptr(dg_unit), L.ptr(db2_unit), L.ptr(loss), L.ptr(ws), ws_bytes, L.stream_ptr()),
+        "td_aligner_mse_fwd",
+    )
+    return loss, (h0, h1, dh2, dg_unit, db2_unit)
+
+
+class AlignerBackwardFromDh2:
+    """Two-phase backward of the fused MSE path: everything is multiplied by grad_scale * upstream (a device scalar)."""
+
+    def __init__(self, x, saved, W2, upstream, grad_scale: float = 1.0):
+        self.x, (self.h0, self.h1, self.dh2, self.dg_unit, self.db2_unit), self.W2 = x, saved, W2
+        self.upstream = None if upstream is None else upstream.reshape(1).to(torch.float32).contiguous()
+        self.M, self.Din = x.shape
+        self.D = W2.shape[0]
+        self.grad_scale = float(grad_scale)
+        self.ws_bytes = L.lib().td_aligner_bwd_workspace_bytes(self.M, self.Din, self.D)
+        self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=x.device)
+
+    def _call(self, phase, dW1, db1, dW2, db2, dg):
+        L.launch_count += 2 if phase == L.BWD_NORM_W2 else 3
+        L.check(
+            L.lib().td_aligner_bwd_dh2(L.ptr(self.dh2), L.ptr(self.x), L.ptr(self.h0), L.ptr(self.h1), L.ptr(self.W2),
+                                       L.ptr(self.dg_unit), L.ptr(self.db2_unit), self.M, self.Din, self.D, self.grad_scale,
+                                       L.ptr(self.upstream), L.ptr(dW1), L.ptr(db1), L.ptr(dW2), L.ptr(db2), L.ptr(dg),
+                                       L.ptr(self.ws), self.ws_bytes, phase, L.stream_ptr()),
+            "td_aligner_bwd_dh2",
+        )
+
+    def norm_and_linear2(self, dW2, db2, dg):
+        self._call(L.BWD_NORM_W2, None, None, dW2, db2, dg)
+
+    def gelu_and_linear1(self, dW1, db1):
+        self._call(L.BWD_GELU_W1, dW1, db1, None, None, None)
+
+
 def rmsnorm_fwd(x: torch.Tensor, g: torch.Tensor, eps: float = 1e-6, out_bf16: bool = False):
     _need_cuda(x, g)
     M, D = x.shape

@@ -45,7 +45,7 @@ def synthetic_lvlm_batch(num_seqs: int, max_len: int, din: int, d: int, seed: in
     if with_target:
         extras["flat_target"] = torch.randn((rows, d), generator=g, dtype=torch.float32).to(torch.bfloat16)
     if pin and torch.cuda.is_available():
-        flat = flat.pin_memory()
+        flat, start, lens = flat.pin_memory(), start.pin_memory(), lens.pin_memory()
         if with_target:
             extras["flat_target"] = extras["flat_target"].pin_memory()
     return FlatBatch(flat, start, lens, int(lens.max()), extras)
@@ -54,19 +54,24 @@ def synthetic_lvlm_batch(num_seqs: int, max_len: int, din: int, d: int, seed: in
 class AlignerTrainStep:
     """One data-parallel training step of the aligner against T5-space targets (masked MSE)."""
 
-    def __init__(self, aligner: ThinkDiffAligner, optimizer=None, loss_scale: float = 1.0):
+    def __init__(self, aligner: ThinkDiffAligner, optimizer=None, loss_scale: float = 1.0, fused_loss: bool = True):
         self.aligner = aligner
         self.optimizer = optimizer
         self.loss_scale = float(loss_scale)  # GradScaler-style static scale (backward is linear in it)
+        self.fused_loss = fused_loss         # True: aligner.mse_loss_packed (y / dy stay on chip); False: module boundary path
 
     def step_device(self, flat, src_row_start, lens_dev, total_rows: int, l_max: int, flat_target) -> torch.Tensor:
         """Inputs already resident in HBM. Returns the (unscaled) loss as a device scalar; nothing syncs the host."""
         packed = pack_device(flat, src_row_start, lens_dev, total_rows, l_max)
         target = ops.pack_varlen(flat_target, src_row_start, packed.cu_seqlens, total_rows)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            y = self.aligner.forward_packed(packed.x, packed.cu_seqlens)
-        loss, dy = ops.masked_mse_fwd_bwd(y, target, None, self.loss_scale)
-        y.backward(dy)
+        if self.fused_loss:
+            loss = self.aligner.mse_loss_packed(packed.x, target)
+            (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
+        else:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = self.aligner.forward_packed(packed.x, packed.cu_seqlens)
+            loss, dy = ops.masked_mse_fwd_bwd(y, target, None, self.loss_scale)
+            y.backward(dy)
         if self.optimizer is not None:
             if self.loss_scale != 1.0:
                 for group in self.optimizer.param_groups:
@@ -74,6 +79,31 @@ class AlignerTrainStep:
             self.optimizer.step()
             self.optimizer.zero_grad(set_to_none=True)
         return loss
+
+    # -- host-fed path with the copy of batch i+1 overlapping the compute of batch i (what the reference's PrefetchLoader
+    #    does on a side stream, thinkdiff/datasets/datasets/dataloader_utils.py:45-118)
+    def prefetch(self, batch: FlatBatch, device="cuda"):
+        """Start the H2D copies of ``batch`` (pinned host memory) on a dedicated copy stream; returns a handle for
+        ``step_prefetched``. Nothing blocks the host."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=device)
+        with torch.cuda.stream(self._copy_stream):
+            flat = batch.flat.to(device, non_blocking=True)
+            tgt = batch.extras["flat_target"].to(device, non_blocking=True)
+            start = batch.src_row_start.to(device, non_blocking=True)
+            lens = batch.lens.to(device, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        return (flat, start, lens, batch.total_rows, batch.l_max, tgt), ready
+
+    def step_prefetched(self, handle) -> torch.Tensor:
+        tensors, ready = handle
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ready)
+        for t in tensors:
+            if isinstance(t, torch.Tensor):
+                t.record_stream(cur)  # allocated on the copy stream, consumed here
+        return self.step_device(*tensors)
 
     def step_host(self, batch: FlatBatch, device="cuda") -> torch.Tensor:
         """Inputs in (pinned) host memory: async H2D of the flat features/targets, then ``step_device``."""
