@@ -159,7 +159,7 @@ def run_reference_arm(args, emit):
 def workload_config(n):
     return {"workload": "ThinkDiff-LVLM aligner train step (BASELINE config 2 per GPU; N=8 = config 3 global batch 512)",
             "seqs_per_gpu": SEQS_PER_GPU, "global_batch": SEQS_PER_GPU * n, "max_len": MAX_LEN, "ragged": "len ~ U{1..256}",
-            "din": DIN, "d": D, "loss": "masked_mse", "optimizer": "AdamW(fused) wd=0.05", "parallelism": f"dp{n}",
+            "din": DIN, "d": D, "loss": "masked_mse", "optimizer": "AdamW wd=0.05", "parallelism": f"dp{n}",
             "l2_policy": f"{NUM_BATCHES} distinct input batches cycled; per-step working set (~1.3 GB) exceeds the 126 MB L2"}
 
 
@@ -174,6 +174,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after backward instead of overlapped")
     ap.add_argument("--profile-out", default="", help="write the per-kernel table (JSON) here")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused: this repo's one-pass AdamW (+ bf16 copies, per-bucket overlap); torch: torch.optim.AdamW(fused=True)")
     ap.add_argument("--loss-path", default="fused", choices=["fused", "module"],
                     help="fused: aligner.mse_loss_packed (y/dy stay on chip); module: forward() -> masked MSE -> backward()")
     args = ap.parse_args()
@@ -214,8 +216,8 @@ def main():
     torch.manual_seed(0)  # identical init on every rank (DDP broadcasts rank 0's; same seed is equivalent)
     aligner = td.ThinkDiffAligner(DIN, D).to(dev)
     if world > 1:
-        aligner.enable_data_parallel(overlap=not args.no_overlap)
-    opt = make_reference_optimizer(aligner)
+        aligner.enable_data_parallel(overlap=not args.no_overlap, defer_wait=args.optimizer == "fused")
+    opt = td.FusedAdamW(aligner, lr=1e-4, weight_decay=0.05) if args.optimizer == "fused" else make_reference_optimizer(aligner)
     stepper = td.AlignerTrainStep(aligner, opt, fused_loss=args.loss_path == "fused")
 
     host = [td.synthetic_lvlm_batch(SEQS_PER_GPU, MAX_LEN, DIN, D, seed=1234 + rank + 1000 * j) for j in range(NUM_BATCHES)]
@@ -327,7 +329,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": dict(workload_config(world), loss_path=args.loss_path), "clocks": clocks.summary(), "e2e": e2e,
+            "data": "synthetic", "config": dict(workload_config(world), loss_path=args.loss_path, optimizer_impl=args.optimizer), "clocks": clocks.summary(), "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_peak": step_tflops / peaks["bf16_tflops_sustained"],
             "step_frac_of_nominal_2250": step_tflops / 2250.0, "tokens_per_step": tokens / steps, "final_loss": final_loss,

@@ -109,6 +109,16 @@ int32_t td_gemm_bf16_f32out(const void* A, int64_t lda, int32_t a_mn_major, cons
                             int32_t b_mn_major, int64_t M, int32_t N, int64_t K, float alpha, float* out,
                             int32_t cta_pair, int32_t splits, td_stream_t stream);
 
+/* ---- optimizer: torch.optim.AdamW semantics (thinkdiff/runners/runner_base.py:122-127), one pass
+ * that reads the (all-reduced) gradient, updates p / exp_avg / exp_avg_sq in place and writes the bf16 compute copy of p.
+ * Arrays below are HOST arrays of `num_tensors` (1..3) entries holding device pointers / sizes; params_bf16 (or its
+ * entries) may be NULL. `step` counts from 1; gradients are multiplied by grad_scale (1 / loss scale) first. */
+int32_t td_adamw_step(int32_t num_tensors, float* const* params /*[host]*/, const float* const* grads /*[host]*/,
+                      float* const* exp_avg /*[host]*/, float* const* exp_avg_sq /*[host]*/,
+                      void* const* params_bf16 /*[host]*/, const int64_t* numel /*[host]*/,
+                      const float* weight_decay /*[host]*/, float lr, float beta1, float beta2, float eps, int64_t step,
+                      float grad_scale, td_stream_t stream);
+
 /* ---- (3) masked losses, forward + gradient in one pass -----------------------------------------------------
  * Cross entropy replaces `CrossEntropyLoss(ignore_index=-100)(lm_logits.view(-1, V), labels.view(-1))`
  * (thinkdiff/models/mllama_vllm_t5_embed_decoder_2.py:241-246; blip_vision_t5_decoder.py:222-227).

@@ -363,3 +363,40 @@ def test_fused_mse_path_equals_module_boundary_path_and_oracle(M, tdt):
         assert rel(dict(m.named_parameters())[k].grad / 1024.0, out[ORACLE_NAME[k]]) < BF16_RTOL, k
     ref_loss = float(((fwd["y"] - t.float().cpu()) ** 2).mean())
     assert abs(float(loss) - ref_loss) < 1e-3 * ref_loss
+
+
+def test_fused_adamw_matches_torch_adamw_and_refreshes_bf16_copies():
+    """td_adamw_step vs torch.optim.AdamW (the reference optimiser, runner_base.py:122-127) over several steps on the
+    same gradients; and the bf16 compute copies it writes must equal a fresh cast of the updated parameters."""
+    import copy
+
+    import thinkdiff_mlre_b200 as td
+    from thinkdiff_mlre_b200.train_step import make_reference_optimizer
+
+    m1, _ = make_module(192, 512, seed=31)
+    m2 = copy.deepcopy(m1)
+    o1 = td.FusedAdamW(m1, lr=1e-3, weight_decay=0.05)
+    o2 = make_reference_optimizer(m2, lr=1e-3, weight_decay=0.05)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for step in range(4):
+        for (k, p1), p2 in zip(m1.named_parameters(), m2.parameters()):
+            p1.grad = torch.randn(p1.shape, generator=g, device="cuda") * 1e-2
+            p2.grad = p1.grad.clone()
+        o1.step(), o2.step()
+        for (k, p1), p2 in zip(m1.named_parameters(), m2.parameters()):
+            torch.testing.assert_close(p1, p2, rtol=2e-6, atol=1e-7, msg=lambda s: f"{k} step {step}: {s}")
+    for buf, p in zip(m1._bf16_buffers(), (m1[0].weight, m1[0].bias, m1[2].weight, m1[2].bias)):
+        assert torch.equal(buf, p.detach().to(torch.bfloat16))
+    # the next training forward must use those copies (no recast) and still be correct
+    from thinkdiff_mlre_b200 import _lib as L
+
+    x = torch.randn(50, 192, device="cuda").to(torch.bfloat16)
+    n0 = L.launch_count
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y1 = m1(x)
+    assert L.launch_count - n0 == 3  # two GEMMs + norm, no cast kernels
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y2 = m2(x)
+    assert rel(y1, y2.float().cpu()) < 1e-3
+    sd = o1.state_dict()
+    assert len(sd["state"]) == 5 and sd["param_groups"][0]["weight_decay"] == 0.05

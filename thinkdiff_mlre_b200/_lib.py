@@ -39,6 +39,7 @@ SIGNATURES = {
     "td_rmsnorm_bwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "td_linear_bf16": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
     "td_gemm_bf16_f32out": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i32, _i64, _f32, _vp, _i32, _i32, _vp]),
+    "td_adamw_step": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_f32), _f32, _f32, _f32, _f32, _i64, _f32, _vp]),
     "td_loss_workspace_bytes": (_i64, [_i64]),
     "td_masked_mse_fwd_bwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _i64, _vp]),
     "td_masked_ce_fwd_bwd": (_i32, [_vp, _i32, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _i64, _vp]),

@@ -60,13 +60,17 @@ class DataParallelState:
     remaining backward GEMMs run on the compute stream.
     """
 
-    def __init__(self, group=None, overlap: bool = True):
+    def __init__(self, group=None, overlap: bool = True, defer_wait: bool = False):
         import torch.distributed as dist
 
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group)
         self.overlap = overlap
+        # defer_wait: backward returns without ordering the compute stream after the all-reduces; the consumer of the
+        # gradients (FusedAdamW, or aligner.wait_grads()) waits bucket by bucket, so the Linear2 update overlaps the
+        # Linear1 all-reduce.
+        self.defer_wait = defer_wait
 
     def all_reduce_async(self, flat):
         return self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
@@ -111,24 +115,30 @@ class _AlignerFn(torch.autograd.Function):
             dy = dy.float()
         bwd = ops.AlignerBackward(x2d, (h0, h1, h2, rstd), W2b, gf, dy.contiguous(), grad_scale=scale)
         gb = GradBuckets(Din, D, dev)
-        _reduce_and_return(dp, gb, lambda: bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg), lambda: bwd.gelu_and_linear1(gb.dW1, gb.db1))
+        _reduce_and_return(module, gb, lambda: bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg), lambda: bwd.gelu_and_linear1(gb.dW1, gb.db1))
         return (None, *gb.in_parameter_order(), None, None)
 
 
-def _reduce_and_return(dp, gb, run_phase1, run_phase2):
+def _reduce_and_return(module, gb, run_phase1, run_phase2):
     """Shared backward schedule: phase 1 (Linear2 / norm gradients) -> start its all-reduce -> phase 2 (Linear1
-    gradients, overlapping the first all-reduce) -> all-reduce the second bucket -> stream-level waits."""
+    gradients, overlapping the first all-reduce) -> all-reduce the second bucket -> stream-level waits (or, with
+    ``defer_wait``, leave the waits to the consumer of each bucket)."""
+    dp = module._dp
     run_phase1()
-    works = []
+    works = {}
     if dp is not None and dp.world > 1 and dp.overlap:
-        works.append(dp.all_reduce_async(gb.linear2))  # rides NVLink while the next two GEMMs run
+        works["linear2"] = dp.all_reduce_async(gb.linear2)  # rides NVLink while the next two GEMMs run
     run_phase2()
     if dp is not None and dp.world > 1:
         if not dp.overlap:
-            works.append(dp.all_reduce_async(gb.linear2))
-        works.append(dp.all_reduce_async(gb.linear1))
-        for w in works:
-            w.wait()  # the compute stream orders after the NCCL stream; the host does not block
+            works["linear2"] = dp.all_reduce_async(gb.linear2)
+        works["linear1"] = dp.all_reduce_async(gb.linear1)
+        if dp.defer_wait:
+            module.wait_grads()  # anything still pending from an earlier backward
+            module._pending = works
+        else:
+            for w in works.values():
+                w.wait()  # the compute stream orders after the NCCL stream; the host does not block
 
 
 class _AlignerMSEFn(torch.autograd.Function):
@@ -151,7 +161,7 @@ class _AlignerMSEFn(torch.autograd.Function):
         scale = 1.0 / dp.world if dp is not None else 1.0
         bwd = ops.AlignerBackwardFromDh2(x2d, (h0, h1, dh2, dg_unit, db2_unit), W2b, grad_loss, grad_scale=scale)
         gb = GradBuckets(x2d.shape[1], W2b.shape[0], x2d.device)
-        _reduce_and_return(dp, gb, lambda: bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg), lambda: bwd.gelu_and_linear1(gb.dW1, gb.db1))
+        _reduce_and_return(module, gb, lambda: bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg), lambda: bwd.gelu_and_linear1(gb.dW1, gb.db1))
         return (None, None, *gb.in_parameter_order(), None)
 
 
@@ -168,7 +178,9 @@ class ThinkDiffAligner(nn.Sequential):
             )
         self.mm_hidden_size, self.hidden_size, self.eps = mm_hidden_size, hidden_size, eps
         self._cache_key = None
-        self._cache = None
+        self._cache = None      # persistent bf16 compute copies of (W1, b1, W2, b2)
+        self._bf16_fresh = False  # set by FusedAdamW: the copies were written by the optimizer step itself
+        self._pending = {}      # bucket name -> in-flight all-reduce (defer_wait mode)
         self._dp: DataParallelState | None = None
         self.fp32_mode = "bf16x3"
 
@@ -178,27 +190,53 @@ class ThinkDiffAligner(nn.Sequential):
         return {"mm_projector_type": FUSED_TYPE}
 
     # -- data parallel (replaces DDP for this module)
-    def enable_data_parallel(self, group=None, overlap: bool = True):
-        self._dp = DataParallelState(group, overlap)
+    def enable_data_parallel(self, group=None, overlap: bool = True, defer_wait: bool = False):
+        self._dp = DataParallelState(group, overlap, defer_wait)
         return self
+
+    BUCKETS = {"linear2": ("2.weight", "2.bias", "3.weight"), "linear1": ("0.weight", "0.bias")}
+
+    def wait_bucket(self, name: str):
+        """Order the current stream after the all-reduce of one gradient bucket (no-op unless ``defer_wait``)."""
+        w = self._pending.pop(name, None)
+        if w is not None:
+            w.wait()
+
+    def wait_grads(self):
+        for name in list(self._pending):
+            self.wait_bucket(name)
 
     def disable_data_parallel(self):
         self._dp = None
         return self
 
-    def _bf16_params(self, allow_cache: bool = False):
-        """bf16 compute copies of the Linear parameters.
-
-        Training casts on every forward, exactly as autocast does (fused optimizers update parameters without bumping
-        ``Tensor._version``, so a version-keyed cache would go stale). Only ``eval()`` + ``no_grad`` inference reuses the
-        copies, keyed on (data_ptr, version) so that ``load_state_dict`` / ``.to()`` still invalidate them."""
+    def _bf16_buffers(self):
         ps = (self[0].weight, self[0].bias, self[2].weight, self[2].bias)
-        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
-        if not allow_cache or key != self._cache_key:
-            with torch.no_grad():
-                self._cache = tuple(p.detach() if p.dtype == torch.bfloat16 else ops.cast_to_bf16(p.detach().contiguous()) for p in ps)
-            self._cache_key = key
+        if self._cache is None or any(b.shape != p.shape or b.device != p.device for b, p in zip(self._cache, ps)):
+            self._cache = tuple(torch.empty(p.shape, dtype=torch.bfloat16, device=p.device) for p in ps)
+            self._cache_key, self._bf16_fresh = None, False
         return self._cache
+
+    def _bf16_params(self, allow_cache: bool = False):
+        """bf16 compute copies of the Linear parameters (persistent buffers).
+
+        Training casts on every forward, exactly as autocast does (torch's fused optimizers update parameters without
+        bumping ``Tensor._version``, so a version-keyed cache would go stale) -- unless this repo's ``FusedAdamW`` wrote
+        the copies itself during its step (``_bf16_fresh``). ``eval()`` + ``no_grad`` inference reuses the copies,
+        keyed on (data_ptr, version) so that ``load_state_dict`` / ``.to()`` still invalidate them."""
+        ps = (self[0].weight, self[0].bias, self[2].weight, self[2].bias)
+        if ps[0].dtype == torch.bfloat16:
+            return tuple(p.detach() for p in ps)
+        bufs = self._bf16_buffers()
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        fresh = self._bf16_fresh and key == self._cache_key
+        self._bf16_fresh = False
+        if not fresh and not (allow_cache and key == self._cache_key):
+            with torch.no_grad():
+                for p, b in zip(ps, bufs):
+                    ops.cast_to_bf16(p.detach().contiguous(), out=b)
+            self._cache_key = key
+        return bufs
 
     def _regime(self, x):
         wdt = self[0].weight.dtype

@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -108,6 +109,20 @@ inline int device_sm_count() {
   return sms;
 }
 
+// Pool of {next unit, finished workers} counter pairs for the dynamic tile scheduler. Every launch takes the next
+// pair; a pair is re-armed (zeroed) by the kernel that used it, so no per-launch memset is needed. 1024 pairs is far
+// more than the launches that can be in flight at once.
+inline int* next_sched_counter() {
+  static int* pool = nullptr;
+  static std::atomic<unsigned> seq{0};
+  constexpr unsigned kPairs = 1024;
+  if (!pool) {
+    if (cudaMalloc(&pool, sizeof(int) * 2 * kPairs) != cudaSuccess) return nullptr;
+    cudaMemset(pool, 0, sizeof(int) * 2 * kPairs);
+  }
+  return pool + 2 * (seq.fetch_add(1) % kPairs);
+}
+
 struct GemmOperand {
   const void* ptr;
   long long ld;   // elements
@@ -176,6 +191,8 @@ int launch_gemm(GemmOperand a, GemmOperand b, GemmParams p, int splits, cudaStre
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  p.sched_counter = next_sched_counter();
+  if (!p.sched_counter) TD_FAIL(TD_ERR_DRIVER, "cannot allocate the tile-scheduler counters");
   ProfScope prof(tag, 2.0 * double(p.M) * double(p.N) * double(p.K), stream);
   TD_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
   return TD_OK;

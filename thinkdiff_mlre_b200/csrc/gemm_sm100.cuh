@@ -40,6 +40,7 @@ struct GemmParams {
   long long ld_out;  // elements
   float alpha;
   const float* alpha_ptr;  // optional device scalar multiplied into alpha (upstream loss gradient / GradScaler scale)
+  int* sched_counter;      // [2] zero-initialised {next unit, finished workers}; re-armed by the kernel itself
 };
 
 constexpr int kBlockM = 128;  // rows per CTA (TMEM lanes)
@@ -202,6 +203,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
 }
 
 // ------------------------------------------------------------------------------------------ kernel
+// Work distribution: a unit = (output tile, split-K slice). The first unit of every CTA (pair) is its own index; after
+// that the leader's producer thread claims units from a global atomic counter and publishes each claim through a small
+// shared-memory ring (`sched_*`) to the MMA thread and the epilogue warps -- and, for a pair, to the peer CTA over
+// DSMEM. CTAs that become resident late (e.g. because an NCCL kernel holds some SMs) simply find less work left,
+// instead of delaying a statically assigned share of the tiles.
+constexpr int kSchedStages = 4;
+
 template <int CTAS, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -213,16 +221,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
-  uint64_t* full_bar = bars;                               // [kStages]   TMA -> MMA
-  uint64_t* empty_bar = bars + kStages;                    // [kStages]   MMA -> TMA
-  uint64_t* acc_full_bar = bars + 2 * kStages;             // [kAccStages] MMA -> epilogue
-  uint64_t* acc_empty_bar = bars + 2 * kStages + kAccStages;  // [kAccStages] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages);
+  uint64_t* full_bar = bars;                                  // [kStages]   TMA -> MMA
+  uint64_t* empty_bar = full_bar + kStages;                   // [kStages]   MMA -> TMA
+  uint64_t* acc_full_bar = empty_bar + kStages;               // [kAccStages] MMA -> epilogue
+  uint64_t* acc_empty_bar = acc_full_bar + kAccStages;        // [kAccStages] epilogue -> MMA
+  uint64_t* sched_full_bar = acc_empty_bar + kAccStages;      // [kSchedStages] scheduler -> consumers
+  uint64_t* sched_empty_bar = sched_full_bar + kSchedStages;  // [kSchedStages] consumers -> scheduler (leader's copy is used)
+  int* sched_unit = reinterpret_cast<int*>(sched_empty_bar + kSchedStages);  // [kSchedStages]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_unit + kSchedStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
+  // consumers of a published unit, per CTA: 8 epilogue warps + 1 (the MMA thread in the leader, the producer in the peer)
+  constexpr uint32_t kSchedConsumers = (kEpiWarps + 1) * CTAS;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -235,6 +248,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&acc_full_bar[s], 1);
       mbar_init(&acc_empty_bar[s], 32 * kEpiWarps * CTAS);
     }
+    for (int s = 0; s < kSchedStages; ++s) {
+      mbar_init(&sched_full_bar[s], 1);
+      mbar_init(&sched_empty_bar[s], kSchedConsumers);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -246,7 +263,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // persistent schedule: work unit = (tile, split); units are dealt round-robin to CTAs (or CTA pairs)
   const int num_workers = gridDim.x / CTAS;
   const int worker = blockIdx.x / CTAS;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
@@ -265,13 +281,43 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     kb0 = split * p.k_blocks_per_split;
     kb1 = min(p.num_k_blocks, kb0 + p.k_blocks_per_split);
   };
+  // consumer side of the scheduler ring: wait for slot `ss`, read the unit, release the slot (one arrive per warp)
+  auto sched_consume = [&](int ss, uint32_t sphase, bool whole_warp) -> int {
+    mbar_wait_cluster(&sched_full_bar[ss], sphase);
+    const int unit = *reinterpret_cast<volatile int*>(&sched_unit[ss]);
+    if (whole_warp) __syncwarp();
+    if (!whole_warp || lane == 0) {
+      if constexpr (CTAS == 1) mbar_arrive(&sched_empty_bar[ss]);
+      else mbar_arrive_cluster(&sched_empty_bar[ss], 0);
+    }
+    return unit;
+  };
 
   if (warp == 0) {
-    // ===================================================== TMA producer
+    // ===================================================== scheduler + TMA producer
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int unit = worker; unit < num_units; unit += num_workers) {
+      int stage = 0, ss = 0;
+      uint32_t phase = 0, sphase = 0;
+      // the claim for the NEXT unit is issued before the current unit's loads, so the atomic's round trip is hidden
+      int claimed = worker;
+      while (true) {
+        int unit;
+        if (leader) {
+          unit = claimed;
+          if (unit < num_units) claimed = atomicAdd(p.sched_counter, 1) + num_workers;
+          if (unit >= num_units) unit = -1;
+          mbar_wait_cluster(&sched_empty_bar[ss], sphase ^ 1);  // every consumer (both CTAs) has read the old value
+          sched_unit[ss] = unit;
+          mbar_arrive(&sched_full_bar[ss]);  // release.cta: orders the store above for this CTA's consumers
+          if constexpr (CTAS == 2) {
+            st_shared_cluster_s32(&sched_unit[ss], 1, unit);
+            mbar_arrive_cluster(&sched_full_bar[ss], 1);  // release.cluster: orders the remote store
+          }
+        } else {
+          unit = sched_consume(ss, sphase, false);
+        }
+        if (++ss == kSchedStages) { ss = 0; sphase ^= 1; }
+        if (unit < 0) break;
         int m_blk, n_blk, kb0, kb1;
         unit_coords(unit, m_blk, n_blk, kb0, kb1);
         const int a_row0 = m_blk * (kBlockM * CTAS) + cta_rank * kBlockM;
@@ -305,6 +351,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+      if (leader) {
+        // the last worker to run out of units re-arms the counter pair for the next launch that uses this slot
+        __threadfence();
+        if (atomicAdd(p.sched_counter + 1, 1) == num_workers - 1) {
+          p.sched_counter[0] = 0;
+          p.sched_counter[1] = 0;
+          __threadfence();
+        }
+      }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -317,11 +372,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       constexpr uint32_t sbo = 1024;
       constexpr uint32_t a_kstep = A_MN ? kUmmaK * 128 : kUmmaK * 2;  // bytes per UMMA_K step
       constexpr uint32_t b_kstep = B_MN ? kUmmaK * 128 : kUmmaK * 2;
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int unit = worker; unit < num_units; unit += num_workers) {
+      int stage = 0, ss = 0, acc = 0;
+      uint32_t phase = 0, sphase = 0, acc_phase = 0;
+      while (true) {
+        const int unit = sched_consume(ss, sphase, false);
+        if (++ss == kSchedStages) { ss = 0; sphase ^= 1; }
+        if (unit < 0) break;
         int m_blk, n_blk, kb0, kb1;
         unit_coords(unit, m_blk, n_blk, kb0, kb1);
         mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);
@@ -350,9 +406,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================================================== epilogue warps (TMEM lane quarter = warp % 4)
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int unit = worker; unit < num_units; unit += num_workers) {
+    int acc = 0, ss = 0;
+    uint32_t acc_phase = 0, sphase = 0;
+    while (true) {
+      const int unit = sched_consume(ss, sphase, true);
+      if (++ss == kSchedStages) { ss = 0; sphase ^= 1; }
+      if (unit < 0) break;
       int m_blk, n_blk, kb0, kb1;
       unit_coords(unit, m_blk, n_blk, kb0, kb1);
       mbar_wait(&acc_full_bar[acc], acc_phase);

@@ -56,6 +56,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n"
+      " mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      " selp.b32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Store a 32-bit value into the same shared-memory location of CTA `cta` of this cluster (DSMEM).
+__device__ __forceinline__ void st_shared_cluster_s32(int* local_addr, uint32_t cta, int value) {
+  asm volatile(
+      "{\n .reg .b32 ra;\n"
+      " mapa.shared::cluster.u32 ra, %0, %1;\n"
+      " st.shared::cluster.s32 [ra], %2;\n}" ::"r"(smem_u32(local_addr)),
+      "r"(cta), "r"(value)
+      : "memory");
+}
 // A pipeline wait that cannot hang the GPU: if a barrier does not flip within ~4 s the kernel
 // traps, which surfaces as a launch failure on the host instead of a wedged device.
 #ifndef TD_MBAR_TIMEOUT_NS
@@ -67,6 +87,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (global_timer_ns() - t0 > TD_MBAR_TIMEOUT_NS) {
       printf("td: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
+             smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
+// Same, with cluster-scope acquire: the barrier may have been arrived on by (and orders data written by) the peer CTA.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (global_timer_ns() - t0 > TD_MBAR_TIMEOUT_NS) {
+      printf("td: cluster mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
              smem_u32(bar), parity);
       __trap();
     }

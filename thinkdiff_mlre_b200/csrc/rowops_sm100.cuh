@@ -329,6 +329,51 @@ rmsnorm_bwd_kernel(const void* __restrict__ dy_in, const __nv_bfloat16* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------ AdamW (+ bf16 compute copy)
+// Decoupled-weight-decay Adam exactly as torch.optim.AdamW (amsgrad=False, maximize=False), the reference optimiser
+// (thinkdiff/runners/runner_base.py:122-127):
+//   p *= 1 - lr*wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+// One pass also emits the bf16 copy of the parameter that the next forward's GEMMs read (replacing autocast's per-call
+// cast), and consumes the gradient straight out of the all-reduced flat bucket. Up to 3 tensors per launch
+// (blockIdx.y = segment). 30 B/parameter of HBM traffic.
+struct AdamSegment {
+  float* p; const float* g; float* m; float* v; __nv_bfloat16* p_bf16; long long n; float weight_decay;
+};
+struct AdamParams {
+  AdamSegment seg[3];
+  float lr, beta1, beta2, eps, bias_c1, sqrt_bias_c2, grad_scale;
+};
+
+__global__ void __launch_bounds__(256)
+adamw_kernel(const AdamParams a) {
+  const AdamSegment s = a.seg[blockIdx.y];
+  const long long n4 = s.n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float decay = 1.0f - a.lr * s.weight_decay;
+  const float step_size = a.lr / a.bias_c1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 p = reinterpret_cast<float4*>(s.p)[i];
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(s.g) + i);
+    float4 m = reinterpret_cast<float4*>(s.m)[i];
+    float4 v = reinterpret_cast<float4*>(s.v)[i];
+    float pp[4] = {p.x, p.y, p.z, p.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, mm[4] = {m.x, m.y, m.z, m.w}, vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float g = gg[q] * a.grad_scale;
+      pp[q] *= decay;
+      mm[q] = a.beta1 * mm[q] + (1.0f - a.beta1) * g;
+      vv[q] = a.beta2 * vv[q] + (1.0f - a.beta2) * g * g;
+      const float denom = sqrtf(vv[q]) / a.sqrt_bias_c2 + a.eps;
+      pp[q] -= step_size * (mm[q] / denom);
+    }
+    reinterpret_cast<float4*>(s.p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    reinterpret_cast<float4*>(s.m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(s.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    if (s.p_bf16 != nullptr)
+      reinterpret_cast<uint2*>(s.p_bf16)[i] = make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
+  }
+}
+
 // ------------------------------------------------------------------------------------------ fused norm + MSE + norm-backward
 // rstd[row] = rsqrt(mean(h2^2) + eps) from the GEMM2 epilogue's per-half-tile partial sums ssq_part[P][M].
 __global__ void __launch_bounds__(256)

@@ -493,6 +493,40 @@ int32_t td_aligner_bwd_dh2(const void* dh2, const void* x, const void* h0, const
                       dW2, w, phases, st);
 }
 
+// ------------------------------------------------------------------------------------------------ optimizer
+int32_t td_adamw_step(int32_t num_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                      float* const* exp_avg_sq, void* const* params_bf16, const int64_t* numel, const float* weight_decay,
+                      float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (num_tensors < 1 || num_tensors > 3) TD_FAIL(TD_ERR_ARG, "td_adamw_step: 1..3 tensors per call, got %d", num_tensors);
+  if (step < 1) TD_FAIL(TD_ERR_ARG, "td_adamw_step: step counts from 1");
+  AdamParams a;
+  memset(&a, 0, sizeof(a));
+  long long max_n = 0;
+  for (int i = 0; i < num_tensors; ++i) {
+    if (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i] || numel[i] < 0) TD_FAIL(TD_ERR_ARG, "td_adamw_step: null pointer");
+    if (numel[i] % 4) TD_FAIL(TD_ERR_UNSUPPORTED, "td_adamw_step: tensor sizes must be multiples of 4 (got %lld)", (long long)numel[i]);
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(params[i]) | reinterpret_cast<uintptr_t>(grads[i]) |
+                           reinterpret_cast<uintptr_t>(exp_avg[i]) | reinterpret_cast<uintptr_t>(exp_avg_sq[i]);
+    if (bits & 15) TD_FAIL(TD_ERR_ARG, "td_adamw_step: buffers must be 16-byte aligned");
+    a.seg[i] = AdamSegment{params[i], grads[i], exp_avg[i], exp_avg_sq[i],
+                           static_cast<__nv_bfloat16*>(params_bf16 ? params_bf16[i] : nullptr), numel[i], weight_decay[i]};
+    if (numel[i] > max_n) max_n = numel[i];
+  }
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_scale = grad_scale;
+  a.bias_c1 = 1.0f - powf(beta1, float(step));
+  a.sqrt_bias_c2 = sqrtf(1.0f - powf(beta2, float(step)));
+  if (max_n == 0) return TD_OK;
+  double total = 0;
+  for (int i = 0; i < num_tensors; ++i) total += double(numel[i]);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int gx = grid_for_rows(max_n / 4, 256, 8);
+  ProfScope prof("adamw_bf16", 30.0 * total, st);
+  adamw_kernel<<<dim3(gx, num_tensors), 256, 0, st>>>(a);
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ losses
 int64_t td_loss_workspace_bytes(int64_t rows) {
   const size_t parts = (size_t)device_sm_count() * 8 + 8;
