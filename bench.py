@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after backward instead of overlapped")
+    ap.add_argument("--no-pipeline", action="store_true", help="N > 1: apply every parameter update inside its own step")
     ap.add_argument("--profile-out", default="", help="write the per-kernel table (JSON) here")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: this repo's one-pass AdamW (+ bf16 copies, per-bucket overlap); torch: torch.optim.AdamW(fused=True)")
@@ -218,7 +219,8 @@ def main():
     if world > 1:
         aligner.enable_data_parallel(overlap=not args.no_overlap, defer_wait=args.optimizer == "fused")
     opt = td.FusedAdamW(aligner, lr=1e-4, weight_decay=0.05) if args.optimizer == "fused" else make_reference_optimizer(aligner)
-    stepper = td.AlignerTrainStep(aligner, opt, fused_loss=args.loss_path == "fused")
+    pipelined = world > 1 and args.optimizer == "fused" and args.loss_path == "fused" and not args.no_pipeline
+    stepper = td.AlignerTrainStep(aligner, opt, fused_loss=args.loss_path == "fused", pipelined=pipelined)
 
     host = [td.synthetic_lvlm_batch(SEQS_PER_GPU, MAX_LEN, DIN, D, seed=1234 + rank + 1000 * j) for j in range(NUM_BATCHES)]
     resident = [(b.flat.to(dev), b.src_row_start.to(dev), b.lens.to(dev), b.total_rows, b.l_max, b.extras["flat_target"].to(dev)) for b in host]
@@ -257,6 +259,7 @@ def main():
         for i in range(steps):
             loss = stepper.step_device(*resident[i % NUM_BATCHES])
         host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / steps  # CPU time to enqueue one step (no sync inside)
+        stepper.flush()  # pipelined mode: the last step's updates are part of the timed work
         e1.record()
         sync_all()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -278,6 +281,7 @@ def main():
             if i + 1 < steps:
                 nxt = stepper.prefetch(host[(i + 1) % NUM_BATCHES], dev)  # copy of step i+1 overlaps compute of step i
             loss_host = float(stepper.step_prefetched(cur))  # .item(): D2H read of the loss, as base_task.py:262
+        stepper.flush()
         e1.record()
         sync_all()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
@@ -291,6 +295,7 @@ def main():
     L.profile_enable(True)
     for i in range(psteps):
         stepper.step_device(*resident[i % NUM_BATCHES])
+    stepper.flush()
     torch.cuda.synchronize()
     prof = L.profile_report()
     L.profile_enable(False)
@@ -319,6 +324,23 @@ def main():
                 "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}); sustained bf16 figure: kernel timed inside a long step",
                 "ms_per_launch": kernels[dom]["ms_per_launch"], "share_of_kernel_time": kernels[dom]["share_of_kernel_time"]}
 
+    # the gradient all-reduce on its own (both buckets back to back, nothing else running): what overlap has to hide
+    ar_alone = None
+    if world > 1:
+        from thinkdiff_mlre_b200.aligner import GradBuckets
+
+        gb = GradBuckets(DIN, D, dev)
+        gb.linear2.zero_(), gb.linear1.zero_()
+        for _ in range(3):
+            dist.all_reduce(gb.linear2), dist.all_reduce(gb.linear1)
+        sync_all()
+        e0.record()
+        for _ in range(10):
+            dist.all_reduce(gb.linear2), dist.all_reduce(gb.linear1)
+        e1.record()
+        sync_all()
+        ar_alone = max_over_ranks(e0.elapsed_time(e1)) / 10
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(5, 2)
@@ -329,11 +351,11 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": dict(workload_config(world), loss_path=args.loss_path, optimizer_impl=args.optimizer), "clocks": clocks.summary(), "e2e": e2e,
+            "data": "synthetic", "config": dict(workload_config(world), loss_path=args.loss_path, optimizer_impl=args.optimizer, pipelined_updates=pipelined), "clocks": clocks.summary(), "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_peak": step_tflops / peaks["bf16_tflops_sustained"],
             "step_frac_of_nominal_2250": step_tflops / 2250.0, "tokens_per_step": tokens / steps, "final_loss": final_loss,
-            "host_enqueue_ms_per_step": host_enqueue_ms, "kernels": kernels,
+            "host_enqueue_ms_per_step": host_enqueue_ms, "allreduce_alone_ms": ar_alone, "kernels": kernels,
         }
         if args.profile_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)

@@ -80,12 +80,15 @@ int32_t td_aligner_bwd(const void* dy, int32_t dy_dtype, const void* x, const vo
  * -- y and dy never touch HBM. Outputs for a UNIT upstream gradient: dh2 bf16 [M, D], dg_unit / db2_unit fp32 [D], and the
  * loss (fp32 device scalar). td_aligner_bwd_dh2 finishes the backward, multiplying by grad_scale * (*grad_scale_ptr)
  * (grad_scale_ptr: optional DEVICE scalar = the upstream gradient of the loss, e.g. GradScaler's scale; no host sync).
- * Same gradients as td_aligner_fwd -> td_masked_mse_fwd_bwd -> td_aligner_bwd (base_task.py:237-244 with an MSE loss). */
+ * Same gradients as td_aligner_fwd -> td_masked_mse_fwd_bwd -> td_aligner_bwd (base_task.py:237-244 with an MSE loss).
+ * `stages` lets the caller run Linear1 and the rest as two calls (same buffers), e.g. to apply the Linear2 parameter update
+ * of the previous step in between while that bucket's all-reduce was still in flight. */
 int64_t td_aligner_mse_fwd_workspace_bytes(int64_t M, int32_t Din, int32_t D);
 int32_t td_aligner_mse_fwd(const void* x, int64_t M, int32_t Din, int32_t D, const void* W1, const void* b1, const void* W2,
                            const void* b2, const float* g, float eps, const void* target, int32_t target_dtype, void* h0,
                            void* h1, void* dh2, float* dg_unit, float* db2_unit, float* loss, void* workspace,
-                           int64_t workspace_bytes, td_stream_t stream);
+                           int64_t workspace_bytes, int32_t stages /* 1 = Linear1+GELU, 2 = the rest, 3 = all */,
+                           td_stream_t stream);
 int32_t td_aligner_bwd_dh2(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
                            const float* dg_unit, const float* db2_unit, int64_t M, int32_t Din, int32_t D, float grad_scale,
                            const float* grad_scale_ptr, float* dW1, float* db1, float* dW2, float* db2, float* dg,

@@ -400,3 +400,28 @@ def test_fused_adamw_matches_torch_adamw_and_refreshes_bf16_copies():
     assert rel(y1, y2.float().cpu()) < 1e-3
     sd = o1.state_dict()
     assert len(sd["state"]) == 5 and sd["param_groups"][0]["weight_decay"] == 0.05
+
+
+def test_pipelined_updates_equal_sequential_updates():
+    """AlignerTrainStep(pipelined=True) applies step i's parameter updates inside step i+1 (Linear1's after the pack,
+    Linear2's between the two forward GEMMs). Same arithmetic -> bit-identical parameters and losses."""
+    import copy
+
+    import thinkdiff_mlre_b200 as td
+
+    m1, _ = make_module(192, 512, seed=41)
+    m2 = copy.deepcopy(m1)
+    s1 = td.AlignerTrainStep(m1, td.FusedAdamW(m1, lr=1e-3), pipelined=False)
+    s2 = td.AlignerTrainStep(m2, td.FusedAdamW(m2, lr=1e-3), pipelined=True)
+    batches = [td.synthetic_lvlm_batch(5, 40, 192, 512, seed=100 + j, pin=False) for j in range(3)]
+    for j in range(5):
+        b = batches[j % 3]
+        args = (b.flat.cuda(), b.src_row_start.cuda(), b.lens.cuda(), b.total_rows, b.l_max, b.extras["flat_target"].cuda())
+        l1, l2 = s1.step_device(*args), s2.step_device(*args)
+        assert torch.equal(l1, l2), j
+    s2.flush()
+    for (k, p1), p2 in zip(m1.named_parameters(), m2.parameters()):
+        assert torch.equal(p1, p2), k
+    for b1, b2 in zip(m1._bf16_buffers(), m2._bf16_buffers()):
+        assert torch.equal(b1, b2)
+    assert all(p.grad is None for p in m2.parameters())

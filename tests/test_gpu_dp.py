@@ -89,3 +89,55 @@ def test_two_gpu_bucketed_allreduce_equals_oracle_mean(overlap):
     for a, b, n in zip(got, want, NAMES):
         err = np.linalg.norm(a - b.numpy()) / np.linalg.norm(b.numpy())
         assert err < 2e-2, (n, err)
+
+
+def _train_worker(rank, world, port, pipelined, ret):
+    import torch.distributed as dist
+
+    import thinkdiff_mlre_b200 as td
+    from oracle import aligner_ref
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        m = td.ThinkDiffAligner(DIN, D).cuda()
+        m.load_state_dict(aligner_ref.init_params_numpy(DIN, D, seed=3))
+        m.enable_data_parallel(defer_wait=True)
+        step = td.AlignerTrainStep(m, td.FusedAdamW(m, lr=1e-3), pipelined=pipelined)
+        losses = []
+        for j in range(4):
+            b = td.synthetic_lvlm_batch(4, 50, DIN, D, seed=10 * j + rank, pin=False)
+            losses.append(step.step_device(b.flat.cuda(), b.src_row_start.cuda(), b.lens.cuda(), b.total_rows, b.l_max,
+                                           b.extras["flat_target"].cuda()))
+        step.flush()
+        torch.cuda.synchronize()
+        ret.put((rank, [p.detach().float().cpu().numpy() for p in m.parameters()], [float(l) for l in losses]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_pipelined_training_equals_sequential_and_keeps_replicas_in_sync():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    out = {}
+    for pipelined in (False, True):
+        ctx = mp.get_context("spawn")
+        ret = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_train_worker, args=(r, 2, port, pipelined, ret)) for r in range(2)]
+        for p in procs:
+            p.start()
+        res = [ret.get(timeout=300) for _ in range(2)]
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+        out[pipelined] = {r: (params, losses) for r, params, losses in res}
+    for pipelined in (False, True):  # replicas stay identical (same averaged gradients on every rank)
+        for a, b in zip(out[pipelined][0][0], out[pipelined][1][0]):
+            np.testing.assert_array_equal(a, b)
+    for a, b in zip(out[False][0][0], out[True][0][0]):  # pipelining does not change the arithmetic
+        np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(out[False][0][1], out[True][0][1], rtol=1e-6)

@@ -32,7 +32,7 @@ SIGNATURES = {
     "td_aligner_bwd_workspace_bytes": (_i64, [_i64, _i32, _i32]),
     "td_aligner_bwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "td_aligner_mse_fwd_workspace_bytes": (_i64, [_i64, _i32, _i32]),
-    "td_aligner_mse_fwd": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "td_aligner_mse_fwd": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "td_aligner_bwd_dh2": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "td_rmsnorm_fwd": (_i32, [_vp, _vp, _f32, _i64, _i32, _vp, _i32, _vp, _vp]),
     "td_rmsnorm_bwd_workspace_bytes": (_i64, [_i64, _i32]),

@@ -124,15 +124,20 @@ def _reduce_and_return(module, gb, run_phase1, run_phase2):
     gradients, overlapping the first all-reduce) -> all-reduce the second bucket -> stream-level waits (or, with
     ``defer_wait``, leave the waits to the consumer of each bucket)."""
     dp = module._dp
-    run_phase1()
+    # (name, bucket, launcher) in execution order; "linear1_first" is used by the pipelined train step, where the
+    # Linear2 bucket is the one whose update can be deferred furthest into the next step (W2 is first read by GEMM2)
+    order = [("linear2", gb.linear2, run_phase1), ("linear1", gb.linear1, run_phase2)]
+    if module._bwd_order == "linear1_first":
+        order.reverse()
     works = {}
+    order[0][2]()
     if dp is not None and dp.world > 1 and dp.overlap:
-        works["linear2"] = dp.all_reduce_async(gb.linear2)  # rides NVLink while the next two GEMMs run
-    run_phase2()
+        works[order[0][0]] = dp.all_reduce_async(order[0][1])  # rides NVLink while the remaining GEMMs run
+    order[1][2]()
     if dp is not None and dp.world > 1:
         if not dp.overlap:
-            works["linear2"] = dp.all_reduce_async(gb.linear2)
-        works["linear1"] = dp.all_reduce_async(gb.linear1)
+            works[order[0][0]] = dp.all_reduce_async(order[0][1])
+        works[order[1][0]] = dp.all_reduce_async(order[1][1])
         if dp.defer_wait:
             module.wait_grads()  # anything still pending from an earlier backward
             module._pending = works
@@ -148,7 +153,7 @@ class _AlignerMSEFn(torch.autograd.Function):
     def forward(ctx, x2d, target, W1, b1, W2, b2, g, module):
         W1b, b1b, W2b, b2b = module._bf16_params()
         gf = g.detach() if g.dtype == torch.float32 else g.detach().float()
-        loss, saved = ops.aligner_mse_fwd(x2d, W1b, b1b, W2b, b2b, gf, module.eps, target)
+        loss, saved = ops.aligner_mse_fwd(x2d, W1b, b1b, W2b, b2b, gf, module.eps, target, module._between_fwd_stages)
         ctx.save_for_backward(x2d, W2b, *saved)
         ctx.module = module
         return loss
@@ -181,6 +186,9 @@ class ThinkDiffAligner(nn.Sequential):
         self._cache = None      # persistent bf16 compute copies of (W1, b1, W2, b2)
         self._bf16_fresh = False  # set by FusedAdamW: the copies were written by the optimizer step itself
         self._pending = {}      # bucket name -> in-flight all-reduce (defer_wait mode)
+        self._bwd_order = "linear2_first"   # or "linear1_first" (pipelined train step)
+        self._between_fwd_stages = None     # callable run between Linear1 and Linear2 of the fused-loss forward
+        self._bf16_managed = False          # True: an optimizer keeps the bf16 copies current; training never re-casts
         self._dp: DataParallelState | None = None
         self.fp32_mode = "bf16x3"
 
@@ -228,6 +236,8 @@ class ThinkDiffAligner(nn.Sequential):
         if ps[0].dtype == torch.bfloat16:
             return tuple(p.detach() for p in ps)
         bufs = self._bf16_buffers()
+        if self._bf16_managed and self._cache_key is not None:
+            return bufs
         key = tuple((p.data_ptr(), p._version) for p in ps)
         fresh = self._bf16_fresh and key == self._cache_key
         self._bf16_fresh = False

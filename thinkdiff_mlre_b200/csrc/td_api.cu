@@ -423,7 +423,7 @@ int64_t td_aligner_mse_fwd_workspace_bytes(int64_t M, int32_t Din, int32_t D) {
 int32_t td_aligner_mse_fwd(const void* x, int64_t M, int32_t Din, int32_t D, const void* W1, const void* b1,
                            const void* W2, const void* b2, const float* g, float eps, const void* target,
                            int32_t target_dtype, void* h0, void* h1, void* dh2, float* dg_unit, float* db2_unit,
-                           float* loss, void* ws, int64_t ws_bytes, td_stream_t stream) {
+                           float* loss, void* ws, int64_t ws_bytes, int32_t stages, td_stream_t stream) {
   TD_DEVICE_OR_RETURN();
   if (!dims_ok(Din, D)) TD_FAIL(TD_ERR_UNSUPPORTED, "td_aligner_mse_fwd: Din=%d, D=%d must be multiples of 64 (D <= 4096)", Din, D);
   if (M <= 0 || M > 0x7fffffffll / D) TD_FAIL(TD_ERR_ARG, "td_aligner_mse_fwd: M=%lld out of range (needs at least one token)", (long long)M);
@@ -444,11 +444,15 @@ int32_t td_aligner_mse_fwd(const void* x, int64_t M, int32_t Din, int32_t D, con
   float* meta = c.take<float>(8);
 
   GemmParams p;
-  memset(&p, 0, sizeof(p));
-  p.M = int(M); p.N = D; p.K = Din; p.ld_out = D; p.alpha = 1.f;
-  p.out0 = h0; p.out1 = h1; p.bias = static_cast<const __nv_bfloat16*>(b1);
-  int rc = launch_gemm<2, false, false, EPI_BIAS_GELU>({x, Din, false}, {W1, Din, false}, p, 1, st, "gemm_fwd1_bias_gelu");
-  if (rc) return rc;
+  int rc;
+  if (stages & 1) {  // Linear1 + GELU (reads W1, b1 only)
+    memset(&p, 0, sizeof(p));
+    p.M = int(M); p.N = D; p.K = Din; p.ld_out = D; p.alpha = 1.f;
+    p.out0 = h0; p.out1 = h1; p.bias = static_cast<const __nv_bfloat16*>(b1);
+    rc = launch_gemm<2, false, false, EPI_BIAS_GELU>({x, Din, false}, {W1, Din, false}, p, 1, st, "gemm_fwd1_bias_gelu");
+    if (rc) return rc;
+  }
+  if (!(stages & 2)) return TD_OK;
   memset(&p, 0, sizeof(p));
   p.M = int(M); p.N = D; p.K = D; p.ld_out = D; p.alpha = 1.f;
   p.out0 = h2; p.bias = static_cast<const __nv_bfloat16*>(b2); p.red0 = ssq_part;

@@ -140,9 +140,10 @@ class AlignerBackward:
         self._call(L.BWD_GELU_W1, dW1, db1, None, None, None)
 
 
-def aligner_mse_fwd(x, W1, b1, W2, b2, g, eps: float, target):
+def aligner_mse_fwd(x, W1, b1, W2, b2, g, eps: float, target, between_stages=None):
     """Fused training forward against T5 targets: returns (loss, saved) with saved = (h0, h1, dh2, dg_unit, db2_unit),
-    where dh2 / dg_unit / db2_unit are the T5LayerNorm backward of the MSE gradient for a unit upstream gradient."""
+    where dh2 / dg_unit / db2_unit are the T5LayerNorm backward of the MSE gradient for a unit upstream gradient.
+    ``between_stages``: optional callable run after Linear1+GELU is enqueued and before anything reads W2 / b2."""
     _need_cuda(x, W1, W2, g, target)
     M, Din = x.shape
     D = W1.shape[0]
@@ -158,12 +159,21 @@ def aligner_mse_fwd(x, W1, b1, W2, b2, g, eps: float, target):
     ws_bytes = L.lib().td_aligner_mse_fwd_workspace_bytes(M, Din, D)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     L.launch_count += 7
-    L.check(
-        L.lib().td_aligner_mse_fwd(L.ptr(_contig(x, "x")), M, Din, D, L.ptr(W1), L.ptr(b1), L.ptr(W2), L.ptr(b2), L.ptr(g), eps,
-                                   L.ptr(_contig(target, "target")), L.dtype_code(target), L.ptr(h0), L.ptr(h1), L.ptr(dh2),
-                                   L.ptr(dg_unit), L.ptr(db2_unit), L.ptr(loss), L.ptr(ws), ws_bytes, L.stream_ptr()),
-        "td_aligner_mse_fwd",
-    )
+
+    def call(stages):
+        L.check(
+            L.lib().td_aligner_mse_fwd(L.ptr(_contig(x, "x")), M, Din, D, L.ptr(W1), L.ptr(b1), L.ptr(W2), L.ptr(b2), L.ptr(g), eps,
+                                       L.ptr(_contig(target, "target")), L.dtype_code(target), L.ptr(h0), L.ptr(h1), L.ptr(dh2),
+                                       L.ptr(dg_unit), L.ptr(db2_unit), L.ptr(loss), L.ptr(ws), ws_bytes, stages, L.stream_ptr()),
+            "td_aligner_mse_fwd",
+        )
+
+    if between_stages is None:
+        call(3)
+    else:
+        call(1)
+        between_stages()
+        call(2)
     return loss, (h0, h1, dh2, dg_unit, db2_unit)
 
 

@@ -35,10 +35,12 @@ class FusedAdamW(torch.optim.Optimizer):
         raise KeyError("parameter not in any group")
 
     @torch.no_grad()
-    def step_bucket(self, name: str):
+    def step_bucket(self, name: str, t: int | None = None, release_grads: bool = False):
         """Update the parameters of one gradient bucket ('linear2' = 2.weight, 2.bias, 3.weight; 'linear1' = 0.weight,
-        0.bias), after ordering the stream behind that bucket's all-reduce."""
+        0.bias), after ordering the stream behind that bucket's all-reduce. ``t`` = optimizer step number the gradients
+        belong to (defaults to the current one); ``release_grads`` drops the ``.grad`` references afterwards."""
         a = self.aligner
+        t = self._t if t is None else t
         a.wait_bucket(name)
         named = dict(a.named_parameters())
         bf16 = dict(zip(("0.weight", "0.bias", "2.weight", "2.bias"), a._bf16_buffers()))
@@ -55,7 +57,7 @@ class FusedAdamW(torch.optim.Optimizer):
             if not st:
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-            st["step"] = self._t
+            st["step"] = t
             if p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
                 raise TypeError("FusedAdamW needs contiguous float32 parameters and gradients")
             states.append(st)
@@ -69,16 +71,30 @@ class FusedAdamW(torch.optim.Optimizer):
                 arr([s["exp_avg"].data_ptr() for s in states]), arr([s["exp_avg_sq"].data_ptr() for s in states]),
                 arr([bf16[k].data_ptr() if k in bf16 else None for k in keys]),
                 (C.c_int64 * n)(*[p.numel() for p in ps]), (C.c_float * n)(*[g["weight_decay"] for g in groups]),
-                g0["lr"], g0["betas"][0], g0["betas"][1], g0["eps"], self._t, self.grad_scale, L.stream_ptr()),
+                g0["lr"], g0["betas"][0], g0["betas"][1], g0["eps"], t, self.grad_scale, L.stream_ptr()),
             "td_adamw_step",
         )
+        if release_grads:
+            for p in ps:
+                p.grad = None
+
+    def next_step_number(self) -> int:
+        self._t += 1
+        return self._t
+
+    def mark_bf16_current(self):
+        a = self.aligner
+        ps = (a[0].weight, a[0].bias, a[2].weight, a[2].bias)
+        a._cache_key = tuple((p.data_ptr(), p._version) for p in ps)
+        a._bf16_fresh = True
 
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         self._t += 1
-        self.step_bucket("linear2")  # its all-reduce finished first; this update overlaps the linear1 all-reduce
-        self.step_bucket("linear1")
+        order = ("linear1", "linear2") if self.aligner._bwd_order == "linear1_first" else ("linear2", "linear1")
+        self.step_bucket(order[0])  # its all-reduce finished first; this update overlaps the other bucket's all-reduce
+        self.step_bucket(order[1])
         a = self.aligner
         ps = (a[0].weight, a[0].bias, a[2].weight, a[2].bias)
         a._cache_key = tuple((p.data_ptr(), p._version) for p in ps)

@@ -54,16 +54,31 @@ def synthetic_lvlm_batch(num_seqs: int, max_len: int, din: int, d: int, seed: in
 class AlignerTrainStep:
     """One data-parallel training step of the aligner against T5-space targets (masked MSE)."""
 
-    def __init__(self, aligner: ThinkDiffAligner, optimizer=None, loss_scale: float = 1.0, fused_loss: bool = True):
+    def __init__(self, aligner: ThinkDiffAligner, optimizer=None, loss_scale: float = 1.0, fused_loss: bool = True,
+                 pipelined: bool = False):
         self.aligner = aligner
         self.optimizer = optimizer
         self.loss_scale = float(loss_scale)  # GradScaler-style static scale (backward is linear in it)
         self.fused_loss = fused_loss         # True: aligner.mse_loss_packed (y / dy stay on chip); False: module boundary path
+        # pipelined (data parallel + FusedAdamW + fused loss): the parameter updates of step i are applied inside step
+        # i+1, each just before its parameter is first read -- Linear1's after the next batch is packed, Linear2's
+        # between the two forward GEMMs -- so both gradient all-reduces hide behind compute. Same arithmetic, same
+        # order of updates as the sequential step; call flush() before reading parameters outside the loop.
+        self.pipelined = pipelined
+        self._pending_t = None
+        if pipelined:
+            from .optim import FusedAdamW
+
+            if not (isinstance(optimizer, FusedAdamW) and fused_loss):
+                raise ValueError("pipelined=True needs FusedAdamW and fused_loss=True")
+            aligner._bwd_order = "linear1_first"
 
     def step_device(self, flat, src_row_start, lens_dev, total_rows: int, l_max: int, flat_target) -> torch.Tensor:
         """Inputs already resident in HBM. Returns the (unscaled) loss as a device scalar; nothing syncs the host."""
         packed = pack_device(flat, src_row_start, lens_dev, total_rows, l_max)
         target = ops.pack_varlen(flat_target, src_row_start, packed.cu_seqlens, total_rows)
+        if self.pipelined:
+            return self._step_pipelined(packed, target)
         if self.fused_loss:
             loss = self.aligner.mse_loss_packed(packed.x, target)
             (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
@@ -79,6 +94,31 @@ class AlignerTrainStep:
             self.optimizer.step()
             self.optimizer.zero_grad(set_to_none=True)
         return loss
+
+    def _step_pipelined(self, packed, target) -> torch.Tensor:
+        a, opt = self.aligner, self.optimizer
+        opt.grad_scale = 1.0 / self.loss_scale
+        t_prev = self._pending_t
+        if t_prev is not None:
+            opt.step_bucket("linear1", t=t_prev, release_grads=True)  # W1, b1 (+ bf16 copies) before GEMM1 reads them
+            a._between_fwd_stages = lambda: opt.step_bucket("linear2", t=t_prev, release_grads=True)  # W2, b2, g before GEMM2
+            a._bf16_managed = True
+        try:
+            loss = a.mse_loss_packed(packed.x, target)
+        finally:
+            a._between_fwd_stages = None
+        (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
+        self._pending_t = opt.next_step_number()
+        return loss
+
+    def flush(self):
+        """Apply the parameter updates still pending from the last pipelined step (no-op otherwise)."""
+        if self._pending_t is not None:
+            self.optimizer.step_bucket("linear1", t=self._pending_t, release_grads=True)
+            self.optimizer.step_bucket("linear2", t=self._pending_t, release_grads=True)
+            self.optimizer.mark_bf16_current()
+            self._pending_t = None
+            self.aligner._bf16_managed = False
 
     # -- host-fed path with the copy of batch i+1 overlapping the compute of batch i (what the reference's PrefetchLoader
     #    does on a side stream, thinkdiff/datasets/datasets/dataloader_utils.py:45-118)
