@@ -55,7 +55,7 @@ struct GemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;           // 16 KB
   static constexpr int kBBytes = (kBlockN / CTAS) * kBlockK * 2;  // 32 KB or 16 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (CTAS == 1) ? 4 : 6;
+  static constexpr int kStages = (CTAS == 1) ? 4 : 7;
   static constexpr int kBarrierBytes = 1024;
   static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // +1024 alignment slack
 };
@@ -246,7 +246,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&acc_full_bar[s], 1);
-      mbar_init(&acc_empty_bar[s], 32 * kEpiWarps * CTAS);
+      mbar_init(&acc_empty_bar[s], kEpiWarps * CTAS);
     }
     for (int s = 0; s < kSchedStages; ++s) {
       mbar_init(&sched_full_bar[s], 1);
@@ -420,8 +420,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (kb1 > kb0)
         epilogue_tile<EPI>(p, tmem_base + acc * kBlockN, m_slab * kBlockM, n_blk * kBlockN, n_blk, m_slab, quarter, half, lane);
       tc_fence_before();
-      if constexpr (CTAS == 1) mbar_arrive(&acc_empty_bar[acc]);
-      else mbar_arrive_cluster(&acc_empty_bar[acc], 0);
+      __syncwarp();  // all 32 lanes have drained their TMEM loads; one (release) arrive per warp
+      if (lane == 0) {
+        if constexpr (CTAS == 1) mbar_arrive(&acc_empty_bar[acc]);
+        else mbar_arrive_cluster(&acc_empty_bar[acc], 0);
+      }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   }

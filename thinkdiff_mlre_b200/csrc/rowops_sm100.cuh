@@ -654,108 +654,110 @@ __global__ void loss_finish_kernel(const float* __restrict__ part, int P, const 
 }
 
 // ------------------------------------------------------------------------------------------ masked cross-entropy
-// One CTA per logits row; the row (V values) is staged once in shared memory as fp32, so HBM sees one read of the
-// logits and one write of dlogits: loss_row = logsumexp(z) - z[label]; dz = (softmax(z) - onehot) * grad_scale / n_valid.
+// One CTA per logits row. The row is read from HBM exactly once: it is staged in shared memory IN ITS INPUT DTYPE
+// (bf16: 64 KB for V = 32128, so three CTAs share an SM) while each thread keeps an online (max, sum-of-exp) pair;
+// after one block reduction the gradient is produced from the staged copy:
+//   loss_row = logsumexp(z) - z[label];  dz = (softmax(z) - onehot) * grad_scale / n_valid.
 // Rows with label == -100 write zeros (ignore_index, ...embed_decoder_2.py:243) and contribute nothing.
-constexpr int kCeThreads = 512;
+constexpr int kCeThreads = 256;
 
 template <bool Z_BF16>
 __global__ void __launch_bounds__(kCeThreads)
 masked_ce_kernel(const void* __restrict__ z_in, const long long* __restrict__ labels, int V, const float* __restrict__ meta,
                  float grad_scale, void* __restrict__ dz_out, float* __restrict__ row_loss) {
-  extern __shared__ float zs[];  // V floats
-  __shared__ float red[kCeThreads / 32];
-  __shared__ float bcast;
+  extern __shared__ uint4 zs[];  // the row, raw: V/8 uint4 (bf16) or V/4 uint4 (fp32)
+  __shared__ float red_m[kCeThreads / 32], red_s[kCeThreads / 32];
+  __shared__ float bc_m, bc_s;
+  constexpr int EPV = Z_BF16 ? 8 : 4;  // elements per 16-byte vector
   const int row = blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const long long label = labels[row];
   const bool valid = label != -100;
-  const int nvec = V >> 3;  // V % 8 == 0 enforced on the host
+  const int nvec = V / EPV;  // V % 8 == 0 enforced on the host
+  const size_t esize = Z_BF16 ? 2 : 4;
+  const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(z_in) + (size_t)row * V * esize);
+  uint4* dst = dz_out ? reinterpret_cast<uint4*>(reinterpret_cast<char*>(dz_out) + (size_t)row * V * esize) : nullptr;
   if (!valid) {
-    if (dz_out != nullptr) {
+    if (dst != nullptr) {
       const uint4 z4 = make_uint4(0, 0, 0, 0);
-      if constexpr (Z_BF16) {
-        uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dz_out) + (long long)row * V);
-        for (int v = t; v < nvec; v += kCeThreads) st_stream(d + v, z4);
-      } else {
-        uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<float*>(dz_out) + (long long)row * V);
-        for (int v = t; v < 2 * nvec; v += kCeThreads) st_stream(d + v, z4);
-      }
+      for (int v = t; v < nvec; v += kCeThreads) st_stream(dst + v, z4);
     }
     if (t == 0) row_loss[row] = 0.f;
     return;
   }
-  // pass 1: stage + max
-  float mx = -INFINITY;
-  for (int v = t; v < nvec; v += kCeThreads) {
-    float x[8];
+  auto unpack = [](const uint4& u, float* x) {
     if constexpr (Z_BF16) {
-      const uint4 u = ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(z_in) + (long long)row * V) + v);
-      const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { x[2 * q] = bf16lo(ww[q]); x[2 * q + 1] = bf16hi(ww[q]); }
+      x[0] = bf16lo(u.x); x[1] = bf16hi(u.x); x[2] = bf16lo(u.y); x[3] = bf16hi(u.y);
+      x[4] = bf16lo(u.z); x[5] = bf16hi(u.z); x[6] = bf16lo(u.w); x[7] = bf16hi(u.w);
     } else {
-      const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(z_in) + (long long)row * V) + 2 * v;
-      const uint4 a = ld_stream(p), b = ld_stream(p + 1);
-      x[0] = __uint_as_float(a.x); x[1] = __uint_as_float(a.y); x[2] = __uint_as_float(a.z); x[3] = __uint_as_float(a.w);
-      x[4] = __uint_as_float(b.x); x[5] = __uint_as_float(b.y); x[6] = __uint_as_float(b.z); x[7] = __uint_as_float(b.w);
+      x[0] = __uint_as_float(u.x); x[1] = __uint_as_float(u.y); x[2] = __uint_as_float(u.z); x[3] = __uint_as_float(u.w);
     }
-    float4* s = reinterpret_cast<float4*>(zs) + 2 * v;
-    s[0] = make_float4(x[0], x[1], x[2], x[3]);
-    s[1] = make_float4(x[4], x[5], x[6], x[7]);
+  };
+  // pass 1: HBM -> smem, online softmax statistics (4 independent 16-byte loads in flight per thread)
+  float m = -INFINITY, ssum = 0.f;
+  constexpr int U = 4;
+  for (int v0 = t; v0 < nvec; v0 += kCeThreads * U) {
+    uint4 u[U];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) mx = fmaxf(mx, x[q]);
+    for (int k = 0; k < U; ++k)
+      if (v0 + k * kCeThreads < nvec) u[k] = ld_stream(src + v0 + k * kCeThreads);
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int v = v0 + k * kCeThreads;
+      if (v >= nvec) break;
+      zs[v] = u[k];
+      float x[8];
+      unpack(u[k], x);
+      float vm = x[0];
+#pragma unroll
+      for (int q = 1; q < EPV; ++q) vm = fmaxf(vm, x[q]);
+      if (vm > m) { ssum *= __expf(m - vm); m = vm; }
+#pragma unroll
+      for (int q = 0; q < EPV; ++q) ssum += __expf(x[q] - m);
+    }
   }
-  mx = warp_max(mx);
-  if (lane == 0) red[w] = mx;
+  // block reduction of (m, ssum)
+  float wm = warp_max(m);
+  ssum = (m == -INFINITY) ? 0.f : ssum * __expf(m - wm);  // idle threads (m = -inf) contribute nothing
+  ssum = warp_sum(ssum);
+  if (lane == 0) { red_m[w] = wm; red_s[w] = ssum; }
   __syncthreads();
   if (w == 0) {
-    float v = lane < kCeThreads / 32 ? red[lane] : -INFINITY;
-    v = warp_max(v);
-    if (lane == 0) bcast = v;
+    float mm = lane < kCeThreads / 32 ? red_m[lane] : -INFINITY;
+    float sv = lane < kCeThreads / 32 ? red_s[lane] : 0.f;
+    const float bm = warp_max(mm);
+    sv = (mm == -INFINITY) ? 0.f : sv * __expf(mm - bm);
+    sv = warp_sum(sv);
+    if (lane == 0) { bc_m = bm; bc_s = sv; }
   }
   __syncthreads();
-  mx = bcast;
-  // pass 2: sum of exp (from smem)
-  float sum = 0.f;
-  for (int v = t; v < 2 * nvec; v += kCeThreads) {
-    const float4 x = reinterpret_cast<const float4*>(zs)[v];
-    sum += __expf(x.x - mx) + __expf(x.y - mx) + __expf(x.z - mx) + __expf(x.w - mx);
+  const float mx = bc_m, sum = bc_s;
+  if (t == 0) {
+    float zl = __int_as_float(0x7fc00000);
+    if (label >= 0 && label < V) {
+      if constexpr (Z_BF16) zl = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(zs)[label]);
+      else zl = reinterpret_cast<const float*>(zs)[label];
+    }
+    row_loss[row] = (logf(sum) + mx) - zl;
   }
-  sum = warp_sum(sum);
-  __syncthreads();  // everyone has read bcast
-  if (lane == 0) red[w] = sum;
-  __syncthreads();
-  if (w == 0) {
-    float v = lane < kCeThreads / 32 ? red[lane] : 0.f;
-    v = warp_sum(v);
-    if (lane == 0) bcast = v;
-  }
-  __syncthreads();
-  sum = bcast;
-  if (t == 0) row_loss[row] = (label >= 0 && label < V) ? (logf(sum) + mx) - zs[label] : __int_as_float(0x7fc00000);
-  if (dz_out == nullptr) return;
-  // pass 3: gradient
+  if (dst == nullptr) return;
+  // pass 2: gradient from the staged row
   const float inv_sum = 1.0f / sum;
   const float gs = grad_scale / meta[0];
   for (int v = t; v < nvec; v += kCeThreads) {
-    const float4 a = reinterpret_cast<const float4*>(zs)[2 * v], b = reinterpret_cast<const float4*>(zs)[2 * v + 1];
-    float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    const int c0 = v * 8;
+    float x[8];
+    unpack(zs[v], x);
+    const int c0 = v * EPV;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float p = __expf(x[q] - mx) * inv_sum;
-      if (c0 + q == label) p -= 1.0f;
-      x[q] = p * gs;
+    for (int q = 0; q < EPV; ++q) {
+      float pr = __expf(x[q] - mx) * inv_sum;
+      if (c0 + q == label) pr -= 1.0f;
+      x[q] = pr * gs;
     }
-    if constexpr (Z_BF16) {
-      st_stream(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dz_out) + (long long)row * V) + v,
-                make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7])));
-    } else {
-      uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<float*>(dz_out) + (long long)row * V) + 2 * v;
-      st_stream(p, make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3])));
-      st_stream(p + 1, make_uint4(__float_as_uint(x[4]), __float_as_uint(x[5]), __float_as_uint(x[6]), __float_as_uint(x[7])));
-    }
+    if constexpr (Z_BF16)
+      st_stream(dst + v, make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7])));
+    else
+      st_stream(dst + v, make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3])));
   }
 }
 

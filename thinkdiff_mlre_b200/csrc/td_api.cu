@@ -585,7 +585,7 @@ int32_t td_masked_ce_fwd_bwd(const void* logits, int32_t dtype, const int64_t* l
   float* row_loss = c.take<float>((size_t)(R > 0 ? R : 1));
   count_valid_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const long long*>(labels), R, 1, meta);
   if (R > 0) {
-    const size_t smem = (size_t)V * sizeof(float);
+    const size_t smem = (size_t)V * (dtype == TD_DTYPE_BF16 ? 2 : 4);  // the row is staged in its input dtype
     ProfScope prof("masked_ce", double(R) * V * (dtype == TD_DTYPE_BF16 ? 2.0 : 4.0) * (dlogits ? 2.0 : 1.0), st);
     static bool attr_done[2] = {false, false};
     if (dtype == TD_DTYPE_BF16) {
