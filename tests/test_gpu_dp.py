@@ -72,7 +72,7 @@ def test_two_gpu_bucketed_allreduce_equals_oracle_mean(overlap):
     procs = [ctx.Process(target=_worker, args=(r, world, port, overlap, ret)) for r in range(world)]
     for p in procs:
         p.start()
-    got = ret.get(timeout=300)
+    got = ret.get(timeout=90)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -91,7 +91,7 @@ def test_two_gpu_bucketed_allreduce_equals_oracle_mean(overlap):
         assert err < 2e-2, (n, err)
 
 
-def _train_worker(rank, world, port, pipelined, ret):
+def _train_worker(rank, world, port, pipelined, ret, sharded=False):
     import torch.distributed as dist
 
     import thinkdiff_mlre_b200 as td
@@ -103,7 +103,7 @@ def _train_worker(rank, world, port, pipelined, ret):
     try:
         m = td.ThinkDiffAligner(DIN, D).cuda()
         m.load_state_dict(aligner_ref.init_params_numpy(DIN, D, seed=3))
-        m.enable_data_parallel(defer_wait=True)
+        m.enable_data_parallel(defer_wait=True, sharded=sharded)
         step = td.AlignerTrainStep(m, td.FusedAdamW(m, lr=1e-3), pipelined=pipelined)
         losses = []
         for j in range(4):
@@ -123,21 +123,22 @@ def test_two_gpu_pipelined_training_equals_sequential_and_keeps_replicas_in_sync
     import torch.multiprocessing as mp
 
     out = {}
-    for pipelined in (False, True):
+    for pipelined in (False, True, "sharded"):
         ctx = mp.get_context("spawn")
         ret = ctx.Queue()
         port = _free_port()
-        procs = [ctx.Process(target=_train_worker, args=(r, 2, port, pipelined, ret)) for r in range(2)]
+        procs = [ctx.Process(target=_train_worker, args=(r, 2, port, bool(pipelined), ret, pipelined == "sharded")) for r in range(2)]
         for p in procs:
             p.start()
-        res = [ret.get(timeout=300) for _ in range(2)]
+        res = [ret.get(timeout=90) for _ in range(2)]
         for p in procs:
             p.join(timeout=120)
             assert p.exitcode == 0
         out[pipelined] = {r: (params, losses) for r, params, losses in res}
-    for pipelined in (False, True):  # replicas stay identical (same averaged gradients on every rank)
+    for pipelined in (False, True, "sharded"):  # replicas stay identical (same averaged gradients on every rank)
         for a, b in zip(out[pipelined][0][0], out[pipelined][1][0]):
             np.testing.assert_array_equal(a, b)
-    for a, b in zip(out[False][0][0], out[True][0][0]):  # pipelining does not change the arithmetic
-        np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-8)
-    np.testing.assert_allclose(out[False][0][1], out[True][0][1], rtol=1e-6)
+    for mode in (True, "sharded"):  # neither pipelining nor row-sharding the optimizer changes the arithmetic
+        for a, b in zip(out[False][0][0], out[mode][0][0]):
+            np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(out[False][0][1], out[mode][0][1], rtol=1e-6)

@@ -60,13 +60,22 @@ class DataParallelState:
     remaining backward GEMMs run on the compute stream.
     """
 
-    def __init__(self, group=None, overlap: bool = True, defer_wait: bool = False):
+    def __init__(self, group=None, overlap: bool = True, defer_wait: bool = False, sharded: bool = False):
         import torch.distributed as dist
 
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
         self.overlap = overlap
+        # sharded (ZeRO-1 style, needs defer_wait + FusedAdamW): the two weight-gradient matrices are reduce-SCATTERED by
+        # rows (rank r receives rows [r D/world, (r+1) D/world)), each rank runs AdamW on its rows only and the updated
+        # bf16 rows are all-gathered; the three small vectors stay all-reduced and replicated.
+        self.sharded = sharded
+        if sharded and not defer_wait:
+            raise ValueError("sharded=True requires defer_wait=True (the optimizer consumes the shards)")
+        # a second communicator for the parameter all-gathers, so they are not queued behind the next reduce-scatter
+        self.ag_group = dist.new_group(ranks=dist.get_process_group_ranks(group) if group is not None else None) if sharded and self.world > 1 else group
         # defer_wait: backward returns without ordering the compute stream after the all-reduces; the consumer of the
         # gradients (FusedAdamW, or aligner.wait_grads()) waits bucket by bucket, so the Linear2 update overlaps the
         # Linear1 all-reduce.
@@ -75,17 +84,46 @@ class DataParallelState:
     def all_reduce_async(self, flat):
         return self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
 
+    def shard_rows(self, rows: int):
+        if rows % self.world:
+            raise ValueError(f"sharded data parallel needs the {rows} weight rows to divide by world size {self.world}")
+        n = rows // self.world
+        return self.rank * n, (self.rank + 1) * n
+
+    def reduce_scatter_rows_async(self, mat):
+        """In-place reduce-scatter of a contiguous [rows, cols] gradient: this rank's row block ends up holding the sum."""
+        lo, hi = self.shard_rows(mat.shape[0])
+        return self.dist.reduce_scatter_tensor(mat[lo:hi], mat, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def all_gather_rows_async(self, mat):
+        """In-place all-gather of a contiguous [rows, cols] tensor whose row block [lo, hi) is current on this rank."""
+        lo, hi = self.shard_rows(mat.shape[0])
+        return self.dist.all_gather_into_tensor(mat, mat[lo:hi], group=self.ag_group, async_op=True)
+
 
 class GradBuckets:
     """The aligner's five gradients laid out as two flat fp32 all-reduce buckets, in gradient-ready order:
     ``linear2 = [dW2 | db2 | dg]`` (ready after the first backward GEMM) and ``linear1 = [dW1 | db1]``.
     The parameter gradients handed to autograd are views into the buckets."""
 
-    def __init__(self, din: int, d: int, device):
-        self.linear2 = torch.empty(d * d + 2 * d, dtype=torch.float32, device=device)
-        self.linear1 = torch.empty(d * din + d, dtype=torch.float32, device=device)
-        self.dW2, self.db2, self.dg = self.linear2[: d * d].view(d, d), self.linear2[d * d : d * d + d], self.linear2[d * d + d :]
-        self.dW1, self.db1 = self.linear1[: d * din].view(d, din), self.linear1[d * din :]
+    def __init__(self, din: int, d: int, device, small_separate: bool = False):
+        # small_separate (sharded data parallel): the matrices are reduce-scattered, so the three small vectors live in
+        # their own flat buffer ``small = [db2 | dg | db1]`` and need a single all-reduce
+        self.small = torch.empty(3 * d, dtype=torch.float32, device=device) if small_separate else None
+        self.linear2 = torch.empty(d * d + (0 if small_separate else 2 * d), dtype=torch.float32, device=device)
+        self.linear1 = torch.empty(d * din + (0 if small_separate else d), dtype=torch.float32, device=device)
+        self.dW2, self.dW1 = self.linear2[: d * d].view(d, d), self.linear1[: d * din].view(d, din)
+        if small_separate:
+            self.db2, self.dg, self.db1 = self.small[:d], self.small[d : 2 * d], self.small[2 * d :]
+        else:
+            self.db2, self.dg = self.linear2[d * d : d * d + d], self.linear2[d * d + d :]
+            self.db1 = self.linear1[d * din :]
+
+    def flats(self):
+        f = {"linear2": self.linear2, "linear1": self.linear1}
+        if self.small is not None:
+            f["small"] = self.small
+        return f
 
     def in_parameter_order(self):
         return self.dW1, self.db1, self.dW2, self.db2, self.dg
@@ -114,7 +152,8 @@ class _AlignerFn(torch.autograd.Function):
         if dy.dtype not in (torch.float32, torch.bfloat16):
             dy = dy.float()
         bwd = ops.AlignerBackward(x2d, (h0, h1, h2, rstd), W2b, gf, dy.contiguous(), grad_scale=scale)
-        gb = GradBuckets(Din, D, dev)
+        gb = GradBuckets(Din, D, dev, small_separate=dp is not None and dp.sharded and dp.world > 1)
+        module._grad_flats = gb.flats()
         _reduce_and_return(module, gb, lambda: bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg), lambda: bwd.gelu_and_linear1(gb.dW1, gb.db1))
         return (None, *gb.in_parameter_order(), None, None)
 
@@ -129,6 +168,18 @@ def _reduce_and_return(module, gb, run_phase1, run_phase2):
     order = [("linear2", gb.linear2, run_phase1), ("linear1", gb.linear1, run_phase2)]
     if module._bwd_order == "linear1_first":
         order.reverse()
+    if dp is not None and dp.world > 1 and dp.sharded:
+        # fresh view objects: a collective's Work handle keeps a reference to its tensors, and autograd only adopts a
+        # returned gradient as .grad (instead of cloning it) while nobody else references that tensor object
+        big = {"linear2": gb.linear2.view(gb.dW2.shape), "linear1": gb.linear1.view(gb.dW1.shape)}
+        module.wait_grads()
+        works = {}
+        for name, _, launch in order:  # each matrix's reduce-scatter starts as soon as its GEMM is enqueued
+            launch()
+            works[name + ".big"] = dp.reduce_scatter_rows_async(big[name])
+        works["small"] = dp.all_reduce_async(gb.small[:])  # [db2 | dg | db1], 48 KB
+        module._pending = works
+        return
     works = {}
     order[0][2]()
     if dp is not None and dp.world > 1 and dp.overlap:
@@ -165,7 +216,8 @@ class _AlignerMSEFn(torch.autograd.Function):
         dp = module._dp
         scale = 1.0 / dp.world if dp is not None else 1.0
         bwd = ops.AlignerBackwardFromDh2(x2d, (h0, h1, dh2, dg_unit, db2_unit), W2b, grad_loss, grad_scale=scale)
-        gb = GradBuckets(x2d.shape[1], W2b.shape[0], x2d.device)
+        gb = GradBuckets(x2d.shape[1], W2b.shape[0], x2d.device, small_separate=dp is not None and dp.sharded and dp.world > 1)
+        module._grad_flats = gb.flats()
         _reduce_and_return(module, gb, lambda: bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg), lambda: bwd.gelu_and_linear1(gb.dW1, gb.db1))
         return (None, None, *gb.in_parameter_order(), None)
 
@@ -186,6 +238,7 @@ class ThinkDiffAligner(nn.Sequential):
         self._cache = None      # persistent bf16 compute copies of (W1, b1, W2, b2)
         self._bf16_fresh = False  # set by FusedAdamW: the copies were written by the optimizer step itself
         self._pending = {}      # bucket name -> in-flight all-reduce (defer_wait mode)
+        self._grad_flats = None  # the flat gradient buckets of the last backward ({"linear2": ..., "linear1": ...})
         self._bwd_order = "linear2_first"   # or "linear1_first" (pipelined train step)
         self._between_fwd_stages = None     # callable run between Linear1 and Linear2 of the fused-loss forward
         self._bf16_managed = False          # True: an optimizer keeps the bf16 copies current; training never re-casts
@@ -198,9 +251,19 @@ class ThinkDiffAligner(nn.Sequential):
         return {"mm_projector_type": FUSED_TYPE}
 
     # -- data parallel (replaces DDP for this module)
-    def enable_data_parallel(self, group=None, overlap: bool = True, defer_wait: bool = False):
-        self._dp = DataParallelState(group, overlap, defer_wait)
+    def enable_data_parallel(self, group=None, overlap: bool = True, defer_wait: bool = False, sharded: bool = False):
+        self._dp = DataParallelState(group, overlap, defer_wait, sharded)
         return self
+
+    def sync_parameters(self):
+        """Sharded data parallel: all-gather the fp32 master rows every rank updated for the others (collective; call on
+        all ranks before reading parameters / saving a checkpoint). No-op otherwise."""
+        dp = self._dp
+        if dp is None or not dp.sharded or dp.world == 1:
+            return
+        works = [dp.all_gather_rows_async(self[0].weight.data), dp.all_gather_rows_async(self[2].weight.data)]
+        for w in works:
+            w.wait()
 
     BUCKETS = {"linear2": ("2.weight", "2.bias", "3.weight"), "linear1": ("0.weight", "0.bias")}
 
@@ -209,6 +272,19 @@ class ThinkDiffAligner(nn.Sequential):
         w = self._pending.pop(name, None)
         if w is not None:
             w.wait()
+
+    def bucket_grads(self, name: str):
+        """Views (in BUCKETS[name] order) into the flat gradient bucket written by the last backward."""
+        flats = self._grad_flats
+        flat, small = flats[name], flats.get("small")
+        d, din = self.hidden_size, self.mm_hidden_size
+        if name == "linear2":
+            if small is not None:
+                return flat.view(d, d), small[:d], small[d : 2 * d]
+            return flat[: d * d].view(d, d), flat[d * d : d * d + d], flat[d * d + d :]
+        if small is not None:
+            return flat.view(d, din), small[2 * d :]
+        return flat[: d * din].view(d, din), flat[d * din :]
 
     def wait_grads(self):
         for name in list(self._pending):

@@ -28,6 +28,25 @@ class FusedAdamW(torch.optim.Optimizer):
         self.grad_scale = 1.0  # multiply gradients by this before the update (1 / static loss scale)
         self._t = 0
 
+    def _grads(self, name: str):
+        """{key: gradient} for one bucket. Under data parallel the gradients are read from the flat buckets the backward
+        wrote (and the collectives reduced in place); ``.grad`` must alias them -- a mismatch means autograd accumulated or
+        cloned (e.g. two backward passes per step), which the in-place bucket reduction cannot support."""
+        a = self.aligner
+        named = dict(a.named_parameters())
+        keys = ThinkDiffAligner.BUCKETS[name]
+        dp = a._dp
+        if dp is None or dp.world == 1 or a._grad_flats is None or a._grad_flats.get(name) is None:
+            return {k: named[k].grad for k in keys if named[k].grad is not None}
+        views = dict(zip(keys, a.bucket_grads(name)))
+        for k, v in views.items():
+            g = named[k].grad
+            if g is not None and g.data_ptr() != v.data_ptr():
+                raise RuntimeError(
+                    f"{k}.grad does not alias the all-reduced gradient bucket: data-parallel FusedAdamW supports exactly one "
+                    "backward per optimizer step (no gradient accumulation)")
+        return views
+
     def _group_of(self, p):
         for g in self.param_groups:
             if any(p is q for q in g["params"]):
@@ -44,8 +63,9 @@ class FusedAdamW(torch.optim.Optimizer):
         a.wait_bucket(name)
         named = dict(a.named_parameters())
         bf16 = dict(zip(("0.weight", "0.bias", "2.weight", "2.bias"), a._bf16_buffers()))
-        ps = [named[k] for k in ThinkDiffAligner.BUCKETS[name] if named[k].grad is not None]
-        keys = [k for k in ThinkDiffAligner.BUCKETS[name] if named[k].grad is not None]
+        grads = self._grads(name)
+        keys = [k for k in ThinkDiffAligner.BUCKETS[name] if k in grads]
+        ps = [named[k] for k in keys]
         if not ps:
             return
         g0 = self._group_of(ps[0])
@@ -58,8 +78,8 @@ class FusedAdamW(torch.optim.Optimizer):
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             st["step"] = t
-            if p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
-                raise TypeError("FusedAdamW needs contiguous float32 parameters and gradients")
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise TypeError("FusedAdamW needs contiguous float32 parameters")
             states.append(st)
         groups = [self._group_of(p) for p in ps]
         if any(g["lr"] != g0["lr"] or g["betas"] != g0["betas"] or g["eps"] != g0["eps"] for g in groups):
@@ -67,7 +87,7 @@ class FusedAdamW(torch.optim.Optimizer):
         L.launch_count += 1
         L.check(
             L.lib().td_adamw_step(
-                n, arr([p.data_ptr() for p in ps]), arr([p.grad.data_ptr() for p in ps]),
+                n, arr([p.data_ptr() for p in ps]), arr([grads[k].data_ptr() for k in keys]),
                 arr([s["exp_avg"].data_ptr() for s in states]), arr([s["exp_avg_sq"].data_ptr() for s in states]),
                 arr([bf16[k].data_ptr() if k in bf16 else None for k in keys]),
                 (C.c_int64 * n)(*[p.numel() for p in ps]), (C.c_float * n)(*[g["weight_decay"] for g in groups]),
@@ -77,6 +97,88 @@ class FusedAdamW(torch.optim.Optimizer):
         if release_grads:
             for p in ps:
                 p.grad = None
+            if a._grad_flats is not None:
+                a._grad_flats[name] = None
+
+    @torch.no_grad()
+    def launch_sharded_update(self, name: str, t: int):
+        """Sharded data parallel (current stream = the caller's update stream): wait for this bucket's reduce-scatter,
+        run AdamW on this rank's rows of the weight matrix, start the all-gather of the updated bf16 rows, and update the
+        bucket's small vectors (all-reduced, replicated). Returns the all-gather's Work handle."""
+        a = self.aligner
+        dp = a._dp
+        named = dict(a.named_parameters())
+        wkey = "2.weight" if name == "linear2" else "0.weight"
+        W = named[wkey]
+        Wb = dict(zip(("0.weight", "0.bias", "2.weight", "2.bias"), a._bf16_buffers()))[wkey]
+        lo, hi = dp.shard_rows(W.shape[0])
+        grads = self._grads(name)
+        a.wait_bucket(name + ".big")
+        st = self.state[W]
+        if "exp_avg" not in st or st["exp_avg"].shape[0] != hi - lo:
+            st["exp_avg"] = torch.zeros((hi - lo, W.shape[1]), dtype=torch.float32, device=W.device)
+            st["exp_avg_sq"] = torch.zeros((hi - lo, W.shape[1]), dtype=torch.float32, device=W.device)
+            st["shard_rows"] = (lo, hi)
+        st["step"] = t
+        g = self._group_of(W)
+        one = lambda x: (C.c_void_p * 1)(x)  # noqa: E731
+        L.launch_count += 1
+        L.check(
+            L.lib().td_adamw_step(1, one(W.data[lo:hi].data_ptr()), one(grads[wkey][lo:hi].data_ptr()), one(st["exp_avg"].data_ptr()),
+                                  one(st["exp_avg_sq"].data_ptr()), one(Wb[lo:hi].data_ptr()), (C.c_int64 * 1)((hi - lo) * W.shape[1]),
+                                  (C.c_float * 1)(g["weight_decay"]), g["lr"], g["betas"][0], g["betas"][1], g["eps"], t,
+                                  self.grad_scale, L.stream_ptr()),
+            "td_adamw_step",
+        )
+        ag = dp.all_gather_rows_async(Wb)
+        W.grad = None
+        a._grad_flats[name] = None
+        return ag
+
+    @torch.no_grad()
+    def launch_small_update(self, t: int):
+        """Sharded data parallel: the three small vectors (b2, g, b1) are all-reduced together and updated on every rank."""
+        a = self.aligner
+        small, d = a._grad_flats["small"], a.hidden_size
+        grads = {"2.bias": small[:d], "3.weight": small[d : 2 * d], "0.bias": small[2 * d :]}  # GradBuckets layout
+        a.wait_bucket("small")
+        keys = ["2.bias", "3.weight", "0.bias"]
+        self._update_tensors(keys, t, grads)
+        named = dict(a.named_parameters())
+        for k in keys:
+            named[k].grad = None
+        a._grad_flats["small"] = None
+
+    @torch.no_grad()
+    def _update_tensors(self, keys, t: int, grads):
+        a = self.aligner
+        named = dict(a.named_parameters())
+        bf16 = dict(zip(("0.weight", "0.bias", "2.weight", "2.bias"), a._bf16_buffers()))
+        ps = [named[k] for k in keys]
+        n = len(ps)
+        if n == 0:
+            return
+        arr = lambda ptrs: (C.c_void_p * n)(*ptrs)  # noqa: E731
+        states = []
+        for p in ps:
+            st = self.state[p]
+            if "exp_avg" not in st:
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["step"] = t
+            states.append(st)
+        groups = [self._group_of(p) for p in ps]
+        g0 = groups[0]
+        L.launch_count += 1
+        L.check(
+            L.lib().td_adamw_step(
+                n, arr([p.data_ptr() for p in ps]), arr([grads[k].data_ptr() for k in keys]),
+                arr([s["exp_avg"].data_ptr() for s in states]), arr([s["exp_avg_sq"].data_ptr() for s in states]),
+                arr([bf16[k].data_ptr() if k in bf16 else None for k in keys]),
+                (C.c_int64 * n)(*[p.numel() for p in ps]), (C.c_float * n)(*[g["weight_decay"] for g in groups]),
+                g0["lr"], g0["betas"][0], g0["betas"][1], g0["eps"], t, self.grad_scale, L.stream_ptr()),
+            "td_adamw_step",
+        )
 
     def next_step_number(self) -> int:
         self._t += 1

@@ -66,12 +66,18 @@ class AlignerTrainStep:
         # order of updates as the sequential step; call flush() before reading parameters outside the loop.
         self.pipelined = pipelined
         self._pending_t = None
+        self._sharded = False
         if pipelined:
             from .optim import FusedAdamW
 
             if not (isinstance(optimizer, FusedAdamW) and fused_loss):
                 raise ValueError("pipelined=True needs FusedAdamW and fused_loss=True")
             aligner._bwd_order = "linear1_first"
+            dp = aligner._dp
+            # sharded data parallel (enable_data_parallel(sharded=True)): reduce-scatter -> AdamW on this rank's rows ->
+            # all-gather of the bf16 rows, all on a side stream that runs beside the remaining GEMMs
+            self._sharded = dp is not None and dp.sharded and dp.world > 1
+            self._ag, self._upd_done = {}, {}
 
     def step_device(self, flat, src_row_start, lens_dev, total_rows: int, l_max: int, flat_target) -> torch.Tensor:
         """Inputs already resident in HBM. Returns the (unscaled) loss as a device scalar; nothing syncs the host."""
@@ -95,7 +101,52 @@ class AlignerTrainStep:
             self.optimizer.zero_grad(set_to_none=True)
         return loss
 
+    def _wait_update(self, name: str):
+        """Order the compute stream after bucket ``name``'s sharded update (its bf16 all-gather + small-vector AdamW)."""
+        ag = self._ag.pop(name, None)
+        if ag is not None:
+            ag.wait()
+        ev = self._upd_done.pop(name, None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def _step_pipelined_sharded(self, packed, target) -> torch.Tensor:
+        a, opt = self.aligner, self.optimizer
+        opt.grad_scale = 1.0 / self.loss_scale
+        if self._pending_t is not None:
+            self._wait_update("linear1")                                  # W1 / b1 copies are current before GEMM1
+            a._between_fwd_stages = lambda: self._wait_update("linear2")  # W2 / b2 / g before GEMM2
+            a._bf16_managed = True
+        try:
+            loss = a.mse_loss_packed(packed.x, target)
+        finally:
+            a._between_fwd_stages = None
+        self._grads_hold = None  # the compute stream is now ordered after both updates of the previous step
+        (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
+        t = opt.next_step_number()
+        self._pending_t = t
+        # enqueue both buckets' updates now, on the update stream: each waits (on the device) for its reduce-scatter,
+        # i.e. for its weight-gradient GEMM, and then runs beside whatever the compute stream does next
+        if not hasattr(self, "_update_stream"):
+            self._update_stream = torch.cuda.Stream()
+        grads = list(a._grad_flats.values())
+        if not hasattr(self, "_small_done"):
+            self._small_done = torch.cuda.Event()
+        with torch.cuda.stream(self._update_stream):
+            for name in ("linear1", "linear2"):  # in gradient-ready order: each waits only for its own reduce-scatter
+                self._ag[name] = opt.launch_sharded_update(name, t)
+            opt.launch_small_update(t)  # [b2 | g | b1]: tiny all-reduce (issued last in backward), replicated AdamW
+            self._small_done.record(self._update_stream)
+            self._upd_done["linear1"] = self._small_done
+        # the gradient buckets were allocated on the compute stream and are last read on the update stream: keep them
+        # alive until the compute stream has waited for the updates (next step), instead of record_stream(), which would
+        # keep the caching allocator from recycling the 126 MB of buckets in time
+        self._grads_hold = grads
+        return loss
+
     def _step_pipelined(self, packed, target) -> torch.Tensor:
+        if self._sharded:
+            return self._step_pipelined_sharded(packed, target)
         a, opt = self.aligner, self.optimizer
         opt.grad_scale = 1.0 / self.loss_scale
         t_prev = self._pending_t
@@ -114,8 +165,14 @@ class AlignerTrainStep:
     def flush(self):
         """Apply the parameter updates still pending from the last pipelined step (no-op otherwise)."""
         if self._pending_t is not None:
-            self.optimizer.step_bucket("linear1", t=self._pending_t, release_grads=True)
-            self.optimizer.step_bucket("linear2", t=self._pending_t, release_grads=True)
+            if self._sharded:
+                self._wait_update("linear1")
+                self._wait_update("linear2")
+                self._grads_hold = None
+                self.aligner.sync_parameters()  # fp32 master rows of the other ranks
+            else:
+                self.optimizer.step_bucket("linear1", t=self._pending_t, release_grads=True)
+                self.optimizer.step_bucket("linear2", t=self._pending_t, release_grads=True)
             self.optimizer.mark_bf16_current()
             self._pending_t = None
             self.aligner._bf16_managed = False
