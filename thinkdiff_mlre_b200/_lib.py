@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libthinkdiff_b200.so")
+LIB_PATH = os.environ.get("THINKDIFF_B200_LIB", os.path.join(_HERE, "libthinkdiff_b200.so"))  # override: A/B builds
 
 F32, BF16 = 0, 1
 BWD_NORM_W2, BWD_GELU_W1, BWD_ALL = 1, 2, 3
@@ -84,9 +84,18 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_raw_stream = None
+
+
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the current device (fast path: one C call, no Stream object)."""
+    global _raw_stream
     import torch
 
+    if _raw_stream is None:
+        _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", False)
+    if _raw_stream:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -21,10 +21,19 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
       : "l"(p));
   return r;
 }
+#ifndef TD_ST_VARIANT
+#define TD_ST_VARIANT 0
+#endif
 __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
+#if TD_ST_VARIANT == 0
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                "r"(v.w)
                : "memory");
+#elif TD_ST_VARIANT == 1
+  *p = v;
+#else
+  __stcs(p, v);
+#endif
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -662,7 +671,7 @@ __global__ void loss_finish_kernel(const float* __restrict__ part, int P, const 
 constexpr int kCeThreads = 256;
 
 template <bool Z_BF16>
-__global__ void __launch_bounds__(kCeThreads)
+__global__ void __launch_bounds__(kCeThreads, 3)
 masked_ce_kernel(const void* __restrict__ z_in, const long long* __restrict__ labels, int V, const float* __restrict__ meta,
                  float grad_scale, void* __restrict__ dz_out, float* __restrict__ row_loss) {
   extern __shared__ uint4 zs[];  // the row, raw: V/8 uint4 (bf16) or V/4 uint4 (fp32)
@@ -693,9 +702,11 @@ masked_ce_kernel(const void* __restrict__ z_in, const long long* __restrict__ la
       x[0] = __uint_as_float(u.x); x[1] = __uint_as_float(u.y); x[2] = __uint_as_float(u.z); x[3] = __uint_as_float(u.w);
     }
   };
-  // pass 1: HBM -> smem, online softmax statistics (4 independent 16-byte loads in flight per thread)
-  float m = -INFINITY, ssum = 0.f;
-  constexpr int U = 4;
+  // pass 1: HBM -> smem, online softmax statistics in base 2 (x * log2e: one FFMA + one MUFU.EX2 per element);
+  // 8 independent 16-byte loads in flight per thread
+  constexpr float kLog2e = 1.4426950408889634f;
+  float m = -INFINITY, ssum = 0.f;  // m is kept in the log2 domain: m = max(x) * log2e
+  constexpr int U = 8;
   for (int v0 = t; v0 < nvec; v0 += kCeThreads * U) {
     uint4 u[U];
 #pragma unroll
@@ -711,14 +722,15 @@ masked_ce_kernel(const void* __restrict__ z_in, const long long* __restrict__ la
       float vm = x[0];
 #pragma unroll
       for (int q = 1; q < EPV; ++q) vm = fmaxf(vm, x[q]);
-      if (vm > m) { ssum *= __expf(m - vm); m = vm; }
+      vm *= kLog2e;
+      if (vm > m) { ssum *= exp2f(m - vm); m = vm; }
 #pragma unroll
-      for (int q = 0; q < EPV; ++q) ssum += __expf(x[q] - m);
+      for (int q = 0; q < EPV; ++q) ssum += exp2f(fmaf(x[q], kLog2e, -m));
     }
   }
   // block reduction of (m, ssum)
   float wm = warp_max(m);
-  ssum = (m == -INFINITY) ? 0.f : ssum * __expf(m - wm);  // idle threads (m = -inf) contribute nothing
+  ssum = (m == -INFINITY) ? 0.f : ssum * exp2f(m - wm);  // idle threads (m = -inf) contribute nothing
   ssum = warp_sum(ssum);
   if (lane == 0) { red_m[w] = wm; red_s[w] = ssum; }
   __syncthreads();
@@ -726,7 +738,7 @@ masked_ce_kernel(const void* __restrict__ z_in, const long long* __restrict__ la
     float mm = lane < kCeThreads / 32 ? red_m[lane] : -INFINITY;
     float sv = lane < kCeThreads / 32 ? red_s[lane] : 0.f;
     const float bm = warp_max(mm);
-    sv = (mm == -INFINITY) ? 0.f : sv * __expf(mm - bm);
+    sv = (mm == -INFINITY) ? 0.f : sv * exp2f(mm - bm);
     sv = warp_sum(sv);
     if (lane == 0) { bc_m = bm; bc_s = sv; }
   }
@@ -738,22 +750,21 @@ masked_ce_kernel(const void* __restrict__ z_in, const long long* __restrict__ la
       if constexpr (Z_BF16) zl = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(zs)[label]);
       else zl = reinterpret_cast<const float*>(zs)[label];
     }
-    row_loss[row] = (logf(sum) + mx) - zl;
+    row_loss[row] = (logf(sum) + mx * 0.6931471805599453f) - zl;  // mx is in the log2 domain
   }
   if (dst == nullptr) return;
-  // pass 2: gradient from the staged row
-  const float inv_sum = 1.0f / sum;
+  // pass 2: gradient from the staged row. softmax * gs = exp2(x * log2e - mx + log2(gs / sum)): one FFMA + one MUFU per
+  // element; the "- onehot" correction is applied once, by the thread that owns the label's vector.
   const float gs = grad_scale / meta[0];
+  const float shift = -mx + log2f(fabsf(gs) / sum);
+  const float sgn = gs < 0.f ? -1.f : 1.f;
+  const int label_vec = (label >= 0 && label < V) ? int(label) / EPV : -1;
   for (int v = t; v < nvec; v += kCeThreads) {
     float x[8];
     unpack(zs[v], x);
-    const int c0 = v * EPV;
 #pragma unroll
-    for (int q = 0; q < EPV; ++q) {
-      float pr = __expf(x[q] - mx) * inv_sum;
-      if (c0 + q == label) pr -= 1.0f;
-      x[q] = pr * gs;
-    }
+    for (int q = 0; q < EPV; ++q) x[q] = sgn * exp2f(fmaf(x[q], kLog2e, shift));
+    if (v == label_vec) x[int(label) - v * EPV] -= gs;
     if constexpr (Z_BF16)
       st_stream(dst + v, make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7])));
     else

@@ -27,13 +27,15 @@ class FusedAdamW(torch.optim.Optimizer):
         self.aligner = aligner
         self.grad_scale = 1.0  # multiply gradients by this before the update (1 / static loss scale)
         self._t = 0
+        self._named_cache = None
+        self._group_cache = {}
 
     def _grads(self, name: str):
         """{key: gradient} for one bucket. Under data parallel the gradients are read from the flat buckets the backward
         wrote (and the collectives reduced in place); ``.grad`` must alias them -- a mismatch means autograd accumulated or
         cloned (e.g. two backward passes per step), which the in-place bucket reduction cannot support."""
         a = self.aligner
-        named = dict(a.named_parameters())
+        named = self._named()
         keys = ThinkDiffAligner.BUCKETS[name]
         dp = a._dp
         if dp is None or dp.world == 1 or a._grad_flats is None or a._grad_flats.get(name) is None:
@@ -47,11 +49,24 @@ class FusedAdamW(torch.optim.Optimizer):
                     "backward per optimizer step (no gradient accumulation)")
         return views
 
+    def _named(self):
+        """name -> Parameter (cached: the aligner's parameter objects do not change)."""
+        if self._named_cache is None:
+            self._named_cache = dict(self.aligner.named_parameters())
+        return self._named_cache
+
+    def _bf16(self):
+        return dict(zip(("0.weight", "0.bias", "2.weight", "2.bias"), self.aligner._bf16_buffers()))
+
     def _group_of(self, p):
-        for g in self.param_groups:
-            if any(p is q for q in g["params"]):
-                return g
-        raise KeyError("parameter not in any group")
+        g = self._group_cache.get(id(p))
+        if g is None:
+            for g in self.param_groups:
+                if any(p is q for q in g["params"]):
+                    self._group_cache[id(p)] = g
+                    return g
+            raise KeyError("parameter not in any group")
+        return g
 
     @torch.no_grad()
     def step_bucket(self, name: str, t: int | None = None, release_grads: bool = False):
@@ -61,8 +76,8 @@ class FusedAdamW(torch.optim.Optimizer):
         a = self.aligner
         t = self._t if t is None else t
         a.wait_bucket(name)
-        named = dict(a.named_parameters())
-        bf16 = dict(zip(("0.weight", "0.bias", "2.weight", "2.bias"), a._bf16_buffers()))
+        named = self._named()
+        bf16 = self._bf16()
         grads = self._grads(name)
         keys = [k for k in ThinkDiffAligner.BUCKETS[name] if k in grads]
         ps = [named[k] for k in keys]
@@ -107,10 +122,10 @@ class FusedAdamW(torch.optim.Optimizer):
         bucket's small vectors (all-reduced, replicated). Returns the all-gather's Work handle."""
         a = self.aligner
         dp = a._dp
-        named = dict(a.named_parameters())
+        named = self._named()
         wkey = "2.weight" if name == "linear2" else "0.weight"
         W = named[wkey]
-        Wb = dict(zip(("0.weight", "0.bias", "2.weight", "2.bias"), a._bf16_buffers()))[wkey]
+        Wb = self._bf16()[wkey]
         lo, hi = dp.shard_rows(W.shape[0])
         grads = self._grads(name)
         a.wait_bucket(name + ".big")
@@ -144,7 +159,7 @@ class FusedAdamW(torch.optim.Optimizer):
         a.wait_bucket("small")
         keys = ["2.bias", "3.weight", "0.bias"]
         self._update_tensors(keys, t, grads)
-        named = dict(a.named_parameters())
+        named = self._named()
         for k in keys:
             named[k].grad = None
         a._grad_flats["small"] = None
@@ -152,8 +167,8 @@ class FusedAdamW(torch.optim.Optimizer):
     @torch.no_grad()
     def _update_tensors(self, keys, t: int, grads):
         a = self.aligner
-        named = dict(a.named_parameters())
-        bf16 = dict(zip(("0.weight", "0.bias", "2.weight", "2.bias"), a._bf16_buffers()))
+        named = self._named()
+        bf16 = self._bf16()
         ps = [named[k] for k in keys]
         n = len(ps)
         if n == 0:
