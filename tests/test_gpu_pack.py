@@ -115,3 +115,42 @@ def test_pack_full_size_long_context_roundtrip():
     # packing the padded batch again (source = padded rows) is idempotent
     again = td.pack_device(padded.reshape(-1, 3584), torch.arange(128, device=dev) * b.l_max, lens, b.total_rows, b.l_max)
     assert torch.equal(again.x.view(torch.int16), pb.x.view(torch.int16))
+
+
+def test_clip_two_image_plus_text_composition_config4():
+    """BASELINE config 4 (per-GPU shard: 32 samples): 2 x 32 CLIP tokens [.., 768] -> aligner (pure-bf16 inference
+    regime) -> [64, 4096] per sample, composed with ragged T5 text embeddings [T_i, 4096], T_i ~ U{1..128}. The packed
+    rows and the padded prompt_embeds must equal the reference's per-sample torch.cat (bit-exact: byte moves)."""
+    import thinkdiff_mlre_b200 as td
+    from oracle import aligner_ref
+
+    dev = torch.device("cuda")
+    B, n_img, din, d = 32, 64, 768, 4096
+    g = torch.Generator().manual_seed(4)
+    m = td.ThinkDiffAligner(din, d).to(dev)
+    m.load_state_dict(aligner_ref.init_params_numpy(din, d, seed=4))
+    m = m.to(torch.bfloat16).eval()
+    img = torch.randn((B, n_img, din), generator=g).to(torch.bfloat16).to(dev)
+    with torch.no_grad():
+        y = m(img)
+    assert y.shape == (B, n_img, d) and y.dtype == torch.bfloat16
+    t_lens = torch.randint(1, 129, (B,), generator=g).tolist()
+    text = torch.randn((sum(t_lens), d), generator=g).to(torch.bfloat16).to(dev)
+    pb = td.compose_image_text(y, text, t_lens)
+    off, want = 0, []
+    for i in range(B):
+        want.append(torch.cat([y[i], text[off : off + t_lens[i]]]))
+        off += t_lens[i]
+    assert torch.equal(pb.x.view(torch.int16), torch.cat(want).view(torch.int16))
+    assert pb.cu_seqlens.tolist() == [0] + torch.cumsum(torch.tensor([n_img + t for t in t_lens]), 0).tolist()
+    padded, mask = pb.to_padded()
+    assert padded.shape == (B, n_img + max(t_lens), d)
+    for i in range(B):
+        n = n_img + t_lens[i]
+        assert torch.equal(padded[i, :n].view(torch.int16), want[i].view(torch.int16))
+        assert not padded[i, n:].view(torch.int16).any() and mask[i].sum().item() == n
+    # the aligner rows themselves: pure-bf16 regime vs the oracle on a few samples
+    p16 = {k: v.to(torch.bfloat16).float() for k, v in aligner_ref.init_params_numpy(din, d, seed=4).items()}
+    ref = aligner_ref.aligner_fwd_bwd_manual(img[:2].reshape(-1, din).float().cpu(), p16, regime="bf16", out_bf16=True, accum_dtype=torch.float32)
+    err = (y[:2].reshape(-1, d).float().cpu() - ref["y"]).norm() / ref["y"].norm()
+    assert err < 2e-2

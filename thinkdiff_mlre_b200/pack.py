@@ -115,3 +115,29 @@ def pack_device(flat, src_row_start, lens_dev, total_rows: int, l_max: int, lens
     cu = ops.cu_seqlens(lens_dev)
     x = ops.pack_varlen(flat, src_row_start, cu, total_rows)
     return PackedBatch(x, cu, lens_host, l_max, extras or {})
+
+
+def compose_image_text(image_tokens: torch.Tensor, text_flat: torch.Tensor, text_lens) -> PackedBatch:
+    """Ragged composition of aligner outputs with T5 text embeddings (BASELINE config 4; layout of the reference's
+    two-image demo, scripts/test/test_blip_vision_t5_decoder_flux_text.py:184-208: ``torch.cat([img1, img2, text], dim=1)``
+    per sample). ``image_tokens [B, N_img, D]`` (e.g. 2 x 32 aligner tokens), ``text_flat [sum T_i, D]`` with ``text_lens[B]``
+    (host ints). One gather kernel writes ``[img_i | text_i]`` for every sample back to back; ``to_padded()`` then gives
+    the ``[B, L_max, D]`` prompt_embeds + int64 mask a Flux / T5 consumer takes."""
+    B, n_img, D = image_tokens.shape
+    text_lens = [int(t) for t in text_lens]
+    if len(text_lens) != B or text_flat.shape[1] != D or text_flat.dtype != image_tokens.dtype:
+        raise ValueError("text_flat / text_lens do not match image_tokens")
+    dev = image_tokens.device
+    flat = torch.cat([image_tokens.reshape(B * n_img, D), text_flat])  # segments of one source buffer
+    text_start = [0] * B
+    for i in range(1, B):
+        text_start[i] = text_start[i - 1] + text_lens[i - 1]
+    starts, lens = [], []
+    for i in range(B):  # two segments per sample: its image rows, then its text rows
+        starts += [i * n_img, B * n_img + text_start[i]]
+        lens += [n_img, text_lens[i]]
+    start_t = torch.tensor(starts, dtype=torch.int64).to(dev, non_blocking=True)
+    lens_t = torch.tensor(lens, dtype=torch.int32).to(dev, non_blocking=True)
+    seg = pack_device(flat, start_t, lens_t, sum(lens), max(n_img + t for t in text_lens))
+    sample_lens = torch.tensor([n_img + t for t in text_lens], dtype=torch.int32)
+    return PackedBatch(seg.x, seg.cu_seqlens[::2].contiguous(), sample_lens, int(sample_lens.max()), {"n_img": n_img})
