@@ -48,6 +48,11 @@ int32_t td_cu_seqlens(const int32_t* lens, int32_t B, int32_t* cu_seqlens /*[B+1
 int32_t td_pack_varlen(const void* src, const int64_t* src_row_start /*[B]*/, const int32_t* cu_seqlens /*[B+1]*/,
                        int32_t B, int64_t total_rows /* = cu_seqlens[B], known to the host */, int64_t row_bytes,
                        void* dst_packed /*[total_rows, row_bytes]*/, td_stream_t stream);
+/* Same, and also writes src_row_out[r] (int64, may be NULL) = the source row that packed row r came from, so that a sibling
+ * tensor in the same ragged source layout (e.g. the T5 targets) can be read in place instead of being packed too. */
+int32_t td_pack_varlen_indexed(const void* src, const int64_t* src_row_start, const int32_t* cu_seqlens, int32_t B,
+                               int64_t total_rows, int64_t row_bytes, void* dst_packed, int64_t* src_row_out,
+                               td_stream_t stream);
 /* Reference layout: zero-padded [B, L_max, row_bytes] + int64 mask [B, L_max] (mask may be NULL). With
  * src = a packed buffer and src_row_start[i] = cu_seqlens[i] this is the inverse of td_pack_varlen. */
 int32_t td_pack_padded(const void* src, const int64_t* src_row_start, const int32_t* cu_seqlens, int32_t B, int32_t L_max,
@@ -77,20 +82,23 @@ int32_t td_aligner_bwd(const void* dy, int32_t dy_dtype, const void* x, const vo
 
 /* Fused training path against T5 targets (masked MSE over all M packed rows): forward GEMMs, then ONE pass that forms
  * y = T5LayerNorm(h2) in registers, accumulates sum (y - target)^2 and writes the norm backward of dy = 2 (y - target) / (M D)
- * -- y and dy never touch HBM. Outputs for a UNIT upstream gradient: dh2 bf16 [M, D], dg_unit / db2_unit fp32 [D], and the
- * loss (fp32 device scalar). td_aligner_bwd_dh2 finishes the backward, multiplying by grad_scale * (*grad_scale_ptr)
+ * -- y and dy never touch HBM. Outputs for a UNIT upstream gradient: dh2 bf16 [M, D], the per-CTA partial column sums for
+ * dg / db2 (`norm_partials`, td_aligner_norm_partials_bytes bytes, caller-owned until the backward) and the loss (fp32 device
+ * scalar). `target` rows are read at target_row_index[r] (int64 [M]) when given, else at r -- targets in the un-packed
+ * source layout need no pack pass. td_aligner_bwd_dh2 finishes the backward, multiplying by grad_scale * (*grad_scale_ptr)
  * (grad_scale_ptr: optional DEVICE scalar = the upstream gradient of the loss, e.g. GradScaler's scale; no host sync).
  * Same gradients as td_aligner_fwd -> td_masked_mse_fwd_bwd -> td_aligner_bwd (base_task.py:237-244 with an MSE loss).
  * `stages` lets the caller run Linear1 and the rest as two calls (same buffers), e.g. to apply the Linear2 parameter update
  * of the previous step in between while that bucket's all-reduce was still in flight. */
 int64_t td_aligner_mse_fwd_workspace_bytes(int64_t M, int32_t Din, int32_t D);
+int64_t td_aligner_norm_partials_bytes(int64_t M, int32_t D);
 int32_t td_aligner_mse_fwd(const void* x, int64_t M, int32_t Din, int32_t D, const void* W1, const void* b1, const void* W2,
-                           const void* b2, const float* g, float eps, const void* target, int32_t target_dtype, void* h0,
-                           void* h1, void* dh2, float* dg_unit, float* db2_unit, float* loss, void* workspace,
-                           int64_t workspace_bytes, int32_t stages /* 1 = Linear1+GELU, 2 = the rest, 3 = all */,
-                           td_stream_t stream);
+                           const void* b2, const float* g, float eps, const void* target, int32_t target_dtype,
+                           const int64_t* target_row_index, void* h0, void* h1, void* dh2, void* norm_partials, float* loss,
+                           void* workspace, int64_t workspace_bytes,
+                           int32_t stages /* 1 = Linear1+GELU, 2 = the rest, 3 = all */, td_stream_t stream);
 int32_t td_aligner_bwd_dh2(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
-                           const float* dg_unit, const float* db2_unit, int64_t M, int32_t Din, int32_t D, float grad_scale,
+                           const void* norm_partials, int64_t M, int32_t Din, int32_t D, float grad_scale,
                            const float* grad_scale_ptr, float* dW1, float* db1, float* dW2, float* db2, float* dg,
                            void* workspace, int64_t workspace_bytes, int32_t phases, td_stream_t stream);
 

@@ -468,3 +468,26 @@ def test_no_out_of_bounds_writes_canary():
     with torch.autocast("cuda", dtype=torch.bfloat16), torch.no_grad():
         y_ref = m(x)
     assert torch.equal(y, y_ref)
+
+
+def test_fused_mse_reads_targets_through_row_index():
+    """Targets left in the ragged source layout + the row index from the feature pack == packed targets."""
+    import thinkdiff_mlre_b200 as td
+    from thinkdiff_mlre_b200 import ops
+
+    m, _ = make_module(192, 512, seed=61)
+    b = td.synthetic_lvlm_batch(7, 60, 192, 512, seed=9, pin=False)
+    flat, start, lens, tgt = b.flat.cuda(), b.src_row_start.cuda(), b.lens.cuda(), b.extras["flat_target"].cuda()
+    cu = ops.cu_seqlens(lens)
+    x, index = ops.pack_varlen(flat, start, cu, b.total_rows, want_index=True)
+    t_packed = ops.pack_varlen(tgt, start, cu, b.total_rows)
+    assert torch.equal(tgt[index].view(torch.int16), t_packed.view(torch.int16))
+    l1 = m.mse_loss_packed(x, t_packed)
+    l1.backward()
+    g1 = [p.grad.clone() for p in m.parameters()]
+    m.zero_grad(set_to_none=True)
+    l2 = m.mse_loss_packed(x, tgt, index)
+    l2.backward()
+    assert torch.equal(l1, l2)
+    for a, p in zip(g1, m.parameters()):
+        assert torch.equal(a, p.grad)

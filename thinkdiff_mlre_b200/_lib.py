@@ -25,6 +25,7 @@ SIGNATURES = {
     "td_profile_report": (_i32, [C.c_char_p, _i32]),
     "td_cu_seqlens": (_i32, [_vp, _i32, _vp, _vp]),
     "td_pack_varlen": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp]),
+    "td_pack_varlen_indexed": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp]),
     "td_pack_padded": (_i32, [_vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]),
     "td_cast_f32_to_bf16": (_i32, [_vp, _vp, _i64, _vp]),
     "td_aligner_fwd_workspace_bytes": (_i64, [_i64, _i32, _i32]),
@@ -32,8 +33,9 @@ SIGNATURES = {
     "td_aligner_bwd_workspace_bytes": (_i64, [_i64, _i32, _i32]),
     "td_aligner_bwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "td_aligner_mse_fwd_workspace_bytes": (_i64, [_i64, _i32, _i32]),
+    "td_aligner_norm_partials_bytes": (_i64, [_i64, _i32]),
     "td_aligner_mse_fwd": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
-    "td_aligner_bwd_dh2": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "td_aligner_bwd_dh2": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "td_rmsnorm_fwd": (_i32, [_vp, _vp, _f32, _i64, _i32, _vp, _i32, _vp, _vp]),
     "td_rmsnorm_bwd_workspace_bytes": (_i64, [_i64, _i32]),
     "td_rmsnorm_bwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),

@@ -201,25 +201,26 @@ class _AlignerMSEFn(torch.autograd.Function):
     """loss = mean((aligner(x) - target)^2) with y / dy never materialised (td_aligner_mse_fwd / td_aligner_bwd_dh2)."""
 
     @staticmethod
-    def forward(ctx, x2d, target, W1, b1, W2, b2, g, module):
+    def forward(ctx, x2d, target, W1, b1, W2, b2, g, module, target_row_index):
         W1b, b1b, W2b, b2b = module._bf16_params()
         gf = g.detach() if g.dtype == torch.float32 else g.detach().float()
-        loss, saved = ops.aligner_mse_fwd(x2d, W1b, b1b, W2b, b2b, gf, module.eps, target, module._between_fwd_stages)
+        loss, saved = ops.aligner_mse_fwd(x2d, W1b, b1b, W2b, b2b, gf, module.eps, target, module._between_fwd_stages,
+                                          target_row_index)
         ctx.save_for_backward(x2d, W2b, *saved)
         ctx.module = module
         return loss
 
     @staticmethod
     def backward(ctx, grad_loss):
-        x2d, W2b, h0, h1, dh2, dg_unit, db2_unit = ctx.saved_tensors
+        x2d, W2b, h0, h1, dh2, partials = ctx.saved_tensors
         module = ctx.module
         dp = module._dp
         scale = 1.0 / dp.world if dp is not None else 1.0
-        bwd = ops.AlignerBackwardFromDh2(x2d, (h0, h1, dh2, dg_unit, db2_unit), W2b, grad_loss, grad_scale=scale)
+        bwd = ops.AlignerBackwardFromDh2(x2d, (h0, h1, dh2, partials), W2b, grad_loss, grad_scale=scale)
         gb = GradBuckets(x2d.shape[1], W2b.shape[0], x2d.device, small_separate=dp is not None and dp.sharded and dp.world > 1)
         module._grad_flats = gb.flats()
         _reduce_and_return(module, gb, lambda: bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg), lambda: bwd.gelu_and_linear1(gb.dW1, gb.db1))
-        return (None, None, *gb.in_parameter_order(), None)
+        return (None, None, *gb.in_parameter_order(), None, None)
 
 
 class ThinkDiffAligner(nn.Sequential):
@@ -364,8 +365,11 @@ class ThinkDiffAligner(nn.Sequential):
                 y, _ = ops.aligner_fwd(x2d, W1b, b1b, W2b, b2b, gf, self.eps, regime == "bf16_infer", False)
         return y.reshape(*lead, self.hidden_size)
 
-    def mse_loss_packed(self, x_packed: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        """``F.mse_loss(self.forward_packed(x_packed).float(), target.float())`` as ONE fused training path: the norm
+    def mse_loss_packed(self, x_packed: torch.Tensor, target: torch.Tensor, target_row_index: torch.Tensor | None = None) -> torch.Tensor:
+        """``target_row_index`` (int64 [M], optional): row of ``target`` for each row of ``x_packed`` -- lets the targets stay
+        in their un-packed source layout (``ops.pack_varlen(..., want_index=True)`` returns it).
+
+        ``F.mse_loss(self.forward_packed(x_packed).float(), target.float())`` as ONE fused training path: the norm
         output y and its gradient are formed in registers, never written to HBM. Training regime only (fp32 parameters,
         bf16 compute, as under ``torch.autocast('cuda', dtype=torch.bfloat16)``); differentiable w.r.t. the parameters and
         compatible with a GradScaler (the upstream scalar is applied on the device inside the backward GEMM epilogues)."""
@@ -380,7 +384,7 @@ class ThinkDiffAligner(nn.Sequential):
             target = target.float()
         w1, b1, w2, b2, g = self[0].weight, self[0].bias, self[2].weight, self[2].bias, self[3].weight
         with torch.autocast("cuda", enabled=False):
-            return _AlignerMSEFn.apply(x2d, target.contiguous(), w1, b1, w2, b2, g, self)
+            return _AlignerMSEFn.apply(x2d, target.contiguous(), w1, b1, w2, b2, g, self, target_row_index)
 
     def forward_packed(self, x_packed: torch.Tensor, cu_seqlens: torch.Tensor | None = None) -> torch.Tensor:
         """Ragged entry point: ``x_packed[M, Din]`` (rows of all sequences back to back, ``cu_seqlens`` int32 [B+1]).

@@ -95,7 +95,7 @@ template <bool PADDED>
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const uint4* __restrict__ src, const long long* __restrict__ src_row_start,
                  const int* __restrict__ cu, int B, long long dst_rows, int Lmax, int vec_per_row,
-                 uint4* __restrict__ dst, long long* __restrict__ mask) {
+                 uint4* __restrict__ dst, long long* __restrict__ mask, long long* __restrict__ src_row_out) {
   __shared__ int s_cu[kPackMaxStagedSeqs + 1];
   __shared__ long long s_start[kPackMaxStagedSeqs];
   const bool staged = B <= kPackMaxStagedSeqs;
@@ -128,7 +128,9 @@ pack_rows_kernel(const uint4* __restrict__ src, const long long* __restrict__ sr
     }
     uint4* d = dst + r * vec_per_row;
     if (valid) {
-      const uint4* s = src + (start_t[i] + j) * vec_per_row;
+      const long long src_row = start_t[i] + j;
+      if (src_row_out != nullptr && lane == 0) src_row_out[r] = src_row;  // lets later kernels read sibling tensors unpacked
+      const uint4* s = src + src_row * vec_per_row;
       for (int v0 = 0; v0 < vec_per_row; v0 += 256) {
         uint4 t[8];
 #pragma unroll
@@ -402,26 +404,50 @@ rstd_from_partials_kernel(const float* __restrict__ ssq_part, int P, int M, int 
 // separate passes (norm fwd 24 KB, MSE 40 KB, norm bwd 32 KB).
 template <bool T_BF16>
 __global__ void __launch_bounds__(kNormBwdThreads)
-norm_mse_bwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restrict__ rstd_in, const float* __restrict__ g,
-                    const void* __restrict__ t_in, int M, int D, int rows_per_cta, float dy_coef,
+norm_mse_bwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restrict__ ssq_part, int P, float eps,
+                    const float* __restrict__ g, const void* __restrict__ t_in,
+                    const long long* __restrict__ t_row_index, int M, int D, int rows_per_cta, float dy_coef,
                     __nv_bfloat16* __restrict__ dh2, float* __restrict__ dg_part, float* __restrict__ db2_part,
                     float* __restrict__ loss_part) {
   constexpr int R = kNormBwdRows;
   __shared__ float red[R][kNormBwdThreads / 32];
   __shared__ float tot[R];
   __shared__ float lred[kNormBwdThreads / 32];
+  constexpr int kRstdBlock = 512;        // rows whose rstd is computed at once (one latency round per block)
+  __shared__ float rs_sm[kRstdBlock];
+  __shared__ long long ti_sm[kRstdBlock];  // target row of every row of the block (staged: no dependent global loads later)
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const bool col_ok = t * 8 < D;
   const int row_begin = blockIdx.x * rows_per_cta;
   const int row_end = min(M, row_begin + rows_per_cta);
+  // rstd = rsqrt(mean(h2^2) + eps) from the GEMM2 epilogue's partial sums ssq_part[P][M], for a block of rows at a time:
+  // warp w handles rows w, w + 16, ... of the block (lane p reads partial p), so the whole block costs one load round trip
+  auto block_rstd = [&](int b0) {
+    const int b1 = min(row_end, b0 + kRstdBlock);
+    for (int i = t; i < b1 - b0; i += kNormBwdThreads)
+      ti_sm[i] = t_row_index != nullptr ? __ldg(t_row_index + b0 + i) : (long long)(b0 + i);
+    for (int row = b0 + w; row < b1; row += kNormBwdThreads / 32) {
+      float ssq = 0.f;
+      for (int p = lane; p < P; p += 32) ssq += ssq_part[(long long)p * M + row];
+      ssq = warp_sum(ssq);
+      if (lane == 0) rs_sm[row - b0] = rsqrtf(ssq / float(D) + eps);
+    }
+  };
   float gg[8], adg[8], adb[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) { gg[q] = col_ok ? g[t * 8 + q] : 0.f; adg[q] = 0.f; adb[q] = 0.f; }
   const float inv_d = 1.0f / float(D);
   float loss_acc = 0.f;
 
+  int blk0 = row_begin - kRstdBlock;  // kRstdBlock % R == 0
   for (int r0 = row_begin; r0 < row_end; r0 += R) {
     float dyv[R][8], hv[R][8], part[R], rs[R];
+    if (r0 >= blk0 + kRstdBlock) {  // uniform across the CTA
+      __syncthreads();              // everyone is done reading the previous block's rstd
+      blk0 = r0;
+      block_rstd(blk0);
+      __syncthreads();
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int row = r0 + r;
@@ -429,23 +455,24 @@ norm_mse_bwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restric
       uint4 hu = make_uint4(0, 0, 0, 0);
       float tv[8];
       if (ok) hu = ld_stream(reinterpret_cast<const uint4*>(h2 + (long long)row * D) + t);
+      const long long trow = ok ? ti_sm[row - blk0] : 0ll;
       if constexpr (T_BF16) {
         uint4 tu = make_uint4(0, 0, 0, 0);
-        if (ok) tu = ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(t_in) + (long long)row * D) + t);
+        if (ok) tu = ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(t_in) + trow * D) + t);
         const uint32_t tw[4] = {tu.x, tu.y, tu.z, tu.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) { tv[2 * q] = bf16lo(tw[q]); tv[2 * q + 1] = bf16hi(tw[q]); }
       } else {
         uint4 t0 = make_uint4(0, 0, 0, 0), t1 = t0;
         if (ok) {
-          const uint4* tp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(t_in) + (long long)row * D) + 2 * t;
+          const uint4* tp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(t_in) + trow * D) + 2 * t;
           t0 = ld_stream(tp);
           t1 = ld_stream(tp + 1);
         }
         tv[0] = __uint_as_float(t0.x); tv[1] = __uint_as_float(t0.y); tv[2] = __uint_as_float(t0.z); tv[3] = __uint_as_float(t0.w);
         tv[4] = __uint_as_float(t1.x); tv[5] = __uint_as_float(t1.y); tv[6] = __uint_as_float(t1.z); tv[7] = __uint_as_float(t1.w);
       }
-      rs[r] = (row < row_end) ? __ldg(rstd_in + row) : 0.f;
+      rs[r] = (row < row_end) ? rs_sm[row - blk0] : 0.f;
       const uint32_t hw[4] = {hu.x, hu.y, hu.z, hu.w};
       float s = 0.f;
 #pragma unroll
@@ -648,7 +675,7 @@ masked_mse_kernel(const void* __restrict__ y_in, const void* __restrict__ t_in, 
 
 // loss = sum(part[0..P)) * (use_nd ? 1 / (n_valid * D) : 1 / n_valid); NaN when n_valid == 0 (as torch)
 __global__ void loss_finish_kernel(const float* __restrict__ part, int P, const float* __restrict__ meta, float d_or_1,
-                                   float* __restrict__ loss) {
+                                   float* __restrict__ loss, float n_valid_if_no_meta = 0.f) {
   __shared__ float wsum[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < P; i += blockDim.x) acc += part[i];
@@ -658,7 +685,7 @@ __global__ void loss_finish_kernel(const float* __restrict__ part, int P, const 
   if (threadIdx.x == 0) {
     float tot = 0.f;
     for (int i = 0; i < (blockDim.x >> 5); ++i) tot += wsum[i];
-    loss[0] = tot / (meta[0] * d_or_1);
+    loss[0] = tot / ((meta != nullptr ? meta[0] : n_valid_if_no_meta) * d_or_1);
   }
 }
 

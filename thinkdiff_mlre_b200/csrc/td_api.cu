@@ -110,8 +110,16 @@ int32_t td_cu_seqlens(const int32_t* lens, int32_t B, int32_t* cu, td_stream_t s
   return TD_OK;
 }
 
+int32_t td_pack_varlen_indexed(const void* src, const int64_t* src_row_start, const int32_t* cu, int32_t B,
+                               int64_t total_rows, int64_t row_bytes, void* dst, int64_t* src_row_out, td_stream_t stream);
+
 int32_t td_pack_varlen(const void* src, const int64_t* src_row_start, const int32_t* cu, int32_t B, int64_t total_rows,
                        int64_t row_bytes, void* dst, td_stream_t stream) {
+  return td_pack_varlen_indexed(src, src_row_start, cu, B, total_rows, row_bytes, dst, nullptr, stream);
+}
+
+int32_t td_pack_varlen_indexed(const void* src, const int64_t* src_row_start, const int32_t* cu, int32_t B,
+                               int64_t total_rows, int64_t row_bytes, void* dst, int64_t* src_row_out, td_stream_t stream) {
   TD_DEVICE_OR_RETURN();
   if (B < 0 || total_rows < 0 || row_bytes <= 0 || row_bytes % 16)
     TD_FAIL(TD_ERR_ARG, "td_pack_varlen: row_bytes=%lld must be a positive multiple of 16", (long long)row_bytes);
@@ -124,7 +132,7 @@ int32_t td_pack_varlen(const void* src, const int64_t* src_row_start, const int3
     ProfScope prof("pack_varlen", 2.0 * double(total_rows) * double(row_bytes), (cudaStream_t)stream);
     pack_rows_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
         static_cast<const uint4*>(src), reinterpret_cast<const long long*>(src_row_start), cu, B, total_rows, 0,
-        int(row_bytes / 16), static_cast<uint4*>(dst), nullptr);
+        int(row_bytes / 16), static_cast<uint4*>(dst), nullptr, reinterpret_cast<long long*>(src_row_out));
   }
   TD_CUDA(cudaGetLastError());
   return TD_OK;
@@ -145,7 +153,7 @@ int32_t td_pack_padded(const void* src, const int64_t* src_row_start, const int3
     ProfScope prof("pack_padded", 2.0 * double(rows) * double(row_bytes), (cudaStream_t)stream);
     pack_rows_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
         static_cast<const uint4*>(src), reinterpret_cast<const long long*>(src_row_start), cu, B, rows, L_max,
-        int(row_bytes / 16), static_cast<uint4*>(dst), reinterpret_cast<long long*>(mask));
+        int(row_bytes / 16), static_cast<uint4*>(dst), reinterpret_cast<long long*>(mask), nullptr);
   }
   TD_CUDA(cudaGetLastError());
   return TD_OK;
@@ -416,18 +424,20 @@ int32_t td_aligner_bwd(const void* dy, int32_t dy_dtype, const void* x, const vo
 int64_t td_aligner_mse_fwd_workspace_bytes(int64_t M, int32_t Din, int32_t D) {
   const size_t m = (size_t)(M > 0 ? M : 1);
   return td_aligner_fwd_workspace_bytes(M, Din, D) + (int64_t)align_up(sizeof(__nv_bfloat16) * m * D, 256) +
-         (int64_t)align_up(sizeof(float) * m, 256) + td_rmsnorm_bwd_workspace_bytes((int64_t)m, D) +
          (int64_t)align_up(sizeof(float) * ((size_t)device_sm_count() * 2 + 8), 256) + 256;
 }
 
+int64_t td_aligner_norm_partials_bytes(int64_t M, int32_t D) { return td_rmsnorm_bwd_workspace_bytes(M > 0 ? M : 1, D); }
+
 int32_t td_aligner_mse_fwd(const void* x, int64_t M, int32_t Din, int32_t D, const void* W1, const void* b1,
                            const void* W2, const void* b2, const float* g, float eps, const void* target,
-                           int32_t target_dtype, void* h0, void* h1, void* dh2, float* dg_unit, float* db2_unit,
-                           float* loss, void* ws, int64_t ws_bytes, int32_t stages, td_stream_t stream) {
+                           int32_t target_dtype, const int64_t* target_row_index, void* h0, void* h1, void* dh2,
+                           void* norm_partials, float* loss, void* ws, int64_t ws_bytes, int32_t stages,
+                           td_stream_t stream) {
   TD_DEVICE_OR_RETURN();
   if (!dims_ok(Din, D)) TD_FAIL(TD_ERR_UNSUPPORTED, "td_aligner_mse_fwd: Din=%d, D=%d must be multiples of 64 (D <= 4096)", Din, D);
   if (M <= 0 || M > 0x7fffffffll / D) TD_FAIL(TD_ERR_ARG, "td_aligner_mse_fwd: M=%lld out of range (needs at least one token)", (long long)M);
-  if (!x || !W1 || !W2 || !g || !target || !h0 || !h1 || !dh2 || !dg_unit || !db2_unit || !loss)
+  if (!x || !W1 || !W2 || !g || !target || !h0 || !h1 || !dh2 || !norm_partials || !loss)
     TD_FAIL(TD_ERR_ARG, "td_aligner_mse_fwd: null pointer");
   if (ws_bytes < td_aligner_mse_fwd_workspace_bytes(M, Din, D)) TD_FAIL(TD_ERR_ARG, "td_aligner_mse_fwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
@@ -435,13 +445,12 @@ int32_t td_aligner_mse_fwd(const void* x, int64_t M, int32_t Din, int32_t D, con
   const int nparts = (D + kEpiColsPerWarp - 1) / kEpiColsPerWarp;
   float* ssq_part = c.take<float>((size_t)(2 * ((D + kBlockN - 1) / kBlockN)) * (size_t)M);
   __nv_bfloat16* h2 = c.take<__nv_bfloat16>((size_t)M * D);
-  float* rstd = c.take<float>((size_t)M);
   int rpc;
   const int grid = norm_bwd_grid(M, &rpc);
-  float* dg_part = c.take<float>((size_t)grid * D);
-  float* db_part = c.take<float>((size_t)grid * D);
   float* loss_part = c.take<float>((size_t)grid);
-  float* meta = c.take<float>(8);
+  Carver pc(norm_partials);  // [grid][D] dg partials, then [grid][D] db2 partials: consumed by td_aligner_bwd_dh2
+  float* dg_part = pc.take<float>((size_t)grid * D);
+  float* db_part = pc.take<float>((size_t)grid * D);
 
   GemmParams p;
   int rc;
@@ -458,27 +467,25 @@ int32_t td_aligner_mse_fwd(const void* x, int64_t M, int32_t Din, int32_t D, con
   p.out0 = h2; p.bias = static_cast<const __nv_bfloat16*>(b2); p.red0 = ssq_part;
   rc = launch_gemm<2, false, false, EPI_BIAS_SSQ>({h1, D, false}, {W2, D, false}, p, 1, st, "gemm_fwd2_bias_ssq");
   if (rc) return rc;
-  rstd_from_partials_kernel<<<int((M + 255) / 256), 256, 0, st>>>(ssq_part, nparts, int(M), D, eps, rstd);
   const float dy_coef = 2.0f / (float(M) * float(D));
+  const long long* tri = reinterpret_cast<const long long*>(target_row_index);
   {
     ProfScope prof("norm_mse_bwd_fused", double(M) * D * (4.0 + (target_dtype == TD_DTYPE_BF16 ? 2.0 : 4.0)), st);
     if (target_dtype == TD_DTYPE_BF16)
-      norm_mse_bwd_kernel<true><<<grid, kNormBwdThreads, 0, st>>>(h2, rstd, g, target, int(M), D, rpc, dy_coef,
+      norm_mse_bwd_kernel<true><<<grid, kNormBwdThreads, 0, st>>>(h2, ssq_part, nparts, eps, g, target, tri, int(M), D, rpc, dy_coef,
                                                                   static_cast<__nv_bfloat16*>(dh2), dg_part, db_part, loss_part);
     else
-      norm_mse_bwd_kernel<false><<<grid, kNormBwdThreads, 0, st>>>(h2, rstd, g, target, int(M), D, rpc, dy_coef,
+      norm_mse_bwd_kernel<false><<<grid, kNormBwdThreads, 0, st>>>(h2, ssq_part, nparts, eps, g, target, tri, int(M), D, rpc, dy_coef,
                                                                    static_cast<__nv_bfloat16*>(dh2), dg_part, db_part, loss_part);
   }
   TD_CUDA(cudaGetLastError());
-  colsum_finish_kernel<<<dim3((D + 31) / 32, 2), 256, 0, st>>>(dg_part, dg_unit, db_part, db2_unit, grid, D, 1.0f);
-  count_valid_kernel<<<1, 32, 0, st>>>(nullptr, M, 0, meta);  // meta[0] = M
-  loss_finish_kernel<<<1, 256, 0, st>>>(loss_part, grid, meta, float(D), loss);
+  loss_finish_kernel<<<1, 256, 0, st>>>(loss_part, grid, nullptr, float(D), loss, float(M));
   TD_CUDA(cudaGetLastError());
   return TD_OK;
 }
 
 int32_t td_aligner_bwd_dh2(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
-                           const float* dg_unit, const float* db2_unit, int64_t M, int32_t Din, int32_t D,
+                           const void* norm_partials, int64_t M, int32_t Din, int32_t D,
                            float grad_scale, const float* grad_scale_ptr, float* dW1, float* db1, float* dW2, float* db2,
                            float* dg, void* ws, int64_t ws_bytes, int32_t phases, td_stream_t stream) {
   TD_DEVICE_OR_RETURN();
@@ -488,8 +495,14 @@ int32_t td_aligner_bwd_dh2(const void* dh2, const void* x, const void* h0, const
   cudaStream_t st = (cudaStream_t)stream;
   BwdWorkspace w = carve_bwd(ws, M, D);
   if (phases & TD_BWD_PHASE_NORM_W2) {
-    if (!dh2 || !h1 || !dg_unit || !db2_unit || !dW2 || !db2 || !dg) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (phase 1)");
-    scale_vec_kernel<<<(D + 255) / 256, 256, 0, st>>>(dg_unit, dg, db2_unit, db2, D, grad_scale, grad_scale_ptr);
+    if (!dh2 || !h1 || !norm_partials || !dW2 || !db2 || !dg) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (phase 1)");
+    int rpc;
+    const int grid = norm_bwd_grid(M, &rpc);
+    Carver pc(const_cast<void*>(norm_partials));
+    const float* dg_part = pc.take<float>((size_t)grid * D);
+    const float* db_part = pc.take<float>((size_t)grid * D);
+    // dg / db2 = (grad_scale * upstream) * column sums of the partials the fused forward pass left behind
+    colsum_finish_kernel<<<dim3((D + 31) / 32, 2), 256, 0, st>>>(dg_part, dg, db_part, db2, grid, D, grad_scale, grad_scale_ptr);
     TD_CUDA(cudaGetLastError());
   }
   if ((phases & TD_BWD_PHASE_GELU_W1) && (!x || !h0 || !W2 || !dW1 || !db1)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (phase 2)");

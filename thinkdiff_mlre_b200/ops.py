@@ -33,21 +33,23 @@ def cu_seqlens(lens: torch.Tensor) -> torch.Tensor:
     return cu
 
 
-def pack_varlen(flat: torch.Tensor, src_row_start: torch.Tensor, cu: torch.Tensor, total_rows: int) -> torch.Tensor:
-    """flat [R, C] (any dtype) -> packed [total_rows, C]: rows src_row_start[i] + [0, len_i) of each sample, back to back."""
+def pack_varlen(flat: torch.Tensor, src_row_start: torch.Tensor, cu: torch.Tensor, total_rows: int, want_index: bool = False):
+    """flat [R, C] (any dtype) -> packed [total_rows, C]: rows src_row_start[i] + [0, len_i) of each sample, back to back.
+    ``want_index``: also return int64 [total_rows] = the source row of every packed row."""
     _need_cuda(flat, src_row_start, cu)
     _contig(flat, "flat")
     if src_row_start.dtype != torch.int64 or cu.dtype != torch.int32:
         raise TypeError("src_row_start must be int64 and cu_seqlens int32")
     out = torch.empty((total_rows, flat.shape[1]), dtype=flat.dtype, device=flat.device)
+    index = torch.empty((total_rows,), dtype=torch.int64, device=flat.device) if want_index else None
     row_bytes = flat.shape[1] * flat.element_size()
     L.launch_count += 1
     L.check(
-        L.lib().td_pack_varlen(L.ptr(flat), L.ptr(src_row_start), L.ptr(cu), cu.numel() - 1, total_rows, row_bytes,
-                               L.ptr(out), L.stream_ptr()),
+        L.lib().td_pack_varlen_indexed(L.ptr(flat), L.ptr(src_row_start), L.ptr(cu), cu.numel() - 1, total_rows, row_bytes,
+                                       L.ptr(out), L.ptr(index), L.stream_ptr()),
         "td_pack_varlen",
     )
-    return out
+    return (out, index) if want_index else out
 
 
 def pack_padded(flat: torch.Tensor, src_row_start: torch.Tensor, cu: torch.Tensor, l_max: int, want_mask: bool = True):
@@ -140,31 +142,33 @@ class AlignerBackward:
         self._call(L.BWD_GELU_W1, dW1, db1, None, None, None)
 
 
-def aligner_mse_fwd(x, W1, b1, W2, b2, g, eps: float, target, between_stages=None):
-    """Fused training forward against T5 targets: returns (loss, saved) with saved = (h0, h1, dh2, dg_unit, db2_unit),
-    where dh2 / dg_unit / db2_unit are the T5LayerNorm backward of the MSE gradient for a unit upstream gradient.
-    ``between_stages``: optional callable run after Linear1+GELU is enqueued and before anything reads W2 / b2."""
-    _need_cuda(x, W1, W2, g, target)
+def aligner_mse_fwd(x, W1, b1, W2, b2, g, eps: float, target, between_stages=None, target_row_index=None):
+    """Fused training forward against T5 targets: returns (loss, saved) with saved = (h0, h1, dh2, norm_partials), where
+    dh2 / norm_partials are the T5LayerNorm backward of the MSE gradient for a unit upstream gradient (norm_partials = the
+    per-CTA partial column sums for dg / db2). ``between_stages``: optional callable run after Linear1+GELU is enqueued and
+    before anything reads W2 / b2. ``target_row_index`` (int64 [M]): row of ``target`` that belongs to each row of x."""
+    _need_cuda(x, W1, W2, g, target, target_row_index)
     M, Din = x.shape
     D = W1.shape[0]
-    if target.shape != (M, D):
-        raise ValueError(f"target must be [{M}, {D}], got {tuple(target.shape)}")
+    if target.dim() != 2 or target.shape[1] != D or (target_row_index is None and target.shape[0] != M):
+        raise ValueError(f"target must be [{M}, {D}] (or indexed by target_row_index), got {tuple(target.shape)}")
+    if target_row_index is not None and (target_row_index.dtype != torch.int64 or target_row_index.numel() != M):
+        raise TypeError("target_row_index must be int64 [M]")
     dev = x.device
     h0 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
     h1 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
     dh2 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
-    dg_unit = torch.empty((D,), dtype=torch.float32, device=dev)
-    db2_unit = torch.empty((D,), dtype=torch.float32, device=dev)
+    partials = torch.empty((L.lib().td_aligner_norm_partials_bytes(M, D),), dtype=torch.uint8, device=dev)
     loss = torch.empty((), dtype=torch.float32, device=dev)
     ws_bytes = L.lib().td_aligner_mse_fwd_workspace_bytes(M, Din, D)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-    L.launch_count += 7
+    L.launch_count += 4
 
     def call(stages):
         L.check(
             L.lib().td_aligner_mse_fwd(L.ptr(_contig(x, "x")), M, Din, D, L.ptr(W1), L.ptr(b1), L.ptr(W2), L.ptr(b2), L.ptr(g), eps,
-                                       L.ptr(_contig(target, "target")), L.dtype_code(target), L.ptr(h0), L.ptr(h1), L.ptr(dh2),
-                                       L.ptr(dg_unit), L.ptr(db2_unit), L.ptr(loss), L.ptr(ws), ws_bytes, stages, L.stream_ptr()),
+                                       L.ptr(_contig(target, "target")), L.dtype_code(target), L.ptr(target_row_index), L.ptr(h0),
+                                       L.ptr(h1), L.ptr(dh2), L.ptr(partials), L.ptr(loss), L.ptr(ws), ws_bytes, stages, L.stream_ptr()),
             "td_aligner_mse_fwd",
         )
 
@@ -174,14 +178,14 @@ def aligner_mse_fwd(x, W1, b1, W2, b2, g, eps: float, target, between_stages=Non
         call(1)
         between_stages()
         call(2)
-    return loss, (h0, h1, dh2, dg_unit, db2_unit)
+    return loss, (h0, h1, dh2, partials)
 
 
 class AlignerBackwardFromDh2:
     """Two-phase backward of the fused MSE path: everything is multiplied by grad_scale * upstream (a device scalar)."""
 
     def __init__(self, x, saved, W2, upstream, grad_scale: float = 1.0):
-        self.x, (self.h0, self.h1, self.dh2, self.dg_unit, self.db2_unit), self.W2 = x, saved, W2
+        self.x, (self.h0, self.h1, self.dh2, self.partials), self.W2 = x, saved, W2
         self.upstream = None if upstream is None else upstream.reshape(1).to(torch.float32).contiguous()
         self.M, self.Din = x.shape
         self.D = W2.shape[0]
@@ -193,7 +197,7 @@ class AlignerBackwardFromDh2:
         L.launch_count += 2 if phase == L.BWD_NORM_W2 else 3
         L.check(
             L.lib().td_aligner_bwd_dh2(L.ptr(self.dh2), L.ptr(self.x), L.ptr(self.h0), L.ptr(self.h1), L.ptr(self.W2),
-                                       L.ptr(self.dg_unit), L.ptr(self.db2_unit), self.M, self.Din, self.D, self.grad_scale,
+                                       L.ptr(self.partials), self.M, self.Din, self.D, self.grad_scale,
                                        L.ptr(self.upstream), L.ptr(dW1), L.ptr(db1), L.ptr(dW2), L.ptr(db2), L.ptr(dg),
                                        L.ptr(self.ws), self.ws_bytes, phase, L.stream_ptr()),
             "td_aligner_bwd_dh2",

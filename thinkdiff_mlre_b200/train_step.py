@@ -11,7 +11,7 @@ import torch
 
 from . import ops
 from .aligner import ThinkDiffAligner
-from .pack import FlatBatch, pack_device
+from .pack import FlatBatch, PackedBatch, pack_device
 
 
 def reference_param_groups(module: torch.nn.Module, weight_decay: float = 0.05):
@@ -81,12 +81,19 @@ class AlignerTrainStep:
 
     def step_device(self, flat, src_row_start, lens_dev, total_rows: int, l_max: int, flat_target) -> torch.Tensor:
         """Inputs already resident in HBM. Returns the (unscaled) loss as a device scalar; nothing syncs the host."""
-        packed = pack_device(flat, src_row_start, lens_dev, total_rows, l_max)
-        target = ops.pack_varlen(flat_target, src_row_start, packed.cu_seqlens, total_rows)
+        if self.fused_loss:
+            # the fused loss reads each token's target row straight from the flat source (row index from the feature pack)
+            cu = ops.cu_seqlens(lens_dev)
+            x, index = ops.pack_varlen(flat, src_row_start, cu, total_rows, want_index=True)
+            packed = PackedBatch(x, cu, None, l_max)
+            target = (flat_target, index)
+        else:
+            packed = pack_device(flat, src_row_start, lens_dev, total_rows, l_max)
+            target = ops.pack_varlen(flat_target, src_row_start, packed.cu_seqlens, total_rows)
         if self.pipelined:
             return self._step_pipelined(packed, target)
         if self.fused_loss:
-            loss = self.aligner.mse_loss_packed(packed.x, target)
+            loss = self.aligner.mse_loss_packed(packed.x, *target)
             (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
         else:
             with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -118,7 +125,7 @@ class AlignerTrainStep:
             a._between_fwd_stages = lambda: self._wait_update("linear2")  # W2 / b2 / g before GEMM2
             a._bf16_managed = True
         try:
-            loss = a.mse_loss_packed(packed.x, target)
+            loss = a.mse_loss_packed(packed.x, *target)
         finally:
             a._between_fwd_stages = None
         self._grads_hold = None  # the compute stream is now ordered after both updates of the previous step
@@ -155,7 +162,7 @@ class AlignerTrainStep:
             a._between_fwd_stages = lambda: opt.step_bucket("linear2", t=t_prev, release_grads=True)  # W2, b2, g before GEMM2
             a._bf16_managed = True
         try:
-            loss = a.mse_loss_packed(packed.x, target)
+            loss = a.mse_loss_packed(packed.x, *target)
         finally:
             a._between_fwd_stages = None
         (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
