@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after backward instead of overlapped")
-    ap.add_argument("--no-pipeline", action="store_true", help="N > 1: apply every parameter update inside its own step")
+    ap.add_argument("--no-pipeline", action="store_true", help="apply every parameter update inside its own step, on the compute stream")
     ap.add_argument("--no-shard", action="store_true", help="N > 1: all-reduce + replicated AdamW instead of reduce-scatter + row-sharded AdamW + all-gather")
     ap.add_argument("--profile-out", default="", help="write the per-kernel table (JSON) here")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
@@ -221,7 +221,7 @@ def main():
         sharded = args.optimizer == "fused" and args.loss_path == "fused" and not args.no_pipeline and not args.no_shard and D % world == 0
         aligner.enable_data_parallel(overlap=not args.no_overlap, defer_wait=args.optimizer == "fused", sharded=sharded)
     opt = td.FusedAdamW(aligner, lr=1e-4, weight_decay=0.05) if args.optimizer == "fused" else make_reference_optimizer(aligner)
-    pipelined = world > 1 and args.optimizer == "fused" and args.loss_path == "fused" and not args.no_pipeline
+    pipelined = args.optimizer == "fused" and args.loss_path == "fused" and not args.no_pipeline
     stepper = td.AlignerTrainStep(aligner, opt, fused_loss=args.loss_path == "fused", pipelined=pipelined)
 
     host = [td.synthetic_lvlm_batch(SEQS_PER_GPU, MAX_LEN, DIN, D, seed=1234 + rank + 1000 * j) for j in range(NUM_BATCHES)]

@@ -182,9 +182,15 @@ def _reduce_and_return(module, gb, run_phase1, run_phase2):
         return
     works = {}
     order[0][2]()
+    if module._record_phase_events:  # lets a side stream start on this bucket while the other phase still runs
+        module._phase_done[order[0][0]] = torch.cuda.Event()
+        module._phase_done[order[0][0]].record()
     if dp is not None and dp.world > 1 and dp.overlap:
         works[order[0][0]] = dp.all_reduce_async(order[0][1])  # rides NVLink while the remaining GEMMs run
     order[1][2]()
+    if module._record_phase_events:
+        module._phase_done[order[1][0]] = torch.cuda.Event()
+        module._phase_done[order[1][0]].record()
     if dp is not None and dp.world > 1:
         if not dp.overlap:
             works[order[0][0]] = dp.all_reduce_async(order[0][1])
@@ -241,6 +247,8 @@ class ThinkDiffAligner(nn.Sequential):
         self._pending = {}      # bucket name -> in-flight all-reduce (defer_wait mode)
         self._grad_flats = None  # the flat gradient buckets of the last backward ({"linear2": ..., "linear1": ...})
         self._bwd_order = "linear2_first"   # or "linear1_first" (pipelined train step)
+        self._record_phase_events = False   # pipelined train step: CUDA event after each backward phase
+        self._phase_done = {}
         self._between_fwd_stages = None     # callable run between Linear1 and Linear2 of the fused-loss forward
         self._bf16_managed = False          # True: an optimizer keeps the bf16 copies current; training never re-casts
         self._dp: DataParallelState | None = None

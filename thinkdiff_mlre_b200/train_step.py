@@ -78,6 +78,7 @@ class AlignerTrainStep:
             # all-gather of the bf16 rows, all on a side stream that runs beside the remaining GEMMs
             self._sharded = dp is not None and dp.sharded and dp.world > 1
             self._ag, self._upd_done = {}, {}
+            aligner._record_phase_events = not self._sharded
 
     def step_device(self, flat, src_row_start, lens_dev, total_rows: int, l_max: int, flat_target) -> torch.Tensor:
         """Inputs already resident in HBM. Returns the (unscaled) loss as a device scalar; nothing syncs the host."""
@@ -156,17 +157,31 @@ class AlignerTrainStep:
             return self._step_pipelined_sharded(packed, target)
         a, opt = self.aligner, self.optimizer
         opt.grad_scale = 1.0 / self.loss_scale
-        t_prev = self._pending_t
-        if t_prev is not None:
-            opt.step_bucket("linear1", t=t_prev, release_grads=True)  # W1, b1 (+ bf16 copies) before GEMM1 reads them
-            a._between_fwd_stages = lambda: opt.step_bucket("linear2", t=t_prev, release_grads=True)  # W2, b2, g before GEMM2
+        if self._pending_t is not None:
+            self._wait_update("linear1")                                  # W1 / b1 (+ bf16 copies) before GEMM1 reads them
+            a._between_fwd_stages = lambda: self._wait_update("linear2")  # W2 / b2 / g before GEMM2
             a._bf16_managed = True
         try:
             loss = a.mse_loss_packed(packed.x, *target)
         finally:
             a._between_fwd_stages = None
+        self._grads_hold = None  # the compute stream is now ordered after both updates of the previous step
         (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
-        self._pending_t = opt.next_step_number()
+        t = opt.next_step_number()
+        self._pending_t = t
+        # AdamW of each bucket on the update stream, as soon as that bucket's gradients exist (and, under data parallel,
+        # are all-reduced): the HBM-bound updates run beside the tensor-bound GEMMs instead of after them
+        if not hasattr(self, "_update_stream"):
+            self._update_stream = torch.cuda.Stream()
+        grads = list(a._grad_flats.values())
+        with torch.cuda.stream(self._update_stream):
+            for name in ("linear1", "linear2"):
+                self._update_stream.wait_event(a._phase_done[name])
+                opt.step_bucket(name, t=t, release_grads=True)
+                ev = torch.cuda.Event()
+                ev.record(self._update_stream)
+                self._upd_done[name] = ev
+        self._grads_hold = grads  # freed only after the compute stream has waited for the updates (next step / flush)
         return loss
 
     def flush(self):
@@ -178,8 +193,9 @@ class AlignerTrainStep:
                 self._grads_hold = None
                 self.aligner.sync_parameters()  # fp32 master rows of the other ranks
             else:
-                self.optimizer.step_bucket("linear1", t=self._pending_t, release_grads=True)
-                self.optimizer.step_bucket("linear2", t=self._pending_t, release_grads=True)
+                self._wait_update("linear1")
+                self._wait_update("linear2")
+                self._grads_hold = None
             self.optimizer.mark_bf16_current()
             self._pending_t = None
             self.aligner._bf16_managed = False
