@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Loader measurement for the flat shard format, CPU only: time to produce one training batch
+(64 samples, Qwen2-VL width 3584, config-2 length distribution) ready for H2D, from the page cache:
+  * flat shard: EmbedShardReader.batch()  (one slab copy, no unpickling, no padding)
+  * reference-style: per-sample torch.load of pickled tensors (what wds.decode does for the .pth entries written at
+    thinkdiff/tasks/image_text_process_data.py:111-116) + the collater's pad/stack/mask (oracle restatement of
+    llava_instruct_dataset_mllama_embed_2.py:101-131)
+    python scripts/bench_loader.py [--out profiles/r01_loader_bench.json]"""
+import argparse
+import io
+import json
+import os
+import random
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import thinkdiff_mlre_b200 as td  # noqa: E402
+from oracle import pack_ref  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="")
+    ap.add_argument("--batches", type=int, default=8)
+    args = ap.parse_args()
+    B, C = 64, 3584
+    n = B * args.batches
+    g = torch.Generator().manual_seed(0)
+    lens = torch.randint(2, 258, (n,), generator=g).tolist()
+    bi = dict(use_input_embed=0, use_output_embed=1, random_split_output_embed=1, output_embed_max_split_len=128,
+              output_embed_max_len=256, input_embed_max_len=256)
+    tmp = tempfile.mkdtemp()
+    path = os.path.join(tmp, "bench.tdemb")
+    pickles = []
+    with td.EmbedShardWriter(path, C) as w:
+        for L in lens:
+            e = torch.randn((L, C), generator=g).to(torch.bfloat16)
+            ids = list(range(L))
+            w.add(e, ids, "text")
+            buf = io.BytesIO()
+            torch.save(e.clone(), buf)
+            pickles.append((buf.getvalue(), ids))
+    r = td.EmbedShardReader(path)
+    r.batch(0, B, bi, pin_memory=False)  # touch the pages
+    random.seed(0)
+    t0 = time.perf_counter()
+    rows = 0
+    for fb in r.batches(B, bi, pin_memory=False):
+        rows += fb.flat.shape[0]
+    t_flat = (time.perf_counter() - t0) / args.batches
+    random.seed(0)
+    t0 = time.perf_counter()
+    for b in range(args.batches):
+        embeds, ids = [], []
+        for blob, i in pickles[b * B : (b + 1) * B]:
+            embeds.append(torch.load(io.BytesIO(blob)).view(torch.int16).numpy().view(np.uint16))
+            ids.append(i)
+        split = pack_ref.draw_split_points([e.shape[0] for e in embeds], 128, rng=random)
+        pack_ref.collate_padded(embeds, "random_split", split_points=split, token_ids=ids)
+    t_ref = (time.perf_counter() - t0) / args.batches
+    mb = rows / args.batches * C * 2 / 1e6
+    res = {"batch": B, "width": C, "mean_source_MB_per_batch": mb, "flat_shard_ms_per_batch": t_flat * 1e3,
+           "flat_shard_GBps": mb / 1e3 / t_flat, "reference_style_ms_per_batch": t_ref * 1e3, "speedup": t_ref / t_flat,
+           "cores_used": 1}
+    print(json.dumps(res))
+    if args.out:
+        json.dump(res, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

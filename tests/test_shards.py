@@ -1,0 +1,65 @@
+"""Flat embedding shards: write -> mmap read is bit-exact, and a batch drawn from a shard + the
+reference's kept-length rule reproduces the reference collater's golden output. CPU only."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import thinkdiff_mlre_b200 as td
+from oracle import pack_ref
+from oracle.golden import load_golden
+
+
+def _golden_samples(g):
+    full = [int(v) for v in g["full_lens"]]
+    off = np.concatenate([[0], np.cumsum(full)])
+    out = []
+    for i in range(len(full)):
+        e = torch.from_numpy(g["src_bits"][off[i] : off[i + 1]].view(np.int16).copy()).view(torch.bfloat16)
+        ids = [int(v) for v in g["src_ids_flat"][off[i] : off[i + 1]]]
+        out.append({"__key__": f"k{i}", "json": {"generated_text": f"sample {i}", "output_token_ids": ids},
+                    "model.norm.input_embed.pth": e, "model.norm.output_embed.pth": e})
+    return out
+
+
+@pytest.mark.parametrize("name", ["collater_random_split.npz", "collater_fixed_max.npz"])
+def test_shard_roundtrip_and_batch_equals_reference_collater(tmp_path, name):
+    g = load_golden(name)
+    samples = _golden_samples(g)
+    path = str(tmp_path / "s.tdemb")
+    with td.EmbedShardWriter(path, width=int(g["C"])) as w:
+        for s in samples:
+            w.add_reference_sample(s)
+    r = td.EmbedShardReader(path)
+    assert len(r) == len(samples) and r.width == int(g["C"]) and r.total_rows == int(sum(g["full_lens"]))
+    for i, s in enumerate(samples):
+        assert torch.equal(r.embedding(i).view(torch.int16), s["model.norm.output_embed.pth"].view(torch.int16))
+        assert r.token_ids(i).tolist() == s["json"]["output_token_ids"]
+    bi = {k[3:]: int(v) for k, v in g.items() if k.startswith("bi_")}
+    random.seed(int(g["seed"]))
+    fb = r.batch(0, len(samples), bi, pin_memory=False)
+    bits = fb.flat.view(torch.int16).numpy().view(np.uint16)
+    packed, cu = pack_ref.pack_from_flat(bits, fb.src_row_start.tolist(), fb.lens.tolist())
+    padded, mask = pack_ref.unpack_padded(packed, cu, fb.l_max)
+    np.testing.assert_array_equal(padded, g["out_embed_bits"])
+    np.testing.assert_array_equal(mask, g["out_mask"])
+    ids = [list(g["ids_flat"][g["ids_off"][i] : g["ids_off"][i + 1]]) for i in range(len(samples))]
+    assert fb.extras["output_token_ids"] == [list(map(int, t)) for t in ids]
+    assert fb.extras["generated_texts"] == [f"sample {i}" for i in range(len(samples))]
+    # sub-range batches index rows relative to their own slab
+    random.seed(0)
+    fb2 = r.batch(2, 5, dict(bi, random_split_output_embed=0, output_embed_max_len=1000), pin_memory=False)
+    assert fb2.src_row_start.tolist() == [0, int(g["full_lens"][2]), int(g["full_lens"][2] + g["full_lens"][3])]
+    assert fb2.flat.shape[0] == int(sum(g["full_lens"][2:5]))
+    r.close()
+
+
+def test_shard_rejects_garbage(tmp_path):
+    p = tmp_path / "bad.tdemb"
+    p.write_bytes(b"\0" * 128)
+    with pytest.raises(ValueError, match="TDEMB1"):
+        td.EmbedShardReader(str(p))
+    w = td.EmbedShardWriter(str(tmp_path / "x.tdemb"), width=8)
+    with pytest.raises(ValueError):
+        w.add(torch.zeros(3, 8), [1, 2, 3])  # float32, not bf16

@@ -386,16 +386,6 @@ adamw_kernel(const AdamParams a) {
 }
 
 // ------------------------------------------------------------------------------------------ fused norm + MSE + norm-backward
-// rstd[row] = rsqrt(mean(h2^2) + eps) from the GEMM2 epilogue's per-half-tile partial sums ssq_part[P][M].
-__global__ void __launch_bounds__(256)
-rstd_from_partials_kernel(const float* __restrict__ ssq_part, int P, int M, int D, float eps, float* __restrict__ rstd) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= M) return;
-  float ssq = 0.f;
-  for (int p = 0; p < P; ++p) ssq += ssq_part[(long long)p * M + row];
-  rstd[row] = rsqrtf(ssq / float(D) + eps);
-}
-
 // Training against T5 targets never needs y or dy in memory: with y = g * h2 * rstd,
 //   diff = y - t;  loss += diff^2;  dy = (2 / (M D)) diff;  then the T5LayerNorm backward of dy, all per row in registers.
 // Same CTA organisation as rmsnorm_bwd_kernel (thread = 8 columns, R rows per block reduction). dh2 / dg / db2 are written
@@ -532,16 +522,6 @@ norm_mse_bwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restric
     for (int i = 0; i < kNormBwdThreads / 32; ++i) tot_loss += lred[i];
     loss_part[blockIdx.x] = tot_loss;
   }
-}
-
-// out[i] = scale * (*scale_ptr) * in[i]   (applies the upstream loss gradient, resident on the device, to dg / db2)
-__global__ void scale_vec_kernel(const float* __restrict__ in0, float* __restrict__ out0, const float* __restrict__ in1,
-                                 float* __restrict__ out1, int n, float scale, const float* __restrict__ scale_ptr) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float a = scale * (scale_ptr ? __ldg(scale_ptr) : 1.f);
-  out0[i] = a * in0[i];
-  if (in1 != nullptr) out1[i] = a * in1[i];
 }
 
 // out[n] = scale * sum_p part[p][n]   (fixed order -> deterministic). One CTA per 32 columns; warp w adds rows

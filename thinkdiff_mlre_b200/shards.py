@@ -1,0 +1,170 @@
+"""Flat embedding shards: the on-disk format + loader that feed ``td_pack_varlen``.
+
+Reference being replaced: the pre-compute task writes every sample's hidden states as a pickled ``torch.save`` tensor
+inside WebDataset tar shards (thinkdiff/tasks/image_text_process_data.py:94-118, 500 MB shards) and the training set
+reads them back through ``wds.tarfile_to_samples`` + ``wds.decode`` in Python workers
+(thinkdiff/datasets/datasets/llava_instruct_dataset_mllama_embed_2.py:15-22), then pads/stacks on the CPU.
+
+Here a shard is ONE flat, mmap-able file: a fixed header, the per-sample lengths, the token ids, a small JSON blob for the
+texts, and all embedding rows back to back (bf16, 4096-byte aligned). A batch of consecutive samples is a single contiguous
+slab of rows: ``EmbedShardReader.batch()`` copies it once into pinned memory and returns the ``FlatBatch`` that
+``pack_batch`` / ``AlignerTrainStep.prefetch`` send to the GPU -- no unpickling, no per-sample tensors, no padding.
+
+    header (64 bytes, little endian): magic "TDEMB1\\0\\0" | u32 version | u32 dtype (1 = bf16) | u32 width | u32 n_samples |
+                                      u64 total_rows | u64 off_lens | u64 off_ids_index | u64 off_ids | u64 off_meta | u64 off_rows
+    lens       int32 [n_samples]      full length L_i of every sample (rows)
+    ids_index  int64 [n_samples + 1]  prefix offsets into ids
+    ids        int32 [...]            output_token_ids of every sample, back to back
+    meta       u64 length + UTF-8 JSON {"generated_text": [...], "keys": [...]}
+    rows       bf16  [total_rows, width]
+"""
+from __future__ import annotations
+
+import json
+import mmap
+import os
+import struct
+
+import numpy as np
+import torch
+
+from .pack import FlatBatch, kept_lengths
+
+MAGIC = b"TDEMB1\0\0"
+_HEADER = struct.Struct("<8sIIIIQQQQQQ")
+_ALIGN = 4096
+
+
+def _align(n: int) -> int:
+    return (n + _ALIGN - 1) // _ALIGN * _ALIGN
+
+
+class EmbedShardWriter:
+    """``add()`` samples, ``close()`` writes the shard. Embeddings are kept as raw 16-bit words (bit-exact)."""
+
+    def __init__(self, path: str, width: int):
+        self.path, self.width = path, int(width)
+        self._rows, self._lens, self._ids, self._texts, self._keys = [], [], [], [], []
+
+    def add(self, embed: torch.Tensor, token_ids, generated_text: str = "", key: str = ""):
+        if embed.dtype != torch.bfloat16 or embed.dim() != 2 or embed.shape[1] != self.width:
+            raise ValueError(f"expected a bfloat16 [L, {self.width}] embedding, got {embed.dtype} {tuple(embed.shape)}")
+        self._rows.append(embed.contiguous().view(torch.int16).numpy().view(np.uint16))
+        self._lens.append(int(embed.shape[0]))
+        self._ids.append(np.asarray(token_ids, dtype=np.int32))
+        self._texts.append(generated_text)
+        self._keys.append(key)
+
+    def add_reference_sample(self, sample: dict, which: str = "output"):
+        """A sample dict as the reference's webdataset pipeline yields it (keys ``json``, ``*.{which}_embed.pth``)."""
+        k = [k for k in sample if f"{which}_embed" in k][0]
+        js = sample["json"]
+        self.add(sample[k], js["output_token_ids"], js.get("generated_text", ""), sample.get("__key__", ""))
+
+    def close(self):
+        n = len(self._lens)
+        lens = np.asarray(self._lens, dtype=np.int32)
+        ids_index = np.zeros(n + 1, dtype=np.int64)
+        ids_index[1:] = np.cumsum([len(i) for i in self._ids])
+        ids = np.concatenate(self._ids) if n else np.zeros(0, np.int32)
+        meta = json.dumps({"generated_text": self._texts, "keys": self._keys}).encode("utf-8")
+        off_lens = _HEADER.size
+        off_idx = off_lens + lens.nbytes
+        off_ids = off_idx + ids_index.nbytes
+        off_meta = off_ids + ids.nbytes
+        off_rows = _align(off_meta + 8 + len(meta))
+        total_rows = int(lens.sum())
+        with open(self.path, "wb") as f:
+            f.write(_HEADER.pack(MAGIC, 1, 1, self.width, n, total_rows, off_lens, off_idx, off_ids, off_meta, off_rows))
+            f.write(lens.tobytes()), f.write(ids_index.tobytes()), f.write(ids.tobytes())
+            f.write(struct.pack("<Q", len(meta))), f.write(meta)
+            f.write(b"\0" * (off_rows - f.tell()))
+            for r in self._rows:
+                f.write(r.tobytes())
+        return self.path
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        if exc[0] is None:
+            self.close()
+
+
+class EmbedShardReader:
+    """mmap view of a shard. ``batch(lo, hi, build_info)`` -> FlatBatch for samples [lo, hi) with the reference's kept-length
+    rule (random split / fixed max; seed Python's ``random`` to replay the reference's split points)."""
+
+    def __init__(self, path: str):
+        self._f = open(path, "rb")
+        self._mm = mmap.mmap(self._f.fileno(), 0, access=mmap.ACCESS_READ)
+        for advice in (getattr(mmap, "MADV_POPULATE_READ", 22), getattr(mmap, "MADV_WILLNEED", 3)):
+            try:  # pre-fault the page tables: a batch copy is then a plain memcpy instead of ~14 k minor faults
+                self._mm.madvise(advice)
+                break
+            except (OSError, ValueError):
+                continue
+        magic, ver, dtype, width, n, total, off_lens, off_idx, off_ids, off_meta, off_rows = _HEADER.unpack_from(self._mm, 0)
+        if magic != MAGIC or ver != 1 or dtype != 1:
+            raise ValueError(f"{path}: not a TDEMB1 bf16 shard")
+        self.width, self.n_samples, self.total_rows = width, n, total
+        self.lens = np.frombuffer(self._mm, dtype=np.int32, count=n, offset=off_lens)
+        self.ids_index = np.frombuffer(self._mm, dtype=np.int64, count=n + 1, offset=off_idx)
+        self.ids = np.frombuffer(self._mm, dtype=np.int32, count=int(self.ids_index[-1]) if n else 0, offset=off_ids)
+        (mlen,) = struct.unpack_from("<Q", self._mm, off_meta)
+        self._meta = json.loads(bytes(self._mm[off_meta + 8 : off_meta + 8 + mlen]).decode("utf-8"))
+        self.rows = np.frombuffer(self._mm, dtype=np.uint16, count=total * width, offset=off_rows).reshape(total, width)
+        self.row_start = np.zeros(n + 1, dtype=np.int64)
+        self.row_start[1:] = np.cumsum(self.lens)
+        self._pinned = None
+
+    def __len__(self):
+        return self.n_samples
+
+    def token_ids(self, i: int):
+        return self.ids[self.ids_index[i] : self.ids_index[i + 1]]
+
+    def embedding(self, i: int) -> torch.Tensor:
+        a = np.array(self.rows[self.row_start[i] : self.row_start[i + 1]])
+        return torch.from_numpy(a.view(np.int16)).view(torch.bfloat16)
+
+    def batch(self, lo: int, hi: int, build_info: dict, pin_memory: bool = True) -> FlatBatch:
+        r0, r1 = int(self.row_start[lo]), int(self.row_start[hi])
+        full_lens = self.lens[lo:hi].tolist()
+        lens, l_max = kept_lengths(full_lens, build_info, "output")
+        if pin_memory and torch.cuda.is_available():
+            # ring of 3 pinned staging buffers: a batch's buffer is reused only two batches later, after its async H2D
+            if self._pinned is None:
+                self._pinned, self._ring = [None, None, None], 0
+            self._ring = (self._ring + 1) % 3
+            buf = self._pinned[self._ring]
+            if buf is None or buf.shape[0] < r1 - r0:
+                buf = self._pinned[self._ring] = torch.empty((max(r1 - r0, 1), self.width), dtype=torch.bfloat16).pin_memory()
+            flat = buf[: r1 - r0]
+            flat.view(torch.int16).numpy().view(np.uint16)[:] = self.rows[r0:r1]  # one slab copy, page cache -> pinned
+        else:
+            flat = torch.from_numpy(np.array(self.rows[r0:r1]).view(np.int16)).view(torch.bfloat16)
+        start = torch.from_numpy((self.row_start[lo:hi] - r0).astype(np.int64))
+        if build_info.get("random_split_output_embed"):
+            out_ids = [self.token_ids(i)[n:].tolist() for i, n in zip(range(lo, hi), lens)]
+        else:
+            out_ids = [self.token_ids(i)[:l_max].tolist() if L > l_max else self.token_ids(i).tolist()
+                       for i, L in zip(range(lo, hi), full_lens)]
+        extras = {"generated_texts": self._meta["generated_text"][lo:hi], "output_token_ids": out_ids,
+                  "embed_key": "model.norm.output_embed"}
+        return FlatBatch(flat, start, torch.tensor(lens, dtype=torch.int32), l_max, extras)
+
+    def batches(self, batch_size: int, build_info: dict, drop_last: bool = True, pin_memory: bool = True):
+        for lo in range(0, self.n_samples, batch_size):
+            hi = min(lo + batch_size, self.n_samples)
+            if hi - lo < batch_size and drop_last:
+                return
+            yield self.batch(lo, hi, build_info, pin_memory)
+
+    def close(self):
+        self.rows = self.lens = self.ids_index = self.ids = None
+        try:
+            self._mm.close()
+        except BufferError:  # numpy views still alive somewhere; the OS reclaims the mapping at exit
+            pass
+        self._f.close()
