@@ -292,6 +292,23 @@ def main():
         e2e = {"value": tokens / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / steps, "note": "every step: H2D of its flat bf16 features + T5 targets from pinned memory (on a copy stream, overlapping the previous step's compute) and loss.item()"}
 
+    if os.environ.get("TD_HOST_PROFILE") and rank == 0:  # developer aid: where does the host time of a step go?
+        import cProfile, io, pstats
+
+        pr = cProfile.Profile()
+        pr.enable()
+        for i in range(100):
+            stepper.step_device(*resident[i % NUM_BATCHES])
+        pr.disable()
+        stepper.flush()
+        buf = io.StringIO()
+        pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(22)
+        print(buf.getvalue()[:5000], file=sys.stderr)
+    elif os.environ.get("TD_HOST_PROFILE"):
+        for i in range(100):
+            stepper.step_device(*resident[i % NUM_BATCHES])
+        stepper.flush()
+
     # ---- per-kernel device times (separate pass of the same steps; CUDA events around every launch) --
     psteps = min(steps, 20)
     L.profile_enable(True)

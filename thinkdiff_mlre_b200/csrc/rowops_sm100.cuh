@@ -245,10 +245,10 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restrict
 //   dg_part[cta][col] += dy * h2 * rstd;  db2_part[cta][col] += dh2
 // Column sums stay in registers and are written once per CTA (deterministic two-level reduction).
 constexpr int kNormBwdThreads = 512;
-constexpr int kNormBwdRows = 4;
+constexpr int kNormBwdRows = 2;
 
 template <bool DY_BF16>
-__global__ void __launch_bounds__(kNormBwdThreads)
+__global__ void __launch_bounds__(kNormBwdThreads, 2)
 rmsnorm_bwd_kernel(const void* __restrict__ dy_in, const __nv_bfloat16* __restrict__ h2,
                    const float* __restrict__ rstd_in, const float* __restrict__ g, int M, int D, int rows_per_cta,
                    __nv_bfloat16* __restrict__ dh2, float* __restrict__ dg_part, float* __restrict__ db2_part) {
@@ -393,7 +393,7 @@ adamw_kernel(const AdamParams a) {
 // HBM traffic per token: h2 8 KB + target 8 KB (bf16) read, dh2 8 KB written -- instead of the 96 KB of the three
 // separate passes (norm fwd 24 KB, MSE 40 KB, norm bwd 32 KB).
 template <bool T_BF16>
-__global__ void __launch_bounds__(kNormBwdThreads)
+__global__ void __launch_bounds__(kNormBwdThreads, 2)
 norm_mse_bwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restrict__ ssq_part, int P, float eps,
                     const float* __restrict__ g, const void* __restrict__ t_in,
                     const long long* __restrict__ t_row_index, int M, int D, int rows_per_cta, float dy_coef,
