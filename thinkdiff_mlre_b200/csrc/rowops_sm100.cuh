@@ -171,6 +171,8 @@ cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict
 // (either summed here, or from the per-N-tile partials the GEMM2 epilogue wrote: ssq_part[P][M]).
 //   OUT_BF16 = false: y = g * (h2 * rstd) in fp32            (training: fp32 norm weight)
 //   OUT_BF16 = true : y = bf16(g) * bf16(h2 * rstd) -> bf16  (pure-bf16 inference, rounding before the multiply)
+constexpr int kNormFwdMaxVec = 16;  // 16 x 32 lanes x 8 bf16 = 4096 columns held in registers per warp
+
 template <bool OUT_BF16>
 __global__ void __launch_bounds__(256)
 rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restrict__ ssq_part, int P,
@@ -179,37 +181,38 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restrict
   const int lane = threadIdx.x & 31;
   const int warp0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * (blockDim.x >> 5);
-  const int nvec = D >> 3;  // uint4 of 8 bf16
+  const int nvec = D >> 3;  // uint4 of 8 bf16; nvec <= 32 * kNormFwdMaxVec is enforced on the host
   for (int row = warp0; row < M; row += nwarps) {
     const uint4* hp = reinterpret_cast<const uint4*>(h2 + (long long)row * D);
+    // the whole row goes into registers with all loads in flight at once: read from HBM exactly once
+    uint4 hu[kNormFwdMaxVec];
+#pragma unroll
+    for (int k = 0; k < kNormFwdMaxVec; ++k)
+      if (lane + 32 * k < nvec) hu[k] = ld_stream(hp + lane + 32 * k);
     float ssq = 0.f;
     if (P > 0) {
       for (int p = lane; p < P; p += 32) ssq += ssq_part[(long long)p * M + row];
     } else {
-      for (int v = lane; v < nvec; v += 32) {
-        const uint4 u = __ldg(hp + v);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float a = bf16lo(w[q]), b = bf16hi(w[q]);
-          ssq = fmaf(a, a, ssq);
-          ssq = fmaf(b, b, ssq);
+      for (int k = 0; k < kNormFwdMaxVec; ++k) {
+        if (lane + 32 * k < nvec) {
+          const uint32_t w[4] = {hu[k].x, hu[k].y, hu[k].z, hu[k].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float a = bf16lo(w[q]), b = bf16hi(w[q]);
+            ssq = fmaf(a, a, ssq);
+            ssq = fmaf(b, b, ssq);
+          }
         }
       }
     }
     ssq = warp_sum(ssq);
     const float rstd = rsqrtf(ssq / float(D) + eps);
     if (lane == 0 && rstd_out != nullptr) rstd_out[row] = rstd;
-    constexpr int U = 4;  // 4 independent 16-byte loads in flight per lane
-    for (int v0 = lane; v0 < nvec; v0 += 32 * U) {
-      uint4 hu[U];
 #pragma unroll
-      for (int k = 0; k < U; ++k)
-        if (v0 + 32 * k < nvec) hu[k] = ld_stream(hp + v0 + 32 * k);
-#pragma unroll
-      for (int k = 0; k < U; ++k) {
-        const int v = v0 + 32 * k;
-        if (v >= nvec) break;
+    for (int k = 0; k < kNormFwdMaxVec; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nvec) {
         const uint32_t w[4] = {hu[k].x, hu[k].y, hu[k].z, hu[k].w};
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + 2 * v);
         const float4 g1 = __ldg(reinterpret_cast<const float4*>(g) + 2 * v + 1);

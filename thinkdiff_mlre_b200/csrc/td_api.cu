@@ -179,7 +179,8 @@ int32_t td_cast_f32_to_bf16(const float* src, void* dst, int64_t n, td_stream_t 
 int32_t td_rmsnorm_fwd(const void* x, const float* g, float eps, int64_t M, int32_t D, void* y, int32_t y_dtype,
                        float* rstd, td_stream_t stream) {
   TD_DEVICE_OR_RETURN();
-  if (M < 0 || D <= 0 || D % 8) TD_FAIL(TD_ERR_ARG, "td_rmsnorm_fwd: D=%d must be a positive multiple of 8", D);
+  if (M < 0 || D <= 0 || D % 8 || D > 8 * 32 * kNormFwdMaxVec)
+    TD_FAIL(TD_ERR_ARG, "td_rmsnorm_fwd: D=%d must be a positive multiple of 8, at most %d", D, 8 * 32 * kNormFwdMaxVec);
   if (M == 0) return TD_OK;
   const int grid = grid_for_rows(M, 8, 8);
   if (y_dtype == TD_DTYPE_BF16)
