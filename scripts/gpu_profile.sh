@@ -3,7 +3,7 @@
 # of one step (with source). Run under gpurun; results land in gpurun_out/.
 set -u
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-pipeline"  # sequential step: same kernels, one stream, fixed launch order
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
