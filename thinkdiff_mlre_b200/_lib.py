@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("THINKDIFF_B200_LIB", os.path.join(_HERE, "libthinkdiff_b200.so"))  # override: A/B builds
 
 F32, BF16 = 0, 1
-BWD_NORM_W2, BWD_GELU_W1, BWD_ALL = 1, 2, 3
+BWD_NORM_W2, BWD_GELU_W1, BWD_ALL, BWD_SMALL2_ONLY, BWD_W2_ONLY = 1, 2, 3, 4, 8
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 

@@ -158,7 +158,7 @@ class _AlignerFn(torch.autograd.Function):
         return (None, *gb.in_parameter_order(), None, None)
 
 
-def _reduce_and_return(module, gb, run_phase1, run_phase2):
+def _reduce_and_return(module, gb, run_phase1, run_phase2, split2=None):
     """Shared backward schedule: phase 1 (Linear2 / norm gradients) -> start its all-reduce -> phase 2 (Linear1
     gradients, overlapping the first all-reduce) -> all-reduce the second bucket -> stream-level waits (or, with
     ``defer_wait``, leave the waits to the consumer of each bucket)."""
@@ -174,10 +174,20 @@ def _reduce_and_return(module, gb, run_phase1, run_phase2):
         big = {"linear2": gb.linear2.view(gb.dW2.shape), "linear1": gb.linear1.view(gb.dW1.shape)}
         module.wait_grads()
         works = {}
-        for name, _, launch in order:  # each matrix's reduce-scatter starts as soon as its GEMM is enqueued
-            launch()
-            works[name + ".big"] = dp.reduce_scatter_rows_async(big[name])
-        works["small"] = dp.all_reduce_async(gb.small[:])  # [db2 | dg | db1], 48 KB
+        if split2 is not None and order[0][0] == "linear1":
+            # Linear1 first, then the small vectors, then dW2: the 48 KB all-reduce of [db2 | dg | db1] is queued BEFORE the
+            # dW2 GEMM exists, so the next step's first GEMM (which needs b1) never waits for the last reduce-scatter
+            order[0][2]()
+            works["linear1.big"] = dp.reduce_scatter_rows_async(big["linear1"])
+            split2[0]()
+            works["small"] = dp.all_reduce_async(gb.small[:])
+            split2[1]()
+            works["linear2.big"] = dp.reduce_scatter_rows_async(big["linear2"])
+        else:
+            for name, _, launch in order:  # each matrix's reduce-scatter starts as soon as its GEMM is enqueued
+                launch()
+                works[name + ".big"] = dp.reduce_scatter_rows_async(big[name])
+            works["small"] = dp.all_reduce_async(gb.small[:])  # [db2 | dg | db1], 48 KB
         module._pending = works
         return
     works = {}
@@ -225,7 +235,8 @@ class _AlignerMSEFn(torch.autograd.Function):
         bwd = ops.AlignerBackwardFromDh2(x2d, (h0, h1, dh2, partials), W2b, grad_loss, grad_scale=scale)
         gb = GradBuckets(x2d.shape[1], W2b.shape[0], x2d.device, small_separate=dp is not None and dp.sharded and dp.world > 1)
         module._grad_flats = gb.flats()
-        _reduce_and_return(module, gb, lambda: bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg), lambda: bwd.gelu_and_linear1(gb.dW1, gb.db1))
+        _reduce_and_return(module, gb, lambda: bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg), lambda: bwd.gelu_and_linear1(gb.dW1, gb.db1),
+                           split2=(lambda: bwd.norm_small(gb.db2, gb.dg), lambda: bwd.linear2_only(gb.dW2)))
         return (None, None, *gb.in_parameter_order(), None, None)
 
 

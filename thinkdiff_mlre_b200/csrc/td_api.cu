@@ -358,7 +358,7 @@ int bwd_from_dh2(const __nv_bfloat16* dh2, const void* x, const void* h0, const 
                  int32_t Din, int32_t D, float scale, const float* scale_ptr, float* dW1, float* db1, float* dW2,
                  BwdWorkspace& w, int32_t phases, cudaStream_t st) {
   GemmParams p;
-  if (phases & TD_BWD_PHASE_NORM_W2) {
+  if (phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_W2_ONLY)) {
     // dW2[D, D] = scale * dh2^T . h1  (contraction over tokens; both operands MN-major)
     memset(&p, 0, sizeof(p));
     p.M = D; p.N = D; p.K = int(M); p.ld_out = D; p.alpha = scale; p.alpha_ptr = scale_ptr; p.out0 = dW2;
@@ -495,8 +495,10 @@ int32_t td_aligner_bwd_dh2(const void* dh2, const void* x, const void* h0, const
   if (ws_bytes < td_aligner_bwd_workspace_bytes(M, Din, D)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   BwdWorkspace w = carve_bwd(ws, M, D);
-  if (phases & TD_BWD_PHASE_NORM_W2) {
-    if (!dh2 || !h1 || !norm_partials || !dW2 || !db2 || !dg) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (phase 1)");
+  if ((phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_W2_ONLY)) && (!dh2 || !h1 || !dW2))
+    TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (dW2)");
+  if (phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_SMALL2_ONLY)) {
+    if (!norm_partials || !db2 || !dg) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (dg / db2)");
     int rpc;
     const int grid = norm_bwd_grid(M, &rpc);
     Carver pc(const_cast<void*>(norm_partials));

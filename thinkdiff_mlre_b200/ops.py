@@ -209,6 +209,12 @@ class AlignerBackwardFromDh2:
     def gelu_and_linear1(self, dW1, db1):
         self._call(L.BWD_GELU_W1, dW1, db1, None, None, None)
 
+    def norm_small(self, db2, dg):
+        self._call(L.BWD_SMALL2_ONLY, None, None, None, db2, dg)
+
+    def linear2_only(self, dW2):
+        self._call(L.BWD_W2_ONLY, None, None, dW2, None, None)
+
 
 def rmsnorm_fwd(x: torch.Tensor, g: torch.Tensor, eps: float = 1e-6, out_bf16: bool = False):
     _need_cuda(x, g)

@@ -141,11 +141,12 @@ class AlignerTrainStep:
         if not hasattr(self, "_small_done"):
             self._small_done = torch.cuda.Event()
         with torch.cuda.stream(self._update_stream):
-            for name in ("linear1", "linear2"):  # in gradient-ready order: each waits only for its own reduce-scatter
-                self._ag[name] = opt.launch_sharded_update(name, t)
-            opt.launch_small_update(t)  # [b2 | g | b1]: tiny all-reduce (issued last in backward), replicated AdamW
+            # in the order the collectives were issued: reduce-scatter(dW1), all-reduce(small), reduce-scatter(dW2)
+            self._ag["linear1"] = opt.launch_sharded_update("linear1", t)
+            opt.launch_small_update(t)  # [b2 | g | b1]: 48 KB all-reduce, replicated AdamW
             self._small_done.record(self._update_stream)
             self._upd_done["linear1"] = self._small_done
+            self._ag["linear2"] = opt.launch_sharded_update("linear2", t)
         # the gradient buckets were allocated on the compute stream and are last read on the update stream: keep them
         # alive until the compute stream has waited for the updates (next step), instead of record_stream(), which would
         # keep the caching allocator from recycling the 126 MB of buckets in time
