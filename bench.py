@@ -311,10 +311,19 @@ def main():
 
     # ---- per-kernel device times (separate pass of the same steps; CUDA events around every launch) --
     psteps = min(steps, 20)
+    prof_stepper, profile_pass = stepper, "same pipelined step (kernels of different streams overlap: per-launch times are upper bounds)"
+    if world == 1 and pipelined:
+        # one stream, no overlap between the AdamW side stream and the GEMMs: clean per-kernel times for the roofline
+        stepper.flush()
+        aligner._bwd_order, aligner._record_phase_events = "linear2_first", False
+        prof_stepper = td.AlignerTrainStep(aligner, opt, fused_loss=True, pipelined=False)
+        profile_pass = "sequential step: same kernels, same inputs, single stream (the timed region overlaps AdamW with the GEMMs)"
+        for i in range(2):
+            prof_stepper.step_device(*resident[i % NUM_BATCHES])
     L.profile_enable(True)
     for i in range(psteps):
-        stepper.step_device(*resident[i % NUM_BATCHES])
-    stepper.flush()
+        prof_stepper.step_device(*resident[i % NUM_BATCHES])
+    prof_stepper.flush()
     torch.cuda.synchronize()
     prof = L.profile_report()
     L.profile_enable(False)
@@ -341,7 +350,8 @@ def main():
                 "peak": peaks["bf16_tflops_sustained"] if kernels[dom]["bound"] == "tensor" else peaks["hbm_gbs"],
                 "unit": kernels[dom]["unit"], "frac": kernels[dom]["frac"], "traffic": traffic,
                 "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}); sustained bf16 figure: kernel timed inside a long step",
-                "ms_per_launch": kernels[dom]["ms_per_launch"], "share_of_kernel_time": kernels[dom]["share_of_kernel_time"]}
+                "ms_per_launch": kernels[dom]["ms_per_launch"], "share_of_kernel_time": kernels[dom]["share_of_kernel_time"],
+                "profile_pass": profile_pass}
 
     # the gradient all-reduce on its own (both buckets back to back, nothing else running): what overlap has to hide
     ar_alone = None
