@@ -29,7 +29,6 @@ import re
 import torch
 from torch import nn
 
-from . import _lib as L
 from . import ops
 
 EPS = 1e-6

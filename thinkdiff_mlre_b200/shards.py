@@ -22,7 +22,6 @@ from __future__ import annotations
 
 import json
 import mmap
-import os
 import struct
 
 import numpy as np
