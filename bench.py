@@ -289,8 +289,24 @@ def main():
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
         b0 = host[0]
         h2d = b0.flat.nbytes + b0.extras["flat_target"].nbytes + b0.src_row_start.nbytes + b0.lens.nbytes
+        if os.environ.get("TD_E2E_AB"):  # developer A/B: the same loop with 1 / 2 / 4 copy streams
+            for k in (1, 2, 4):
+                stepper.copy_streams = k
+                sync_all()
+                e0.record()
+                nxt = stepper.prefetch(host[0], dev)
+                for i in range(steps):
+                    cur = nxt
+                    if i + 1 < steps:
+                        nxt = stepper.prefetch(host[(i + 1) % NUM_BATCHES], dev)
+                    float(stepper.step_prefetched(cur))
+                stepper.flush()
+                e1.record()
+                sync_all()
+                print(f"e2e A/B: {k} copy stream(s) {e0.elapsed_time(e1) / steps:.3f} ms/step (default run {ms_e2e / steps:.3f})", file=sys.stderr)
+            stepper.copy_streams = 2
         e2e = {"value": tokens / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-               "ms_per_step": ms_e2e / steps, "note": "every step: H2D of its flat bf16 features + T5 targets from pinned memory (on a copy stream, overlapping the previous step's compute) and loss.item()"}
+               "ms_per_step": ms_e2e / steps, "note": "every step: H2D of its flat bf16 features + T5 targets from pinned memory (row chunks on two copy streams, overlapping the previous step's compute) and loss.item()"}
 
     if os.environ.get("TD_HOST_PROFILE") and rank == 0:  # developer aid: where does the host time of a step go?
         import cProfile, io, pstats

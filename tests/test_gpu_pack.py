@@ -154,3 +154,23 @@ def test_clip_two_image_plus_text_composition_config4():
     ref = aligner_ref.aligner_fwd_bwd_manual(img[:2].reshape(-1, din).float().cpu(), p16, regime="bf16", out_bf16=True, accum_dtype=torch.float32)
     err = (y[:2].reshape(-1, d).float().cpu() - ref["y"]).norm() / ref["y"].norm()
     assert err < 2e-2
+
+
+@pytest.mark.parametrize("k", [1, 2, 4])
+def test_prefetch_multi_stream_h2d_is_exact(k):
+    """AlignerTrainStep.prefetch cuts the flat features / targets into row chunks over k copy streams: the device tensors
+    must equal the pinned host tensors bit for bit once the returned events have been waited on."""
+    import thinkdiff_mlre_b200 as td
+
+    m = td.ThinkDiffAligner(192, 512).cuda()
+    step = td.AlignerTrainStep(m, None)
+    step.copy_streams = k
+    b = td.synthetic_lvlm_batch(9, 70, 192, 512, seed=77)
+    (flat, start, lens, total_rows, l_max, tgt), events = step.prefetch(b, "cuda")
+    for ev in events:
+        torch.cuda.current_stream().wait_event(ev)
+    torch.cuda.synchronize()
+    assert torch.equal(flat.cpu().view(torch.int16), b.flat.view(torch.int16))
+    assert torch.equal(tgt.cpu().view(torch.int16), b.extras["flat_target"].view(torch.int16))
+    assert torch.equal(start.cpu(), b.src_row_start) and torch.equal(lens.cpu(), b.lens)
+    assert total_rows == b.total_rows and l_max == b.l_max
