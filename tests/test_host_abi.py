@@ -127,6 +127,23 @@ def test_flat_collater_reproduces_reference_collater(name):
     assert fb.extras["embed_key"] == "model.norm.output_embed"
 
 
+@pytest.mark.parametrize("name", ["collater_random_split.npz", "collater_fixed_max.npz"])
+def test_flat_collater_truncate_on_host_is_equivalent(name):
+    """truncate_on_host=True ships only the kept rows; the packed / padded result is the same reference-collater output."""
+    g = load_golden(name)
+    bi = {k[3:]: int(v) for k, v in g.items() if k.startswith("bi_")}
+    random.seed(int(g["seed"]))
+    fb = td.FlatCollater(bi, pin_memory=False, truncate_on_host=True)(_samples_from_golden(g))
+    assert fb.flat.shape[0] == int(fb.lens.sum())  # nothing but kept rows crosses PCIe
+    assert fb.src_row_start.tolist() == [0] + torch.cumsum(fb.lens.long(), 0)[:-1].tolist()
+    bits = fb.flat.view(torch.int16).numpy().view(np.uint16)
+    packed, cu = pack_ref.pack_from_flat(bits, fb.src_row_start.tolist(), fb.lens.tolist())
+    padded, mask = pack_ref.unpack_padded(packed, cu, fb.l_max)
+    np.testing.assert_array_equal(padded, g["out_embed_bits"])
+    np.testing.assert_array_equal(mask, g["out_mask"])
+    np.testing.assert_array_equal(packed, bits)  # already compact
+
+
 def test_flat_collater_input_branch_and_errors():
     g = load_golden("collater_input_embed.npz")
     bi = {k[3:]: int(v) for k, v in g.items() if k.startswith("bi_")}

@@ -74,10 +74,13 @@ class FlatCollater:
     and the ``*output_embed*`` / ``*input_embed*`` tensors ``[L_i, C]``. The returned ``extras`` carry the same non-tensor
     keys the reference returns (``generated_texts``, ``output_token_ids`` sliced exactly as at :120 / :147-149)."""
 
-    def __init__(self, build_info: dict, pin_memory: bool = True, which: str = "output"):
+    def __init__(self, build_info: dict, pin_memory: bool = True, which: str = "output", truncate_on_host: bool = False):
         if not (build_info.get("use_output_embed") or build_info.get("use_input_embed")):
             raise ValueError("No input or output embeds are used.")  # reference message (:52-53)
         self.build_info, self.pin_memory, self.which = build_info, pin_memory, which
+        # truncate_on_host: copy only the kept rows of every sample into the flat buffer (what the reference collater's
+        # ``[:split_point]`` does) -- the H2D then moves M rows instead of sum(L_i); the device pack degenerates to a copy
+        self.truncate_on_host = truncate_on_host
 
     def __call__(self, samples) -> FlatBatch:
         key = [k for k in samples[0].keys() if f"{self.which}_embed" in k][0]
@@ -85,12 +88,13 @@ class FlatCollater:
         ids = [s["json"]["output_token_ids"] for s in samples]
         full_lens = [int(e.shape[0]) for e in embeds]
         lens, l_max = kept_lengths(full_lens, self.build_info, self.which)
-        flat = torch.cat(embeds, dim=0)
+        src_lens = lens if self.truncate_on_host else full_lens
+        flat = torch.cat([e[:n] for e, n in zip(embeds, lens)] if self.truncate_on_host else embeds, dim=0)
         if self.pin_memory and torch.cuda.is_available():
             flat = flat.pin_memory()
         start = torch.zeros(len(embeds), dtype=torch.int64)
         if len(embeds) > 1:
-            start[1:] = torch.cumsum(torch.tensor(full_lens[:-1], dtype=torch.int64), 0)
+            start[1:] = torch.cumsum(torch.tensor(src_lens[:-1], dtype=torch.int64), 0)
         if self.which == "output" and self.build_info.get("random_split_output_embed"):
             out_ids = [t[n:] for t, n in zip(ids, lens)]
         elif self.which == "output":
