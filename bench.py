@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after backward instead of overlapped")
     ap.add_argument("--no-pipeline", action="store_true", help="apply every parameter update inside its own step, on the compute stream")
+    ap.add_argument("--peer", action="store_true", help="N > 1, EXPERIMENTAL: gradient exchange over NVLink peer memory from the GEMM epilogues, no NCCL kernels on the step (thinkdiff_mlre_b200/peer.py)")
     ap.add_argument("--no-shard", action="store_true", help="N > 1: all-reduce + replicated AdamW instead of reduce-scatter + row-sharded AdamW + all-gather")
     ap.add_argument("--profile-out", default="", help="write the per-kernel table (JSON) here")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
@@ -219,7 +220,8 @@ def main():
     aligner = td.ThinkDiffAligner(DIN, D).to(dev)
     if world > 1:
         sharded = args.optimizer == "fused" and args.loss_path == "fused" and not args.no_pipeline and not args.no_shard and D % world == 0
-        aligner.enable_data_parallel(overlap=not args.no_overlap, defer_wait=args.optimizer == "fused", sharded=sharded)
+        aligner.enable_data_parallel(overlap=not args.no_overlap, defer_wait=args.optimizer == "fused", sharded=sharded,
+                                     peer=bool(args.peer and sharded))
     opt = td.FusedAdamW(aligner, lr=1e-4, weight_decay=0.05) if args.optimizer == "fused" else make_reference_optimizer(aligner)
     pipelined = args.optimizer == "fused" and args.loss_path == "fused" and not args.no_pipeline
     stepper = td.AlignerTrainStep(aligner, opt, fused_loss=args.loss_path == "fused", pipelined=pipelined)
@@ -396,7 +398,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": dict(workload_config(world), loss_path=args.loss_path, optimizer_impl=args.optimizer, pipelined_updates=pipelined, sharded_optimizer=bool(world > 1 and aligner._dp.sharded)), "clocks": clocks.summary(), "e2e": e2e,
+            "data": "synthetic", "config": dict(workload_config(world), loss_path=args.loss_path, optimizer_impl=args.optimizer, pipelined_updates=pipelined, sharded_optimizer=bool(world > 1 and aligner._dp.sharded), peer_exchange=bool(world > 1 and aligner._dp.peer)), "clocks": clocks.summary(), "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_peak": step_tflops / peaks["bf16_tflops_sustained"],
             "step_frac_of_nominal_2250": step_tflops / 2250.0, "tokens_per_step": tokens / steps, "final_loss": final_loss,

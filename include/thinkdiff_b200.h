@@ -132,6 +132,45 @@ int32_t td_adamw_step(int32_t num_tensors, float* const* params /*[host]*/, cons
                       const float* weight_decay /*[host]*/, float lr, float beta1, float beta2, float eps, int64_t step,
                       float grad_scale, td_stream_t stream);
 
+/* ---- (e) data parallel over NVLink peer memory (EXPERIMENTAL in round 1: compiled, not yet validated on hardware) --------
+ * Replaces DDP's NCCL all-reduce of the aligner gradients + the replicated optimizer step
+ * (thinkdiff/runners/runner_base.py:88-92, :98-127; thinkdiff/tasks/base_task.py:247-258) with a reduce-scatter fused into
+ * the weight-gradient GEMM epilogues: rank o owns rows [o D/world, (o+1) D/world) of W1 and W2; every rank's GEMM stores
+ * those rows of its (1/world-scaled) gradient straight into "slot[this rank]" of rank o's exchange buffer; rank o sums the
+ * slots in rank order inside its AdamW pass and stores the updated bf16 rows into every rank's compute copy. Ordering is by
+ * monotonically increasing step-number flags in the destination's memory (td_peer_signal / td_peer_wait), no collectives.
+ * Buffers come from td_peer_alloc (cudaMalloc + CUDA IPC handle, zero-filled); the other processes map them with td_peer_open.
+ * All pointer arrays are HOST arrays of `n` / `world` device pointers (<= TD_MAX_PEERS), entry o = the address in rank o. */
+enum { TD_MAX_PEERS = 8, TD_IPC_HANDLE_BYTES = 64 };
+int32_t td_peer_alloc(int64_t bytes, void** ptr /*[host] out*/, uint8_t* handle /*[host] out, TD_IPC_HANDLE_BYTES*/);
+int32_t td_peer_free(void* ptr);
+int32_t td_peer_open(const uint8_t* handle /*[host]*/, void** ptr /*[host] out*/);
+int32_t td_peer_close(void* ptr);
+/* flag_arrays[i][slot] = value at every rank i (release, system scope), ordered after all earlier work on `stream`. */
+int32_t td_peer_signal(void* const* flag_arrays /*[host]*/, int32_t n, int32_t slot, int32_t value, td_stream_t stream);
+/* Blocks `stream` until flags[0..n) >= value (local int32 flags written by the peers). Traps after timeout_s (<= 0: 30 s). */
+int32_t td_peer_wait(const int32_t* flags, int32_t n, int32_t value, float timeout_s, td_stream_t stream);
+/* dst[i][0..numel) = src[0..numel) for every rank i (the three small gradient vectors: every rank gets every rank's copy). */
+int32_t td_peer_post(const float* src, void* const* dst /*[host]*/, int32_t n, int64_t numel, td_stream_t stream);
+/* out = slots[0] + slots[1] + ... + slots[n_slots - 1] (slot s at slots + s * slot_stride), always in that order. */
+int32_t td_sum_slots(const float* slots, int64_t slot_stride, int32_t n_slots, float* out, int64_t numel, td_stream_t stream);
+/* td_adamw_step for one row block whose gradient is the sum of n_slots slots; the bf16 rows go to params_bf16[0..n_dst). */
+int32_t td_adamw_slots_step(float* param, const float* grad_slots, int64_t slot_stride, int32_t n_slots, float* exp_avg,
+                            float* exp_avg_sq, void* const* params_bf16 /*[host]*/, int32_t n_dst, int64_t numel,
+                            float weight_decay, float lr, float beta1, float beta2, float eps, int64_t step,
+                            float grad_scale, td_stream_t stream);
+/* td_aligner_bwd_dh2 with the two weight gradients row-scattered: dW?_dst[o] = [D / world, cols] fp32 block for the rows
+ * rank o owns. The weight-gradient GEMMs run un-split (bit-reproducible) with coalesced 128-byte stores. */
+int32_t td_aligner_bwd_dh2_scatter(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
+                                   const void* norm_partials, int64_t M, int32_t Din, int32_t D, float grad_scale,
+                                   const float* grad_scale_ptr, float* const* dW1_dst /*[host]*/, float* db1,
+                                   float* const* dW2_dst /*[host]*/, float* db2, float* dg, int32_t world, void* workspace,
+                                   int64_t workspace_bytes, int32_t phases, td_stream_t stream);
+/* Test entry for the scatter epilogue: out[M, N] = alpha * A^T.B with A [K, M], B [K, N] (both MN-major, the weight-gradient
+ * shape), rows [o M/world, (o+1) M/world) written to dst[o] ([M / world, N] fp32). */
+int32_t td_gemm_tn_scatter(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int32_t N, int64_t K,
+                           float alpha, float* const* dst /*[host]*/, int32_t world, td_stream_t stream);
+
 /* ---- (3) masked losses, forward + gradient in one pass -----------------------------------------------------
  * Cross entropy replaces `CrossEntropyLoss(ignore_index=-100)(lm_logits.view(-1, V), labels.view(-1))`
  * (thinkdiff/models/mllama_vllm_t5_embed_decoder_2.py:241-246; blip_vision_t5_decoder.py:222-227).

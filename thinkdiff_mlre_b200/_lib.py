@@ -42,6 +42,17 @@ SIGNATURES = {
     "td_linear_bf16": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
     "td_gemm_bf16_f32out": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i32, _i64, _f32, _vp, _i32, _i32, _vp]),
     "td_adamw_step": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_f32), _f32, _f32, _f32, _f32, _i64, _f32, _vp]),
+    "td_peer_alloc": (_i32, [_i64, C.POINTER(_vp), C.c_char_p]),
+    "td_peer_free": (_i32, [_vp]),
+    "td_peer_open": (_i32, [C.c_char_p, C.POINTER(_vp)]),
+    "td_peer_close": (_i32, [_vp]),
+    "td_peer_signal": (_i32, [_vp, _i32, _i32, _i32, _vp]),
+    "td_peer_wait": (_i32, [_vp, _i32, _i32, _f32, _vp]),
+    "td_peer_post": (_i32, [_vp, _vp, _i32, _i64, _vp]),
+    "td_sum_slots": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp]),
+    "td_adamw_slots_step": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _f32, _vp]),
+    "td_aligner_bwd_dh2_scatter": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _vp]),
+    "td_gemm_tn_scatter": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _i64, _f32, _vp, _i32, _vp]),
     "td_loss_workspace_bytes": (_i64, [_i64]),
     "td_masked_mse_fwd_bwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _i64, _vp]),
     "td_masked_ce_fwd_bwd": (_i32, [_vp, _i32, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _i64, _vp]),

@@ -59,7 +59,7 @@ class DataParallelState:
     remaining backward GEMMs run on the compute stream.
     """
 
-    def __init__(self, group=None, overlap: bool = True, defer_wait: bool = False, sharded: bool = False):
+    def __init__(self, group=None, overlap: bool = True, defer_wait: bool = False, sharded: bool = False, peer: bool = False):
         import torch.distributed as dist
 
         self.dist = dist
@@ -67,6 +67,12 @@ class DataParallelState:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.overlap = overlap
+        # peer (EXPERIMENTAL, see peer.py): the row-sharded plan below with NO collective on the step -- the weight-gradient
+        # GEMM epilogues store each owner's rows into its exchange buffer over NVLink, the owner's AdamW sums the slots and
+        # stores the bf16 rows into every rank's compute copy; step-number flags order it. Implies sharded + defer_wait.
+        self.peer = peer
+        if peer:
+            sharded = defer_wait = True
         # sharded (ZeRO-1 style, needs defer_wait + FusedAdamW): the two weight-gradient matrices are reduce-SCATTERED by
         # rows (rank r receives rows [r D/world, (r+1) D/world)), each rank runs AdamW on its rows only and the updated
         # bf16 rows are all-gathered; the three small vectors stay all-reduced and replicated.
@@ -74,7 +80,7 @@ class DataParallelState:
         if sharded and not defer_wait:
             raise ValueError("sharded=True requires defer_wait=True (the optimizer consumes the shards)")
         # a second communicator for the parameter all-gathers, so they are not queued behind the next reduce-scatter
-        self.ag_group = dist.new_group(ranks=dist.get_process_group_ranks(group) if group is not None else None) if sharded and self.world > 1 else group
+        self.ag_group = dist.new_group(ranks=dist.get_process_group_ranks(group) if group is not None else None) if sharded and not peer and self.world > 1 else group
         # defer_wait: backward returns without ordering the compute stream after the all-reduces; the consumer of the
         # gradients (FusedAdamW, or aligner.wait_grads()) waits bucket by bucket, so the Linear2 update overlaps the
         # Linear1 all-reduce.
@@ -147,6 +153,8 @@ class _AlignerFn(torch.autograd.Function):
         D = W2b.shape[0]
         dev = x2d.device
         dp = module._dp
+        if dp is not None and dp.peer:
+            raise NotImplementedError("peer data parallel runs through mse_loss_packed (AlignerTrainStep(fused_loss=True))")
         scale = 1.0 / dp.world if dp is not None else 1.0
         if dy.dtype not in (torch.float32, torch.bfloat16):
             dy = dy.float()
@@ -232,11 +240,35 @@ class _AlignerMSEFn(torch.autograd.Function):
         dp = module._dp
         scale = 1.0 / dp.world if dp is not None else 1.0
         bwd = ops.AlignerBackwardFromDh2(x2d, (h0, h1, dh2, partials), W2b, grad_loss, grad_scale=scale)
+        if dp is not None and dp.peer:
+            return (None, None, *_peer_backward(module, bwd, W2b.shape[0], x2d.device), None, None)
         gb = GradBuckets(x2d.shape[1], W2b.shape[0], x2d.device, small_separate=dp is not None and dp.sharded and dp.world > 1)
         module._grad_flats = gb.flats()
         _reduce_and_return(module, gb, lambda: bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg), lambda: bwd.gelu_and_linear1(gb.dW1, gb.db1),
                            split2=(lambda: bwd.norm_small(gb.db2, gb.dg), lambda: bwd.linear2_only(gb.dW2)))
         return (None, None, *gb.in_parameter_order(), None, None)
+
+
+def _peer_backward(module, bwd, d: int, device):
+    """Backward schedule of the peer-memory data-parallel mode (Linear1 first): each weight-gradient GEMM stores its rows into
+    the owners' exchange buffers and is followed by a flag store; the small vectors are posted to every rank in between.
+    Returns the gradients in parameter order -- None for the two matrices, which never exist as local tensors."""
+    from .peer import ROW_GRAD1, ROW_GRAD2, ROW_SMALL
+
+    px = module._ensure_peer()
+    module._peer_epoch += 1
+    e = module._peer_epoch
+    small = torch.empty(3 * d, dtype=torch.float32, device=device)  # [db2 | dg | db1], GradBuckets' small layout
+    db2, dg, db1 = small[:d], small[d : 2 * d], small[2 * d :]
+    module._grad_flats = {"small": small}
+    bwd.gelu_and_linear1_scatter(px.dw_dst(1), db1, px.world)
+    px.signal(ROW_GRAD1, e)
+    bwd.norm_small(db2, dg)
+    px.post_small(small)
+    px.signal(ROW_SMALL, e)
+    bwd.linear2_only_scatter(px.dw_dst(2), px.world)
+    px.signal(ROW_GRAD2, e)
+    return None, db1, None, db2, dg
 
 
 class ThinkDiffAligner(nn.Sequential):
@@ -262,6 +294,8 @@ class ThinkDiffAligner(nn.Sequential):
         self._between_fwd_stages = None     # callable run between Linear1 and Linear2 of the fused-loss forward
         self._bf16_managed = False          # True: an optimizer keeps the bf16 copies current; training never re-casts
         self._dp: DataParallelState | None = None
+        self._peer = None                   # PeerExchange (peer data parallel), created on first use
+        self._peer_epoch = 0                # number of peer-mode backward passes so far = the value the flags carry
         self.fp32_mode = "bf16x3"
 
     # -- reference-compatible config property (IdentityMap has one; harmless here)
@@ -270,9 +304,26 @@ class ThinkDiffAligner(nn.Sequential):
         return {"mm_projector_type": FUSED_TYPE}
 
     # -- data parallel (replaces DDP for this module)
-    def enable_data_parallel(self, group=None, overlap: bool = True, defer_wait: bool = False, sharded: bool = False):
-        self._dp = DataParallelState(group, overlap, defer_wait, sharded)
+    def enable_data_parallel(self, group=None, overlap: bool = True, defer_wait: bool = False, sharded: bool = False,
+                             peer: bool = False):
+        self._dp = DataParallelState(group, overlap, defer_wait, sharded, peer)
         return self
+
+    def _ensure_peer(self):
+        """Peer data parallel: allocate / map the exchange buffers (collective, first call only) and move the bf16 compute
+        copies of the two weights into this rank's buffer, where the owners of the other rows can store into them."""
+        if self._peer is None:
+            from .peer import PeerExchange
+
+            w1, w2 = self[0].weight, self[2].weight
+            if w1.dtype != torch.float32:
+                raise TypeError("peer data parallel is a training mode: parameters must be float32 masters")
+            px = PeerExchange(self.mm_hidden_size, self.hidden_size, self._dp.group, w1.device)
+            self._cache = (px.w1_bf16, torch.empty_like(self[0].bias, dtype=torch.bfloat16), px.w2_bf16,
+                           torch.empty_like(self[2].bias, dtype=torch.bfloat16))
+            self._cache_key, self._bf16_fresh = None, False
+            self._peer = px
+        return self._peer
 
     def sync_parameters(self):
         """Sharded data parallel: all-gather the fp32 master rows every rank updated for the others (collective; call on

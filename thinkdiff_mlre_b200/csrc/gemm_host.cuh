@@ -145,7 +145,8 @@ inline int choose_splits(int num_tiles, int num_k_blocks, int workers, int max_s
 }
 
 template <int CTAS, bool A_MN, bool B_MN, int EPI>
-int launch_gemm(GemmOperand a, GemmOperand b, GemmParams p, int splits, cudaStream_t stream, const char* tag = "gemm") {
+int launch_gemm(GemmOperand a, GemmOperand b, typename ParamsFor<EPI>::type p, int splits, cudaStream_t stream,
+                const char* tag = "gemm") {
   using S = GemmSmem<CTAS>;
   if (p.M <= 0 || p.N <= 0) return TD_OK;
   if (p.N % 32) TD_FAIL(TD_ERR_UNSUPPORTED, "GEMM N=%d must be a multiple of 32", p.N);

@@ -26,7 +26,13 @@ enum EpiKind : int {
   EPI_BIAS_SSQ = 2,   // out0 = h2 = bf16(acc + bias); red0[2 * n_blk + half][row] = sum over 128 cols of h2^2
   EPI_DGELU = 3,      // t = bf16(alpha * acc); out0 = bf16(t * gelu'(aux0)); red0[m_slab][col] = sum_rows out0
   EPI_F32 = 4,        // out0(fp32) = alpha * acc   (splits > 1: red.add into a zeroed out0)
+  // Row-sharded output over peer memory (data-parallel weight gradients, reduce-scatter fused into the GEMM): output row r
+  // belongs to rank o = r / scatter_rows and is written to scatter_dst[o] + (r - o * scatter_rows) * ld_out -- a buffer in
+  // rank o's HBM mapped into this process (NVLink stores), or local memory for o == this rank. The accumulator chunk is
+  // transposed in registers first so that every store instruction of a warp covers one full 128-byte line.
+  EPI_F32_SCATTER = 5,
 };
+constexpr int kMaxPeers = 8;
 
 struct GemmParams {
   int M, N, K;
@@ -42,6 +48,13 @@ struct GemmParams {
   const float* alpha_ptr;  // optional device scalar multiplied into alpha (upstream loss gradient / GradScaler scale)
   int* sched_counter;      // [2] zero-initialised {next unit, finished workers}; re-armed by the kernel itself
 };
+// EPI_F32_SCATTER takes a larger parameter block; every other instantiation keeps the plain GemmParams signature
+struct GemmScatterParams : GemmParams {
+  float* scatter_dst[kMaxPeers];
+  int scatter_rows;        // output rows per owner rank
+};
+template <int EPI> struct ParamsFor { using type = GemmParams; };
+template <> struct ParamsFor<EPI_F32_SCATTER> { using type = GemmScatterParams; };
 
 constexpr int kBlockM = 128;  // rows per CTA (TMEM lanes)
 constexpr int kBlockN = 256;  // accumulator columns (two stages fill the 512-column TMEM)
@@ -76,7 +89,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 
 template <int EPI>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int row0, int n0, int n_blk,
+__device__ __forceinline__ void epilogue_tile(const typename ParamsFor<EPI>::type& p, uint32_t tmem_acc, int row0, int n0, int n_blk,
                                               int m_slab, int quarter, int half, int lane) {
   const int row = row0 + quarter * 32 + lane;
   const bool row_ok = row < p.M;
@@ -85,7 +98,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
   const long long row_off = (long long)row * p.ld_out;
   float ssq = 0.f;
   float alpha = p.alpha;
-  if constexpr (EPI == EPI_F32 || EPI == EPI_DGELU) {
+  if constexpr (EPI == EPI_F32 || EPI == EPI_DGELU || EPI == EPI_F32_SCATTER) {
     if (p.alpha_ptr != nullptr) alpha *= __ldg(p.alpha_ptr);
   }
 
@@ -118,7 +131,34 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
     }
     tmem_ld_wait();
 
-    if constexpr (EPI == EPI_F32) {
+    if constexpr (EPI == EPI_F32_SCATTER) {
+      // 32 x 32 transpose across the warp (5 butterfly rounds of 16 exchanges): afterwards v[r] of lane j is element
+      // (row r of this warp's 32-row slab, column col0 + j), so each store below writes 32 consecutive floats
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if ((i & off) == 0) {
+            const uint32_t send = upper ? v[i] : v[i + off];
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, off);
+            if (upper) v[i] = recv; else v[i + off] = recv;
+          }
+        }
+      }
+      const int slab_row0 = row0 + quarter * 32;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const int orow = slab_row0 + r;  // warp-uniform
+        if (orow < p.M) {
+          const int owner = orow / p.scatter_rows;
+          float* base = p.scatter_dst[0];  // select with constant indices: no local copy of the parameter struct
+#pragma unroll
+          for (int o = 1; o < kMaxPeers; ++o) base = (owner == o) ? p.scatter_dst[o] : base;
+          base[(long long)(orow - owner * p.scatter_rows) * p.ld_out + col0 + lane] = alpha * __uint_as_float(v[r]);
+        }
+      }
+    } else if constexpr (EPI == EPI_F32) {
       float* out = reinterpret_cast<float*>(p.out0) + row_off + col0;
       if (row_ok) {
         if (p.splits == 1) {
@@ -213,7 +253,7 @@ constexpr int kSchedStages = 4;
 template <int CTAS, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmParams p) {
+                 const typename ParamsFor<EPI>::type p) {
   using S = GemmSmem<CTAS>;
   constexpr int kStages = S::kStages;
   constexpr int kBRows = kBlockN / CTAS;  // B rows staged by one CTA

@@ -5,6 +5,7 @@
 
 #include "gemm_host.cuh"
 #include "rowops_sm100.cuh"
+#include "peer_sm100.cuh"
 
 using namespace td;
 
@@ -354,15 +355,35 @@ int64_t td_aligner_bwd_workspace_bytes(int64_t M, int32_t Din, int32_t D) {
 
 namespace {
 // Backward from dh2 (already in the workspace or caller-provided): dW2 GEMM | dh0 GEMM + db1 + dW1 GEMM.
+// Row-sharded destinations of the two weight gradients (data parallel over peer memory): dW?[o] = where the rows owned by
+// rank o go (a [D / world, cols] fp32 block in rank o's memory, this rank's slot). world == 0: plain local outputs.
+struct ScatterDst {
+  int world = 0;
+  float* dW1[kMaxPeers] = {};
+  float* dW2[kMaxPeers] = {};
+};
+
+int launch_dw_gemm(GemmOperand a, GemmOperand b, GemmParams& p, float* const* dst, int world, cudaStream_t st, const char* tag) {
+  if (world <= 0) return launch_gemm<2, true, true, EPI_F32>(a, b, p, 0, st, tag);
+  GemmScatterParams sp;
+  memset(&sp, 0, sizeof(sp));
+  static_cast<GemmParams&>(sp) = p;
+  for (int o = 0; o < world; ++o) sp.scatter_dst[o] = dst[o];
+  sp.scatter_rows = p.M / world;
+  return launch_gemm<2, true, true, EPI_F32_SCATTER>(a, b, sp, 1, st, tag);
+}
+
 int bwd_from_dh2(const __nv_bfloat16* dh2, const void* x, const void* h0, const void* h1, const void* W2, int64_t M,
                  int32_t Din, int32_t D, float scale, const float* scale_ptr, float* dW1, float* db1, float* dW2,
-                 BwdWorkspace& w, int32_t phases, cudaStream_t st) {
+                 BwdWorkspace& w, int32_t phases, cudaStream_t st, const ScatterDst* sc = nullptr) {
   GemmParams p;
+  const int world = sc ? sc->world : 0;
   if (phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_W2_ONLY)) {
     // dW2[D, D] = scale * dh2^T . h1  (contraction over tokens; both operands MN-major)
     memset(&p, 0, sizeof(p));
     p.M = D; p.N = D; p.K = int(M); p.ld_out = D; p.alpha = scale; p.alpha_ptr = scale_ptr; p.out0 = dW2;
-    int rc = launch_gemm<2, true, true, EPI_F32>({dh2, D, true}, {h1, D, true}, p, 0, st, "gemm_dW2");
+    int rc = launch_dw_gemm({dh2, D, true}, {h1, D, true}, p, sc ? sc->dW2 : nullptr, world, st,
+                            world ? "gemm_dW2_scatter" : "gemm_dW2");
     if (rc) return rc;
   }
   if (phases & TD_BWD_PHASE_GELU_W1) {
@@ -378,7 +399,8 @@ int bwd_from_dh2(const __nv_bfloat16* dh2, const void* x, const void* h0, const 
     // dW1[D, Din] = scale * dh0^T . x   (dh0 already carries the upstream scalar)
     memset(&p, 0, sizeof(p));
     p.M = D; p.N = Din; p.K = int(M); p.ld_out = Din; p.alpha = scale; p.out0 = dW1;
-    rc = launch_gemm<2, true, true, EPI_F32>({w.dh0, D, true}, {x, Din, true}, p, 0, st, "gemm_dW1");
+    rc = launch_dw_gemm({w.dh0, D, true}, {x, Din, true}, p, sc ? sc->dW1 : nullptr, world, st,
+                        world ? "gemm_dW1_scatter" : "gemm_dW1");
     if (rc) return rc;
   }
   return TD_OK;
@@ -485,10 +507,12 @@ int32_t td_aligner_mse_fwd(const void* x, int64_t M, int32_t Din, int32_t D, con
   return TD_OK;
 }
 
-int32_t td_aligner_bwd_dh2(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
-                           const void* norm_partials, int64_t M, int32_t Din, int32_t D,
-                           float grad_scale, const float* grad_scale_ptr, float* dW1, float* db1, float* dW2, float* db2,
-                           float* dg, void* ws, int64_t ws_bytes, int32_t phases, td_stream_t stream) {
+}  // extern "C"
+namespace {
+int bwd_dh2_impl(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
+                 const void* norm_partials, int64_t M, int32_t Din, int32_t D,
+                 float grad_scale, const float* grad_scale_ptr, float* dW1, float* db1, float* dW2, float* db2,
+                 float* dg, void* ws, int64_t ws_bytes, int32_t phases, td_stream_t stream, const ScatterDst* sc) {
   TD_DEVICE_OR_RETURN();
   if (!dims_ok(Din, D)) TD_FAIL(TD_ERR_UNSUPPORTED, "td_aligner_bwd_dh2: Din=%d, D=%d must be multiples of 64 (D <= 4096)", Din, D);
   if (M <= 0 || M > 0x7fffffffll / D) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: M=%lld out of range", (long long)M);
@@ -510,7 +534,39 @@ int32_t td_aligner_bwd_dh2(const void* dh2, const void* x, const void* h0, const
   }
   if ((phases & TD_BWD_PHASE_GELU_W1) && (!x || !h0 || !W2 || !dW1 || !db1)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (phase 2)");
   return bwd_from_dh2(static_cast<const __nv_bfloat16*>(dh2), x, h0, h1, W2, M, Din, D, grad_scale, grad_scale_ptr, dW1, db1,
-                      dW2, w, phases, st);
+                      dW2, w, phases, st, sc);
+}
+}  // namespace
+extern "C" {
+
+int32_t td_aligner_bwd_dh2(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
+                           const void* norm_partials, int64_t M, int32_t Din, int32_t D,
+                           float grad_scale, const float* grad_scale_ptr, float* dW1, float* db1, float* dW2, float* db2,
+                           float* dg, void* ws, int64_t ws_bytes, int32_t phases, td_stream_t stream) {
+  return bwd_dh2_impl(dh2, x, h0, h1, W2, norm_partials, M, Din, D, grad_scale, grad_scale_ptr, dW1, db1, dW2, db2, dg, ws,
+                      ws_bytes, phases, stream, nullptr);
+}
+
+int32_t td_aligner_bwd_dh2_scatter(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
+                                   const void* norm_partials, int64_t M, int32_t Din, int32_t D, float grad_scale,
+                                   const float* grad_scale_ptr, float* const* dW1_dst, float* db1, float* const* dW2_dst,
+                                   float* db2, float* dg, int32_t world, void* ws, int64_t ws_bytes, int32_t phases,
+                                   td_stream_t stream) {
+  if (world < 1 || world > kMaxPeers || D % world)
+    TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2_scatter: world=%d must be 1..%d and divide D=%d", world, kMaxPeers, D);
+  ScatterDst sc;
+  sc.world = world;
+  const bool need1 = (phases & TD_BWD_PHASE_GELU_W1) != 0;
+  const bool need2 = (phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_W2_ONLY)) != 0;
+  for (int o = 0; o < world; ++o) {
+    if ((need1 && (!dW1_dst || !dW1_dst[o])) || (need2 && (!dW2_dst || !dW2_dst[o])))
+      TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2_scatter: null destination for rank %d", o);
+    if (need1) sc.dW1[o] = dW1_dst[o];
+    if (need2) sc.dW2[o] = dW2_dst[o];
+  }
+  // the impl's null checks look at dW1 / dW2: hand it the first destination
+  return bwd_dh2_impl(dh2, x, h0, h1, W2, norm_partials, M, Din, D, grad_scale, grad_scale_ptr, need1 ? sc.dW1[0] : nullptr,
+                      db1, need2 ? sc.dW2[0] : nullptr, db2, dg, ws, ws_bytes, phases, stream, &sc);
 }
 
 // ------------------------------------------------------------------------------------------------ optimizer
@@ -545,6 +601,139 @@ int32_t td_adamw_step(int32_t num_tensors, float* const* params, const float* co
   adamw_kernel<<<dim3(gx, num_tensors), 256, 0, st>>>(a);
   TD_CUDA(cudaGetLastError());
   return TD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ peer-memory data parallel
+int32_t td_peer_alloc(int64_t bytes, void** ptr, uint8_t* handle) {
+  TD_DEVICE_OR_RETURN();
+  static_assert(sizeof(cudaIpcMemHandle_t) == TD_IPC_HANDLE_BYTES, "IPC handle size");
+  if (bytes <= 0 || !ptr || !handle) TD_FAIL(TD_ERR_ARG, "td_peer_alloc: bad arguments");
+  void* p = nullptr;
+  TD_CUDA(cudaMalloc(&p, (size_t)bytes));
+  cudaError_t e = cudaMemset(p, 0, (size_t)bytes);  // flags start at step 0
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    TD_FAIL(-100 - int(e), "td_peer_alloc: %s", cudaGetErrorString(e));
+  }
+  memcpy(handle, &h, sizeof(h));
+  *ptr = p;
+  return TD_OK;
+}
+
+int32_t td_peer_free(void* ptr) {
+  if (ptr) TD_CUDA(cudaFree(ptr));
+  return TD_OK;
+}
+
+int32_t td_peer_open(const uint8_t* handle, void** ptr) {
+  TD_DEVICE_OR_RETURN();
+  if (!handle || !ptr) TD_FAIL(TD_ERR_ARG, "td_peer_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  TD_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return TD_OK;
+}
+
+int32_t td_peer_close(void* ptr) {
+  if (ptr) TD_CUDA(cudaIpcCloseMemHandle(ptr));
+  return TD_OK;
+}
+
+namespace {
+int fill_peers(PeerPtrs& pp, void* const* arr, int n, const char* what) {
+  memset(&pp, 0, sizeof(pp));
+  if (n < 1 || n > kMaxPeers || !arr) TD_FAIL(TD_ERR_ARG, "%s: 1..%d destinations, got %d", what, kMaxPeers, n);
+  for (int i = 0; i < n; ++i) {
+    if (!arr[i]) TD_FAIL(TD_ERR_ARG, "%s: null pointer for rank %d", what, i);
+    pp.p[i] = arr[i];
+  }
+  return TD_OK;
+}
+}  // namespace
+
+int32_t td_peer_signal(void* const* flag_arrays, int32_t n, int32_t slot, int32_t value, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  PeerPtrs pp;
+  int rc = fill_peers(pp, flag_arrays, n, "td_peer_signal");
+  if (rc) return rc;
+  if (slot < 0) TD_FAIL(TD_ERR_ARG, "td_peer_signal: negative slot");
+  peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pp, n, slot, value);
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+int32_t td_peer_wait(const int32_t* flags, int32_t n, int32_t value, float timeout_s, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (!flags || n < 1 || n > 32) TD_FAIL(TD_ERR_ARG, "td_peer_wait: 1..32 flags");
+  if (!(timeout_s > 0.f)) timeout_s = 30.f;
+  peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, n, value, (unsigned long long)(double(timeout_s) * 1e9));
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+int32_t td_peer_post(const float* src, void* const* dst, int32_t n, int64_t numel, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  PeerPtrs pp;
+  int rc = fill_peers(pp, dst, n, "td_peer_post");
+  if (rc) return rc;
+  if (!src || numel < 0 || numel % 4) TD_FAIL(TD_ERR_ARG, "td_peer_post: numel must be a non-negative multiple of 4");
+  if (numel == 0) return TD_OK;
+  peer_post_kernel<<<grid_for_rows(numel / 4, 256, 2), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src), pp, n, numel / 4);
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+int32_t td_sum_slots(const float* slots, int64_t slot_stride, int32_t n_slots, float* out, int64_t numel, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (!slots || !out || n_slots < 1 || numel < 0 || numel % 4 || slot_stride % 4 || slot_stride < numel)
+    TD_FAIL(TD_ERR_ARG, "td_sum_slots: bad arguments (numel and slot_stride must be multiples of 4, slot_stride >= numel)");
+  if (numel == 0) return TD_OK;
+  sum_slots_kernel<<<grid_for_rows(numel / 4, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(slots), slot_stride / 4, n_slots, reinterpret_cast<float4*>(out), numel / 4);
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+int32_t td_adamw_slots_step(float* param, const float* grad_slots, int64_t slot_stride, int32_t n_slots, float* exp_avg,
+                            float* exp_avg_sq, void* const* params_bf16, int32_t n_dst, int64_t numel, float weight_decay,
+                            float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
+                            td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (!param || !grad_slots || !exp_avg || !exp_avg_sq || numel < 0) TD_FAIL(TD_ERR_ARG, "td_adamw_slots_step: null pointer");
+  if (numel % 4 || slot_stride % 4 || slot_stride < numel || n_slots < 1)
+    TD_FAIL(TD_ERR_ARG, "td_adamw_slots_step: numel / slot_stride must be multiples of 4, slot_stride >= numel, n_slots >= 1");
+  if (step < 1) TD_FAIL(TD_ERR_ARG, "td_adamw_slots_step: step counts from 1");
+  AdamSlotsParams a;
+  memset(&a, 0, sizeof(a));
+  int rc = fill_peers(a.p_bf16, params_bf16, n_dst, "td_adamw_slots_step");
+  if (rc) return rc;
+  a.p = param; a.m = exp_avg; a.v = exp_avg_sq; a.slots = grad_slots; a.slot_stride = slot_stride; a.n_slots = n_slots;
+  a.n_dst = n_dst; a.n = numel; a.weight_decay = weight_decay;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_scale = grad_scale;
+  a.bias_c1 = 1.0f - powf(beta1, float(step));
+  a.sqrt_bias_c2 = sqrtf(1.0f - powf(beta2, float(step)));
+  if (numel == 0) return TD_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof("adamw_slots", (28.0 + 4.0 * n_slots + 2.0 * n_dst) * double(numel), st);
+  adamw_slots_kernel<<<grid_for_rows(numel / 4, 256, 8), 256, 0, st>>>(a);
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+int32_t td_gemm_tn_scatter(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int32_t N, int64_t K, float alpha,
+                           float* const* dst, int32_t world, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (world < 1 || world > kMaxPeers || M % world) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter: world=%d must be 1..%d and divide M", world, kMaxPeers);
+  if (M <= 0 || M > 0x7fffffffll || K <= 0 || K > 0x7fffffffll) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter: size out of range");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = int(M); p.N = N; p.K = int(K); p.ld_out = N; p.alpha = alpha;
+  for (int o = 0; o < world; ++o) {
+    if (!dst || !dst[o]) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter: null destination for rank %d", o);
+  }
+  return launch_dw_gemm({A, lda, true}, {B, ldb, true}, p, dst, world, (cudaStream_t)stream, "gemm_tn_scatter");
 }
 
 // ------------------------------------------------------------------------------------------------ losses

@@ -212,6 +212,23 @@ class AlignerBackwardFromDh2:
     def norm_small(self, db2, dg):
         self._call(L.BWD_SMALL2_ONLY, None, None, None, db2, dg)
 
+    def _call_scatter(self, phase, dW1_dst, db1, dW2_dst, world):
+        L.launch_count += 3 if phase == L.BWD_GELU_W1 else 1
+        L.check(
+            L.lib().td_aligner_bwd_dh2_scatter(L.ptr(self.dh2), L.ptr(self.x), L.ptr(self.h0), L.ptr(self.h1), L.ptr(self.W2),
+                                               L.ptr(self.partials), self.M, self.Din, self.D, self.grad_scale,
+                                               L.ptr(self.upstream), dW1_dst, L.ptr(db1), dW2_dst, None, None, world,
+                                               L.ptr(self.ws), self.ws_bytes, phase, L.stream_ptr()),
+            "td_aligner_bwd_dh2_scatter",
+        )
+
+    def gelu_and_linear1_scatter(self, dW1_dst, db1, world: int):
+        """Phase 2 with dW1's rows stored to their owner ranks (``dW1_dst``: host array of ``world`` device pointers)."""
+        self._call_scatter(L.BWD_GELU_W1, dW1_dst, db1, None, world)
+
+    def linear2_only_scatter(self, dW2_dst, world: int):
+        self._call_scatter(L.BWD_W2_ONLY, None, None, dW2_dst, world)
+
     def linear2_only(self, dW2):
         self._call(L.BWD_W2_ONLY, None, None, dW2, None, None)
 

@@ -74,6 +74,8 @@ class FusedAdamW(torch.optim.Optimizer):
         0.bias), after ordering the stream behind that bucket's all-reduce. ``t`` = optimizer step number the gradients
         belong to (defaults to the current one); ``release_grads`` drops the ``.grad`` references afterwards."""
         a = self.aligner
+        if a._dp is not None and a._dp.peer:
+            raise RuntimeError("peer data parallel: parameters are updated by AlignerTrainStep(pipelined=True), not by step()")
         t = self._t if t is None else t
         a.wait_bucket(name)
         named = self._named()
@@ -149,6 +151,49 @@ class FusedAdamW(torch.optim.Optimizer):
         W.grad = None
         a._grad_flats[name] = None
         return ag
+
+    @torch.no_grad()
+    def launch_peer_update(self, name: str, t: int, epoch: int):
+        """Peer data parallel (current stream = the caller's update stream): wait until every rank has stored its slot of this
+        weight's gradient rows into this rank's exchange buffer, run AdamW on the summed slots (bf16 rows go straight into every
+        rank's compute copy) and raise this rank's "weights written" flag everywhere."""
+        from .peer import ROW_GRAD1, ROW_GRAD2, ROW_W1, ROW_W2
+
+        a = self.aligner
+        px = a._ensure_peer()
+        which = 1 if name == "linear1" else 2
+        W = self._named()["0.weight" if which == 1 else "2.weight"]
+        lo, hi = a._dp.shard_rows(W.shape[0])
+        st = self.state[W]
+        if "exp_avg" not in st or st["exp_avg"].shape[0] != hi - lo:
+            st["exp_avg"] = torch.zeros((hi - lo, W.shape[1]), dtype=torch.float32, device=W.device)
+            st["exp_avg_sq"] = torch.zeros((hi - lo, W.shape[1]), dtype=torch.float32, device=W.device)
+            st["shard_rows"] = (lo, hi)
+        st["step"] = t
+        g = self._group_of(W)
+        px.wait(ROW_GRAD1 if which == 1 else ROW_GRAD2, epoch)
+        px.adamw_rows(which, W.data[lo:hi], st["exp_avg"], st["exp_avg_sq"], g["weight_decay"], g["lr"], g["betas"], g["eps"], t,
+                      self.grad_scale)
+        px.signal(ROW_W1 if which == 1 else ROW_W2, epoch)
+
+    @torch.no_grad()
+    def launch_peer_small_update(self, t: int, epoch: int):
+        """Peer data parallel: sum every rank's posted [db2 | dg | db1] (rank order, in place of the local values) and update the
+        three replicated vectors."""
+        from .peer import ROW_SMALL
+
+        a = self.aligner
+        px = a._ensure_peer()
+        small, d = a._grad_flats["small"], a.hidden_size
+        px.wait(ROW_SMALL, epoch)
+        px.sum_small(small)
+        grads = {"2.bias": small[:d], "3.weight": small[d : 2 * d], "0.bias": small[2 * d :]}
+        keys = ["2.bias", "3.weight", "0.bias"]
+        self._update_tensors(keys, t, grads)
+        named = self._named()
+        for k in keys:
+            named[k].grad = None
+        a._grad_flats["small"] = None
 
     @torch.no_grad()
     def launch_small_update(self, t: int):

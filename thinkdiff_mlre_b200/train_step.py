@@ -67,6 +67,10 @@ class AlignerTrainStep:
         self.pipelined = pipelined
         self._pending_t = None
         self._sharded = False
+        self._peer = False
+        if aligner._dp is not None and aligner._dp.peer and not pipelined:
+            raise ValueError("peer data parallel needs AlignerTrainStep(pipelined=True) with FusedAdamW (the owners' AdamW "
+                             "kernels are what consume the gradient slots)")
         if pipelined:
             from .optim import FusedAdamW
 
@@ -77,8 +81,9 @@ class AlignerTrainStep:
             # sharded data parallel (enable_data_parallel(sharded=True)): reduce-scatter -> AdamW on this rank's rows ->
             # all-gather of the bf16 rows, all on a side stream that runs beside the remaining GEMMs
             self._sharded = dp is not None and dp.sharded and dp.world > 1
+            self._peer = dp is not None and dp.peer  # (also at world 1: the degenerate case exercises every kernel)
             self._ag, self._upd_done = {}, {}
-            aligner._record_phase_events = not self._sharded
+            aligner._record_phase_events = not (self._sharded or self._peer)
 
     def step_device(self, flat, src_row_start, lens_dev, total_rows: int, l_max: int, flat_target) -> torch.Tensor:
         """Inputs already resident in HBM. Returns the (unscaled) loss as a device scalar; nothing syncs the host."""
@@ -153,7 +158,52 @@ class AlignerTrainStep:
         self._grads_hold = grads
         return loss
 
+    def _step_pipelined_peer(self, packed, target) -> torch.Tensor:
+        """The sharded pipeline with no collectives (peer.py): gradients reach their owner from the GEMM epilogues, updated bf16
+        rows come back from the owners' AdamW kernels, and the compute stream only ever waits on step-number flags."""
+        from .peer import ROW_W1, ROW_W2
+
+        a, opt = self.aligner, self.optimizer
+        px = a._ensure_peer()
+        opt.grad_scale = 1.0 / self.loss_scale
+        if self._pending_t is not None:
+            prev = a._peer_epoch
+            px.wait(ROW_W1, prev)             # every owner has stored its rows of W1 for the previous step
+            self._wait_update("linear1")      # small vectors (b1 for GEMM1's epilogue; b2 / g for stage 2)
+
+            def before_gemm2():
+                px.wait(ROW_W2, prev)
+
+            a._between_fwd_stages = before_gemm2
+            a._bf16_managed = True
+        try:
+            loss = a.mse_loss_packed(packed.x, *target)
+        finally:
+            a._between_fwd_stages = None
+        self._grads_hold = None
+        (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
+        t = opt.next_step_number()
+        self._pending_t = t
+        e = a._peer_epoch
+        if not hasattr(self, "_update_stream"):
+            self._update_stream = torch.cuda.Stream()
+        if not hasattr(self, "_small_done"):
+            self._small_done = torch.cuda.Event()
+        grads = list(a._grad_flats.values())
+        with torch.cuda.stream(self._update_stream):
+            # no event from the compute stream is needed: each update waits on flags, and this rank's own flag is stored by
+            # the compute stream right after the GEMM that produced the data
+            opt.launch_peer_update("linear1", t, e)
+            opt.launch_peer_small_update(t, e)
+            self._small_done.record(self._update_stream)
+            self._upd_done["linear1"] = self._small_done
+            opt.launch_peer_update("linear2", t, e)
+        self._grads_hold = grads
+        return loss
+
     def _step_pipelined(self, packed, target) -> torch.Tensor:
+        if self._peer:
+            return self._step_pipelined_peer(packed, target)
         if self._sharded:
             return self._step_pipelined_sharded(packed, target)
         a, opt = self.aligner, self.optimizer
@@ -188,7 +238,16 @@ class AlignerTrainStep:
     def flush(self):
         """Apply the parameter updates still pending from the last pipelined step (no-op otherwise)."""
         if self._pending_t is not None:
-            if self._sharded:
+            if self._peer:
+                from .peer import ROW_W1, ROW_W2
+
+                px, e = self.aligner._ensure_peer(), self.aligner._peer_epoch
+                px.wait(ROW_W1, e)
+                px.wait(ROW_W2, e)
+                self._wait_update("linear1")
+                self._grads_hold = None
+                self.aligner.sync_parameters()  # fp32 master rows of the other ranks (NCCL all-gather, off the hot path)
+            elif self._sharded:
                 self._wait_update("linear1")
                 self._wait_update("linear2")
                 self._grads_hold = None
