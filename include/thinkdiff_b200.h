@@ -28,7 +28,10 @@ enum { TD_OK_ = 0, TD_ERR_ARG_ = -1, TD_ERR_UNSUPPORTED_ = -2, TD_ERR_DRIVER_ = 
  * while the Linear1 gradients are still being computed (DDP bucket overlap, thinkdiff/runners/runner_base.py:88-92). */
 enum { TD_BWD_PHASE_NORM_W2 = 1, TD_BWD_PHASE_GELU_W1 = 2, TD_BWD_PHASE_ALL = 3,
        /* td_aligner_bwd_dh2 only: the two halves of NORM_W2, so the small vectors' all-reduce can start before the dW2 GEMM */
-       TD_BWD_PHASE_SMALL2_ONLY = 4, TD_BWD_PHASE_W2_ONLY = 8 };
+       TD_BWD_PHASE_SMALL2_ONLY = 4, TD_BWD_PHASE_W2_ONLY = 8,
+       /* td_aligner_bwd_dh2_scatter only: the dh0 GEMM + db1 without dW1, and dW1 + dW2 as ONE grouped GEMM launch (480 tiles
+        * instead of 224 + 256: the un-split launches would leave the last wave of CTA pairs mostly idle) */
+       TD_BWD_PHASE_GELU_ONLY = 16, TD_BWD_PHASE_W12_GROUPED = 32 };
 
 const char* td_last_error(void);
 int32_t td_version(void);
@@ -170,6 +173,12 @@ int32_t td_aligner_bwd_dh2_scatter(const void* dh2, const void* x, const void* h
  * shape), rows [o M/world, (o+1) M/world) written to dst[o] ([M / world, N] fp32). */
 int32_t td_gemm_tn_scatter(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int32_t N, int64_t K,
                            float alpha, float* const* dst /*[host]*/, int32_t world, td_stream_t stream);
+
+/* Test entry for the grouped launch: both products above in one kernel (shared M and K; problem 1's tensor maps are read from
+ * device memory). */
+int32_t td_gemm_tn_scatter_pair(const void* A1, int64_t lda1, const void* B1, int64_t ldb1, int32_t N1, float* const* dst1 /*[host]*/,
+                                const void* A2, int64_t lda2, const void* B2, int64_t ldb2, int32_t N2, float* const* dst2 /*[host]*/,
+                                int64_t M, int64_t K, float alpha, int32_t world, td_stream_t stream);
 
 /* ---- (3) masked losses, forward + gradient in one pass -----------------------------------------------------
  * Cross entropy replaces `CrossEntropyLoss(ignore_index=-100)(lm_logits.view(-1, V), labels.view(-1))`

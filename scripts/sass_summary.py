@@ -40,7 +40,7 @@ def main():
             cur = m.group(1)
             counts[cur] = collections.Counter()
             continue
-        m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z_][A-Z0-9_.]*)", line)
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z_][A-Z0-9_.]*)", line)
         if cur and m:
             op = m.group(1)
             n_instr[cur] += 1

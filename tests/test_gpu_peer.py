@@ -37,6 +37,28 @@ def test_scatter_gemm_matches_unsplit_gemm_bit_exactly(world, shape):
     assert torch.equal(torch.cat(parts), want)
 
 
+@pytest.mark.parametrize("world", [1, 8])
+def test_grouped_scatter_pair_matches_two_unsplit_gemms_bit_exactly(world):
+    from thinkdiff_mlre_b200 import _lib as L
+    from thinkdiff_mlre_b200 import ops
+
+    M, N1, N2, K = 4096, 3584, 4096, 1500  # the two weight gradients of the headline config, short token dimension
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A1 = torch.randn((K, M), generator=g, device="cuda").to(torch.bfloat16)
+    B1 = torch.randn((K, N1), generator=g, device="cuda").to(torch.bfloat16)
+    A2 = torch.randn((K, M), generator=g, device="cuda").to(torch.bfloat16)
+    B2 = torch.randn((K, N2), generator=g, device="cuda").to(torch.bfloat16)
+    want1 = ops.gemm_f32out(A1, B1, True, True, alpha=0.25, cta_pair=True, splits=1)
+    want2 = ops.gemm_f32out(A2, B2, True, True, alpha=0.25, cta_pair=True, splits=1)
+    d1 = [torch.full((M // world, N1), float("nan"), device="cuda") for _ in range(world)]
+    d2 = [torch.full((M // world, N2), float("nan"), device="cuda") for _ in range(world)]
+    L.check(L.lib().td_gemm_tn_scatter_pair(L.ptr(A1), M, L.ptr(B1), N1, N1, _arr(d1), L.ptr(A2), M, L.ptr(B2), N2, N2, _arr(d2), M, K,
+                                            0.25, world, L.stream_ptr()), "td_gemm_tn_scatter_pair")
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat(d1), want1)
+    assert torch.equal(torch.cat(d2), want2)
+
+
 def test_flags_post_sum_and_adamw_slots_loopback():
     from thinkdiff_mlre_b200 import _lib as L
 
@@ -127,8 +149,10 @@ def _run(world, mode):
     return {r: (params, losses) for r, params, losses in res}
 
 
-def test_peer_training_world1_equals_plain_pipeline():
+@pytest.mark.parametrize("grouped", ["0", "1"])
+def test_peer_training_world1_equals_plain_pipeline(grouped, monkeypatch):
     """Degenerate single-rank case: every kernel of the peer path runs (scatter epilogue, flags, slot AdamW), no IPC."""
+    monkeypatch.setenv("TD_PEER_GROUPED", grouped)  # inherited by the spawned worker
     plain, peer = _run(1, "plain"), _run(1, "peer")
     for a, b in zip(plain[0][0], peer[0][0]):
         np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-8)

@@ -61,7 +61,7 @@ class Memory:
         cell["v"] = version
 
 
-def compute_stream(rank, world, steps, fixed=True):
+def compute_stream(rank, world, steps, grouped=False):
     """Operations of the compute stream of ``rank``: ("wait", row, value) | ("wait_event", name, step) | ("signal", row, value) |
     ("data", begin_fn, end_fn)."""
     ops = []
@@ -75,6 +75,14 @@ def compute_stream(rank, world, steps, fixed=True):
             ops.append(("wait", W2, t - 1))
         ops.append(("read_weight", 2, t - 1))        # GEMM2
         ops.append(("read_weight", 2, t - 1))        # backward: dh0 = dh2 . W2
+        if grouped:                                  # TD_PEER_GROUPED=1: dW1 + dW2 as one launch, after the small vectors
+            ops.append(("post_small", t))
+            ops.append(("signal", SMALL, t))
+            ops.append(("write_slots", 1, t))
+            ops.append(("write_slots", 2, t))
+            ops.append(("signal", GRAD1, t))
+            ops.append(("signal", GRAD2, t))
+            continue
         ops.append(("write_slots", 1, t))            # dW1 GEMM, scatter epilogue
         ops.append(("signal", GRAD1, t))
         ops.append(("post_small", t))
@@ -206,10 +214,14 @@ def simulate(world, steps, seed, compute=compute_stream, update=update_stream):
     return mem
 
 
+@pytest.mark.parametrize("grouped", [False, True])
 @pytest.mark.parametrize("world", [1, 2, 3, 4])
-def test_no_hazard_and_no_deadlock_under_random_interleavings(world):
+def test_no_hazard_and_no_deadlock_under_random_interleavings(world, grouped):
+    def compute(rank, w, steps):
+        return compute_stream(rank, w, steps, grouped=grouped)
+
     for seed in range(150):
-        mem = simulate(world, steps=4, seed=seed)
+        mem = simulate(world, steps=4, seed=seed, compute=compute)
         assert all(c["v"] == 4 for c in mem.weight.values())
 
 

@@ -24,6 +24,7 @@ Numerical regimes:
 """
 from __future__ import annotations
 
+import os
 import re
 
 import torch
@@ -261,13 +262,23 @@ def _peer_backward(module, bwd, d: int, device):
     small = torch.empty(3 * d, dtype=torch.float32, device=device)  # [db2 | dg | db1], GradBuckets' small layout
     db2, dg, db1 = small[:d], small[d : 2 * d], small[2 * d :]
     module._grad_flats = {"small": small}
-    bwd.gelu_and_linear1_scatter(px.dw_dst(1), db1, px.world)
-    px.signal(ROW_GRAD1, e)
-    bwd.norm_small(db2, dg)
-    px.post_small(small)
-    px.signal(ROW_SMALL, e)
-    bwd.linear2_only_scatter(px.dw_dst(2), px.world)
-    px.signal(ROW_GRAD2, e)
+    if module._peer_grouped:
+        # one grouped launch for both weight gradients (480 tiles over 74 CTA pairs instead of 224 and 256 on their own)
+        bwd.gelu_only(db1, px.world)
+        bwd.norm_small(db2, dg)
+        px.post_small(small)
+        px.signal(ROW_SMALL, e)
+        bwd.grouped_scatter(px.dw_dst(1), px.dw_dst(2), px.world)
+        px.signal(ROW_GRAD1, e)
+        px.signal(ROW_GRAD2, e)
+    else:
+        bwd.gelu_and_linear1_scatter(px.dw_dst(1), db1, px.world)
+        px.signal(ROW_GRAD1, e)
+        bwd.norm_small(db2, dg)
+        px.post_small(small)
+        px.signal(ROW_SMALL, e)
+        bwd.linear2_only_scatter(px.dw_dst(2), px.world)
+        px.signal(ROW_GRAD2, e)
     return None, db1, None, db2, dg
 
 
@@ -296,6 +307,7 @@ class ThinkDiffAligner(nn.Sequential):
         self._dp: DataParallelState | None = None
         self._peer = None                   # PeerExchange (peer data parallel), created on first use
         self._peer_epoch = 0                # number of peer-mode backward passes so far = the value the flags carry
+        self._peer_grouped = os.environ.get("TD_PEER_GROUPED", "0") == "1"  # dW1 + dW2 as one grouped GEMM launch
         self.fp32_mode = "bf16x3"
 
     # -- reference-compatible config property (IdentityMap has one; harmless here)

@@ -52,6 +52,14 @@ struct GemmParams {
 struct GemmScatterParams : GemmParams {
   float* scatter_dst[kMaxPeers];
   int scatter_rows;        // output rows per owner rank
+  // Optional second problem in the same launch (the two weight-gradient GEMMs of a step share M = weight rows and K = tokens):
+  // tiles [0, num_m_blocks * num_n_blocks) belong to problem 0, the rest to problem 1. One launch of 224 + 256 tiles fills the
+  // 74 CTA pairs far more evenly (6.5 waves) than two un-split launches (3.03 and 3.46 waves).
+  const CUtensorMap* maps2;  // DEVICE memory {A2, B2}; nullptr = single problem
+  int N2, num_n_blocks2;
+  long long ld_out2;
+  const float* alpha_ptr2;
+  float* scatter_dst2[kMaxPeers];
 };
 template <int EPI> struct ParamsFor { using type = GemmParams; };
 template <> struct ParamsFor<EPI_F32_SCATTER> { using type = GemmScatterParams; };
@@ -90,7 +98,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const typename ParamsFor<EPI>::type& p, uint32_t tmem_acc, int row0, int n0, int n_blk,
-                                              int m_slab, int quarter, int half, int lane) {
+                                              int m_slab, int quarter, int half, int lane, int problem = 0) {
   const int row = row0 + quarter * 32 + lane;
   const bool row_ok = row < p.M;
   const int ncol0 = n0 + half * kEpiColsPerWarp;
@@ -98,8 +106,14 @@ __device__ __forceinline__ void epilogue_tile(const typename ParamsFor<EPI>::typ
   const long long row_off = (long long)row * p.ld_out;
   float ssq = 0.f;
   float alpha = p.alpha;
-  if constexpr (EPI == EPI_F32 || EPI == EPI_DGELU || EPI == EPI_F32_SCATTER) {
+  if constexpr (EPI == EPI_F32 || EPI == EPI_DGELU) {
     if (p.alpha_ptr != nullptr) alpha *= __ldg(p.alpha_ptr);
+  }
+  int n_cols = p.N;
+  if constexpr (EPI == EPI_F32_SCATTER) {
+    const float* ap = problem ? p.alpha_ptr2 : p.alpha_ptr;
+    if (ap != nullptr) alpha *= __ldg(ap);
+    if (problem) n_cols = p.N2;
   }
 
   // software prefetch of the saved pre-activation (EPI_DGELU): chunk c+1 is in flight while chunk c is computed
@@ -120,7 +134,7 @@ __device__ __forceinline__ void epilogue_tile(const typename ParamsFor<EPI>::typ
 #pragma unroll 1
   for (int c = 0; c < kEpiChunks; ++c) {
     const int col0 = ncol0 + c * 32;
-    if (col0 >= p.N) break;  // N % 32 == 0 is enforced on the host
+    if (col0 >= n_cols) break;  // N % 32 == 0 is enforced on the host
     uint32_t v[32];
     tmem_ld_32x32(taddr + c * 32, v);
     uint4 aux[4];
@@ -147,15 +161,17 @@ __device__ __forceinline__ void epilogue_tile(const typename ParamsFor<EPI>::typ
         }
       }
       const int slab_row0 = row0 + quarter * 32;
+      const long long ld = problem ? p.ld_out2 : p.ld_out;
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
         const int orow = slab_row0 + r;  // warp-uniform
         if (orow < p.M) {
           const int owner = orow / p.scatter_rows;
-          float* base = p.scatter_dst[0];  // select with constant indices: no local copy of the parameter struct
+          // select with constant indices: no local copy of the parameter struct
+          float* base = problem ? p.scatter_dst2[0] : p.scatter_dst[0];
 #pragma unroll
-          for (int o = 1; o < kMaxPeers; ++o) base = (owner == o) ? p.scatter_dst[o] : base;
-          base[(long long)(orow - owner * p.scatter_rows) * p.ld_out + col0 + lane] = alpha * __uint_as_float(v[r]);
+          for (int o = 1; o < kMaxPeers; ++o) base = (owner == o) ? (problem ? p.scatter_dst2[o] : p.scatter_dst[o]) : base;
+          base[(long long)(orow - owner * p.scatter_rows) * ld + col0 + lane] = alpha * __uint_as_float(v[r]);
         }
       }
     } else if constexpr (EPI == EPI_F32) {
@@ -305,21 +321,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int num_workers = gridDim.x / CTAS;
   const int worker = blockIdx.x / CTAS;
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int tiles0 = p.num_m_blocks * p.num_n_blocks;
+  int tiles_all = tiles0;
+  if constexpr (EPI == EPI_F32_SCATTER) {
+    if (p.maps2 != nullptr) tiles_all += p.num_m_blocks * p.num_n_blocks2;
+  }
+  const int num_tiles = tiles_all;
   const int num_units = num_tiles * p.splits;
   constexpr int kGroupM = 8;  // rasterise m-blocks in groups so that concurrently running tiles share operands in L2
 
-  auto unit_coords = [&](int unit, int& m_blk, int& n_blk, int& kb0, int& kb1) {
-    const int tile = unit % num_tiles;
+  // returns the problem index (always 0 unless this is a grouped EPI_F32_SCATTER launch)
+  auto unit_coords = [&](int unit, int& m_blk, int& n_blk, int& kb0, int& kb1) -> int {
+    int tile = unit % num_tiles;
     const int split = unit / num_tiles;
-    const int group = tile / (kGroupM * p.num_n_blocks);
+    int nnb = p.num_n_blocks;
+    int problem = 0;
+    if constexpr (EPI == EPI_F32_SCATTER) {
+      if (tile >= tiles0) {
+        problem = 1;
+        tile -= tiles0;
+        nnb = p.num_n_blocks2;
+      }
+    }
+    const int group = tile / (kGroupM * nnb);
     const int first_m = group * kGroupM;
     const int gsize = min(kGroupM, p.num_m_blocks - first_m);
-    const int in_group = tile - group * kGroupM * p.num_n_blocks;
+    const int in_group = tile - group * kGroupM * nnb;
     m_blk = first_m + in_group % gsize;
     n_blk = in_group / gsize;
     kb0 = split * p.k_blocks_per_split;
     kb1 = min(p.num_k_blocks, kb0 + p.k_blocks_per_split);
+    return problem;
   };
   // consumer side of the scheduler ring: wait for slot `ss`, read the unit, release the slot (one arrive per warp)
   auto sched_consume = [&](int ss, uint32_t sphase, bool whole_warp) -> int {
@@ -338,6 +370,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int stage = 0, ss = 0;
       uint32_t phase = 0, sphase = 0;
+      if constexpr (EPI == EPI_F32_SCATTER) {
+        // tensor maps in global memory (written by a copy before this launch) need an acquire through the tensormap proxy
+        if (p.maps2 != nullptr) {
+          fence_tensormap_acquire(p.maps2);
+          fence_tensormap_acquire(p.maps2 + 1);
+        }
+      }
       // the claim for the NEXT unit is issued before the current unit's loads, so the atomic's round trip is hidden
       int claimed = worker;
       while (true) {
@@ -359,7 +398,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++ss == kSchedStages) { ss = 0; sphase ^= 1; }
         if (unit < 0) break;
         int m_blk, n_blk, kb0, kb1;
-        unit_coords(unit, m_blk, n_blk, kb0, kb1);
+        const int problem = unit_coords(unit, m_blk, n_blk, kb0, kb1);
+        const CUtensorMap* map_a = &tmap_a;
+        const CUtensorMap* map_b = &tmap_b;
+        if constexpr (EPI == EPI_F32_SCATTER) {
+          if (problem) {
+            map_a = p.maps2;
+            map_b = p.maps2 + 1;
+          }
+        }
         const int a_row0 = m_blk * (kBlockM * CTAS) + cta_rank * kBlockM;
         const int b_row0 = n_blk * kBlockN + cta_rank * kBRows;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -369,23 +416,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes * CTAS);
           const int k0 = kb * kBlockK;
           if constexpr (!A_MN) {
-            if constexpr (CTAS == 1) tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, a_row0);
-            else tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], k0, a_row0);
+            if constexpr (CTAS == 1) tma_load_2d(sa, map_a, &full_bar[stage], k0, a_row0);
+            else tma_load_2d_pair(sa, map_a, &full_bar[stage], k0, a_row0);
           } else {
 #pragma unroll
             for (int j = 0; j < kBlockM / 64; ++j) {
-              if constexpr (CTAS == 1) tma_load_2d(sa + j * (kBlockK * 128), &tmap_a, &full_bar[stage], a_row0 + j * 64, k0);
-              else tma_load_2d_pair(sa + j * (kBlockK * 128), &tmap_a, &full_bar[stage], a_row0 + j * 64, k0);
+              if constexpr (CTAS == 1) tma_load_2d(sa + j * (kBlockK * 128), map_a, &full_bar[stage], a_row0 + j * 64, k0);
+              else tma_load_2d_pair(sa + j * (kBlockK * 128), map_a, &full_bar[stage], a_row0 + j * 64, k0);
             }
           }
           if constexpr (!B_MN) {
-            if constexpr (CTAS == 1) tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, b_row0);
-            else tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], k0, b_row0);
+            if constexpr (CTAS == 1) tma_load_2d(sb, map_b, &full_bar[stage], k0, b_row0);
+            else tma_load_2d_pair(sb, map_b, &full_bar[stage], k0, b_row0);
           } else {
 #pragma unroll
             for (int j = 0; j < kBRows / 64; ++j) {
-              if constexpr (CTAS == 1) tma_load_2d(sb + j * (kBlockK * 128), &tmap_b, &full_bar[stage], b_row0 + j * 64, k0);
-              else tma_load_2d_pair(sb + j * (kBlockK * 128), &tmap_b, &full_bar[stage], b_row0 + j * 64, k0);
+              if constexpr (CTAS == 1) tma_load_2d(sb + j * (kBlockK * 128), map_b, &full_bar[stage], b_row0 + j * 64, k0);
+              else tma_load_2d_pair(sb + j * (kBlockK * 128), map_b, &full_bar[stage], b_row0 + j * 64, k0);
             }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -453,12 +500,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (++ss == kSchedStages) { ss = 0; sphase ^= 1; }
       if (unit < 0) break;
       int m_blk, n_blk, kb0, kb1;
-      unit_coords(unit, m_blk, n_blk, kb0, kb1);
+      const int problem = unit_coords(unit, m_blk, n_blk, kb0, kb1);
       mbar_wait(&acc_full_bar[acc], acc_phase);
       tc_fence_after();
       const int m_slab = m_blk * CTAS + cta_rank;
       if (kb1 > kb0)
-        epilogue_tile<EPI>(p, tmem_base + acc * kBlockN, m_slab * kBlockM, n_blk * kBlockN, n_blk, m_slab, quarter, half, lane);
+        epilogue_tile<EPI>(p, tmem_base + acc * kBlockN, m_slab * kBlockM, n_blk * kBlockN, n_blk, m_slab, quarter, half, lane,
+                           problem);
       tc_fence_before();
       __syncwarp();  // all 32 lanes have drained their TMEM loads; one (release) arrive per warp
       if (lane == 0) {

@@ -117,6 +117,12 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 
 // ---------------------------------------------------------------- TMA
+// A tensor map that lives in GLOBAL memory (not a __grid_constant__ parameter) must be acquired through the tensormap proxy by
+// the thread that is going to issue TMA operations with it.
+__device__ __forceinline__ void fence_tensormap_acquire(const CUtensorMap* m) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(m) : "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
 }

@@ -373,6 +373,82 @@ int launch_dw_gemm(GemmOperand a, GemmOperand b, GemmParams& p, float* const* ds
   return launch_gemm<2, true, true, EPI_F32_SCATTER>(a, b, sp, 1, st, tag);
 }
 
+// Device + pinned-host rings for tensor maps that a kernel reads from global memory (the second problem of a grouped launch).
+// 256 slots: far more than the launches that can be in flight.
+struct MapRing {
+  CUtensorMap* dev = nullptr;
+  CUtensorMap* host = nullptr;
+  std::atomic<unsigned> seq{0};
+  static constexpr unsigned kSlots = 256;
+  bool ok() {
+    if (!dev) {
+      if (cudaMalloc(&dev, sizeof(CUtensorMap) * 2 * kSlots) != cudaSuccess) return false;
+      if (cudaHostAlloc(&host, sizeof(CUtensorMap) * 2 * kSlots, cudaHostAllocDefault) != cudaSuccess) return false;
+    }
+    return true;
+  }
+};
+inline MapRing& map_ring() { static MapRing r; return r; }
+
+// dW1 and dW2 of one step as ONE launch of the scatter GEMM (shared M = weight rows, K = tokens; problem 0 tiles first).
+int launch_dw_pair_scatter(GemmOperand a1, GemmOperand b1, int N1, float* const* dst1, const float* alpha_ptr1,
+                           GemmOperand a2, GemmOperand b2, int N2, float* const* dst2, const float* alpha_ptr2,
+                           int rows, int K, float alpha, int world, cudaStream_t stream) {
+  using S = GemmSmem<2>;
+  if (rows <= 0 || N1 <= 0 || N2 <= 0 || K <= 0) TD_FAIL(TD_ERR_ARG, "grouped weight-gradient GEMM: empty problem");
+  if (N1 % 32 || N2 % 32) TD_FAIL(TD_ERR_UNSUPPORTED, "grouped weight-gradient GEMM: N must be a multiple of 32");
+  if (world < 1 || world > kMaxPeers || rows % world) TD_FAIL(TD_ERR_ARG, "grouped weight-gradient GEMM: bad world size %d", world);
+  CUtensorMap m[4];
+  int rc;
+  if ((rc = make_operand_map(&m[0], a1.ptr, rows, K, a1.ld, true, kBlockM))) return rc;
+  if ((rc = make_operand_map(&m[1], b1.ptr, N1, K, b1.ld, true, kBlockN / 2))) return rc;
+  if ((rc = make_operand_map(&m[2], a2.ptr, rows, K, a2.ld, true, kBlockM))) return rc;
+  if ((rc = make_operand_map(&m[3], b2.ptr, N2, K, b2.ld, true, kBlockN / 2))) return rc;
+  MapRing& ring = map_ring();
+  if (!ring.ok()) TD_FAIL(TD_ERR_DRIVER, "cannot allocate the tensor-map ring");
+  const unsigned slot = ring.seq.fetch_add(1) % MapRing::kSlots;
+  memcpy(ring.host + 2 * slot, &m[2], 2 * sizeof(CUtensorMap));
+  TD_CUDA(cudaMemcpyAsync(ring.dev + 2 * slot, ring.host + 2 * slot, 2 * sizeof(CUtensorMap), cudaMemcpyHostToDevice, stream));
+
+  GemmScatterParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = rows; p.N = N1; p.K = K; p.ld_out = N1; p.alpha = alpha; p.alpha_ptr = alpha_ptr1;
+  p.num_m_blocks = (rows + 2 * kBlockM - 1) / (2 * kBlockM);
+  p.num_n_blocks = (N1 + kBlockN - 1) / kBlockN;
+  p.num_k_blocks = (K + kBlockK - 1) / kBlockK;
+  p.splits = 1; p.k_blocks_per_split = p.num_k_blocks;
+  p.scatter_rows = rows / world;
+  p.maps2 = ring.dev + 2 * slot;
+  p.N2 = N2; p.num_n_blocks2 = (N2 + kBlockN - 1) / kBlockN; p.ld_out2 = N2; p.alpha_ptr2 = alpha_ptr2;
+  for (int o = 0; o < world; ++o) {
+    p.scatter_dst[o] = dst1[o];
+    p.scatter_dst2[o] = dst2[o];
+  }
+  const int workers = device_sm_count() / 2;
+  const long long tiles = (long long)p.num_m_blocks * (p.num_n_blocks + p.num_n_blocks2);
+  const int grid = int(tiles < workers ? tiles : workers) * 2;
+  auto kern = gemm_bf16_kernel<2, true, true, EPI_F32_SCATTER>;
+  TD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  p.sched_counter = next_sched_counter();
+  if (!p.sched_counter) TD_FAIL(TD_ERR_DRIVER, "cannot allocate the tile-scheduler counters");
+  ProfScope prof("gemm_dW12_scatter", 2.0 * double(rows) * double(N1 + N2) * double(K), stream);
+  TD_CUDA(cudaLaunchKernelEx(&cfg, kern, m[0], m[1], p));
+  return TD_OK;
+}
+
 int bwd_from_dh2(const __nv_bfloat16* dh2, const void* x, const void* h0, const void* h1, const void* W2, int64_t M,
                  int32_t Din, int32_t D, float scale, const float* scale_ptr, float* dW1, float* db1, float* dW2,
                  BwdWorkspace& w, int32_t phases, cudaStream_t st, const ScatterDst* sc = nullptr) {
@@ -386,7 +462,7 @@ int bwd_from_dh2(const __nv_bfloat16* dh2, const void* x, const void* h0, const 
                             world ? "gemm_dW2_scatter" : "gemm_dW2");
     if (rc) return rc;
   }
-  if (phases & TD_BWD_PHASE_GELU_W1) {
+  if (phases & (TD_BWD_PHASE_GELU_W1 | TD_BWD_PHASE_GELU_ONLY)) {
     // dh0 = bf16( bf16(scale_ptr * dh2 . W2) * gelu'(h0) ), plus per-slab column sums for db1
     memset(&p, 0, sizeof(p));
     p.M = int(M); p.N = D; p.K = D; p.ld_out = D; p.alpha = 1.f; p.alpha_ptr = scale_ptr;
@@ -396,11 +472,20 @@ int bwd_from_dh2(const __nv_bfloat16* dh2, const void* x, const void* h0, const 
     const int slabs = int((M + 2 * kBlockM - 1) / (2 * kBlockM)) * 2 * 4;  // pair tiles: 2 slabs x 4 warps each
     colsum_finish_kernel<<<dim3((D + 31) / 32, 1), 256, 0, st>>>(w.db1_part, db1, nullptr, nullptr, slabs, D, scale);
     TD_CUDA(cudaGetLastError());
-    // dW1[D, Din] = scale * dh0^T . x   (dh0 already carries the upstream scalar)
-    memset(&p, 0, sizeof(p));
-    p.M = D; p.N = Din; p.K = int(M); p.ld_out = Din; p.alpha = scale; p.out0 = dW1;
-    rc = launch_dw_gemm({w.dh0, D, true}, {x, Din, true}, p, sc ? sc->dW1 : nullptr, world, st,
-                        world ? "gemm_dW1_scatter" : "gemm_dW1");
+    if (phases & TD_BWD_PHASE_GELU_W1) {
+      // dW1[D, Din] = scale * dh0^T . x   (dh0 already carries the upstream scalar)
+      memset(&p, 0, sizeof(p));
+      p.M = D; p.N = Din; p.K = int(M); p.ld_out = Din; p.alpha = scale; p.out0 = dW1;
+      rc = launch_dw_gemm({w.dh0, D, true}, {x, Din, true}, p, sc ? sc->dW1 : nullptr, world, st,
+                          world ? "gemm_dW1_scatter" : "gemm_dW1");
+      if (rc) return rc;
+    }
+  }
+  if (phases & TD_BWD_PHASE_W12_GROUPED) {
+    // both weight gradients in one launch (scatter mode only; dh0 is in the workspace from an earlier GELU phase)
+    if (!world) TD_FAIL(TD_ERR_ARG, "TD_BWD_PHASE_W12_GROUPED needs td_aligner_bwd_dh2_scatter");
+    int rc = launch_dw_pair_scatter({w.dh0, D, true}, {x, Din, true}, Din, sc->dW1, nullptr, {dh2, D, true}, {h1, D, true}, D,
+                                    sc->dW2, scale_ptr, D, int(M), scale, world, st);
     if (rc) return rc;
   }
   return TD_OK;
@@ -533,6 +618,8 @@ int bwd_dh2_impl(const void* dh2, const void* x, const void* h0, const void* h1,
     TD_CUDA(cudaGetLastError());
   }
   if ((phases & TD_BWD_PHASE_GELU_W1) && (!x || !h0 || !W2 || !dW1 || !db1)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (phase 2)");
+  if ((phases & TD_BWD_PHASE_GELU_ONLY) && (!dh2 || !h0 || !W2 || !db1)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (dh0 / db1)");
+  if ((phases & TD_BWD_PHASE_W12_GROUPED) && (!dh2 || !x || !h1 || !dW1 || !dW2)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (grouped dW)");
   return bwd_from_dh2(static_cast<const __nv_bfloat16*>(dh2), x, h0, h1, W2, M, Din, D, grad_scale, grad_scale_ptr, dW1, db1,
                       dW2, w, phases, st, sc);
 }
@@ -556,8 +643,8 @@ int32_t td_aligner_bwd_dh2_scatter(const void* dh2, const void* x, const void* h
     TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2_scatter: world=%d must be 1..%d and divide D=%d", world, kMaxPeers, D);
   ScatterDst sc;
   sc.world = world;
-  const bool need1 = (phases & TD_BWD_PHASE_GELU_W1) != 0;
-  const bool need2 = (phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_W2_ONLY)) != 0;
+  const bool need1 = (phases & (TD_BWD_PHASE_GELU_W1 | TD_BWD_PHASE_W12_GROUPED)) != 0;
+  const bool need2 = (phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_W2_ONLY | TD_BWD_PHASE_W12_GROUPED)) != 0;
   for (int o = 0; o < world; ++o) {
     if ((need1 && (!dW1_dst || !dW1_dst[o])) || (need2 && (!dW2_dst || !dW2_dst[o])))
       TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2_scatter: null destination for rank %d", o);
@@ -734,6 +821,18 @@ int32_t td_gemm_tn_scatter(const void* A, int64_t lda, const void* B, int64_t ld
     if (!dst || !dst[o]) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter: null destination for rank %d", o);
   }
   return launch_dw_gemm({A, lda, true}, {B, ldb, true}, p, dst, world, (cudaStream_t)stream, "gemm_tn_scatter");
+}
+
+int32_t td_gemm_tn_scatter_pair(const void* A1, int64_t lda1, const void* B1, int64_t ldb1, int32_t N1, float* const* dst1,
+                                const void* A2, int64_t lda2, const void* B2, int64_t ldb2, int32_t N2, float* const* dst2,
+                                int64_t M, int64_t K, float alpha, int32_t world, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (M <= 0 || M > 0x7fffffffll || K <= 0 || K > 0x7fffffffll) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter_pair: size out of range");
+  if (world < 1 || world > kMaxPeers || !dst1 || !dst2) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter_pair: bad world / destinations");
+  for (int o = 0; o < world; ++o)
+    if (!dst1[o] || !dst2[o]) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter_pair: null destination for rank %d", o);
+  return launch_dw_pair_scatter({A1, lda1, true}, {B1, ldb1, true}, N1, dst1, nullptr, {A2, lda2, true}, {B2, ldb2, true}, N2, dst2,
+                                nullptr, int(M), int(K), alpha, world, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------ losses

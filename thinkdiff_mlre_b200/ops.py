@@ -213,7 +213,7 @@ class AlignerBackwardFromDh2:
         self._call(L.BWD_SMALL2_ONLY, None, None, None, db2, dg)
 
     def _call_scatter(self, phase, dW1_dst, db1, dW2_dst, world):
-        L.launch_count += 3 if phase == L.BWD_GELU_W1 else 1
+        L.launch_count += {L.BWD_GELU_W1: 3, L.BWD_GELU_ONLY: 2}.get(phase, 1)
         L.check(
             L.lib().td_aligner_bwd_dh2_scatter(L.ptr(self.dh2), L.ptr(self.x), L.ptr(self.h0), L.ptr(self.h1), L.ptr(self.W2),
                                                L.ptr(self.partials), self.M, self.Din, self.D, self.grad_scale,
@@ -228,6 +228,14 @@ class AlignerBackwardFromDh2:
 
     def linear2_only_scatter(self, dW2_dst, world: int):
         self._call_scatter(L.BWD_W2_ONLY, None, None, dW2_dst, world)
+
+    def gelu_only(self, db1, world: int = 1):
+        """dh0 GEMM (+ db1) without the dW1 GEMM; dh0 stays in the workspace for ``grouped_scatter``."""
+        self._call_scatter(L.BWD_GELU_ONLY, None, db1, None, world)
+
+    def grouped_scatter(self, dW1_dst, dW2_dst, world: int):
+        """dW1 and dW2 as ONE grouped GEMM launch, rows stored to their owner ranks."""
+        self._call_scatter(L.BWD_W12_GROUPED, dW1_dst, None, dW2_dst, world)
 
     def linear2_only(self, dW2):
         self._call(L.BWD_W2_ONLY, None, None, dW2, None, None)
