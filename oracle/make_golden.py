@@ -9,6 +9,8 @@ the reference functions exec'd from source by ``oracle.ref_loader``:
   aligner_cfg1_fp32.npz           BASELINE config 1 (4 x 32 x 768 -> 4096, fp32): y rows, loss, sampled grad entries
   collater_{random_split,fixed_max,input_embed}.npz   the reference collater's three branches on ragged batches
   ce_small.npz                    CrossEntropyLoss(ignore_index=-100) expression of ...embed_decoder_2.py:243-246
+  lr_schedule.npz                 the two LR scheduler classes of thinkdiff/common/optims.py at fixed (epoch, step) points
+                                  (``python -m oracle.make_golden lr`` regenerates only this one)
 The bf16 fixtures run the reference module under ``torch.autocast('cpu', dtype=bfloat16)`` -- the CPU analogue of the
 training regime (thinkdiff/tasks/base_task.py:237).
 """
@@ -16,6 +18,7 @@ from __future__ import annotations
 
 import os
 import random
+import sys
 
 import numpy as np
 import torch
@@ -145,8 +148,55 @@ def make_ce(name, R, V, seed):
     print(f"{name}: loss={float(loss):.6f}")
 
 
+LR_CASES = {
+    # the schedule every shipped config uses (configs/*.yaml: lr_sched / init_lr / min_lr / warmup_lr / warmup_steps / ...)
+    "cosine_shipped": ("linear_warmup_cosine_lr", dict(max_epoch=40, iters_per_epoch=5000, min_lr=8e-5, init_lr=1e-4,
+                                                       warmup_start_lr=1e-6, warmup_steps=2000, decay_rate=None)),
+    "cosine_warmup_spans_epochs": ("linear_warmup_cosine_lr", dict(max_epoch=3, iters_per_epoch=10, min_lr=1e-5, init_lr=1e-3,
+                                                                   warmup_start_lr=1e-6, warmup_steps=25, decay_rate=None)),
+    "cosine_no_warmup": ("linear_warmup_cosine_lr", dict(max_epoch=2, iters_per_epoch=7, min_lr=0.0, init_lr=5e-4)),
+    "step_decay": ("linear_warmup_step_lr", dict(max_epoch=6, iters_per_epoch=9, min_lr=2e-5, init_lr=1e-4, decay_rate=0.5,
+                                                  warmup_start_lr=1e-6, warmup_steps=5)),
+}
+
+
+def lr_points(kw):
+    ipe, me = kw["iters_per_epoch"], kw["max_epoch"]
+    steps = sorted({0, 1, 2, ipe // 3, ipe // 2, ipe - 2, ipe - 1} & set(range(ipe)))
+    epochs = sorted({0, 1, 2, me // 2, me - 1} & set(range(me)))
+    pts = [(e, s) for e in epochs for s in steps]
+    ws = kw.get("warmup_steps", 0)
+    for it in (ws - 1, ws, ws + 1):  # around the end of the warm-up
+        if 0 <= it < ipe * me:
+            pts.append((it // ipe, it % ipe))
+    return pts
+
+
+def make_lr_schedule(name="lr_schedule.npz"):
+    """LR values produced by the reference's own scheduler classes (thinkdiff/common/optims.py) at fixed (epoch, step) points."""
+    import types
+
+    classes = ref_loader.load_lr_schedulers()
+    out = {}
+    for case, (sched, kw) in LR_CASES.items():
+        opt = types.SimpleNamespace(param_groups=[{"lr": -1.0}, {"lr": -1.0}])
+        obj = classes[sched](optimizer=opt, **kw)
+        pts, lrs = lr_points(kw), []
+        for e, s in pts:
+            obj.step(cur_epoch=e, cur_step=s)
+            assert opt.param_groups[0]["lr"] == opt.param_groups[1]["lr"]
+            lrs.append(opt.param_groups[0]["lr"])
+        out[case + ".points"] = np.asarray(pts, dtype=np.int64)
+        out[case + ".lr"] = np.asarray(lrs, dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLDEN, name), **out)
+    print(f"{name}: {sum(len(v) for k, v in out.items() if k.endswith('.lr'))} lr values")
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
+    if len(sys.argv) > 1 and sys.argv[1] == "lr":  # only the (later-added) schedule fixture; the others stay as committed
+        os.makedirs(GOLDEN, exist_ok=True)
+        return make_lr_schedule()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.manual_seed(0)
     make_aligner("aligner_small_fp32.npz", 64, 128, (3, 7, 64), 11, autocast=False, full=True)
@@ -170,6 +220,7 @@ def main():
                   dict(use_input_embed=1, use_output_embed=1, random_split_output_embed=1, output_embed_max_split_len=128,
                        output_embed_max_len=64, input_embed_max_len=10), lens, 16, 104)
     make_ce("ce_small.npz", 24, 512, 7)
+    make_lr_schedule()
 
 
 if __name__ == "__main__":

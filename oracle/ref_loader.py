@@ -79,3 +79,30 @@ def load_collater():
         return fn(types.SimpleNamespace(build_info=build_info), samples)
 
     return collater
+
+
+_OPTIMS_FILE = "thinkdiff/common/optims.py"
+
+
+def load_lr_schedulers() -> dict:
+    """The reference's LR schedulers (thinkdiff/common/optims.py:13-112), exec'd from the source where it lies with a stub for
+    the ``registry`` decorator (the only import of that file besides ``math``). Returns {registered name: class}."""
+    import math
+
+    registered = {}
+
+    class _Registry:
+        @staticmethod
+        def register_lr_scheduler(name):
+            def deco(cls):
+                registered[name] = cls
+                return cls
+
+            return deco
+
+    with open(os.path.join(REFERENCE_ROOT, _OPTIMS_FILE)) as f:
+        src = f.read()
+    src = src.replace("from thinkdiff.common.registry import registry", "")
+    ns = {"math": math, "registry": _Registry}
+    exec(compile(src, _OPTIMS_FILE, "exec"), ns)
+    return registered
