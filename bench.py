@@ -1,23 +1,27 @@
 #!/usr/bin/env python
 """Benchmark of the ThinkDiff aligner training step (BASELINE.json metric: aligner train tokens/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]                  # this repo's sm_100a path
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   # N > 1 (NCCL)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg5|cfg4]       # this repo's sm_100a path
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   # N > 1
     python bench.py --impl reference ...                                  # the reference's CPU path (oracle port)
 
-One step = pack (features + T5 targets, ragged -> cu_seqlens) -> aligner forward (bf16 autocast) -> masked MSE ->
-aligner backward (-> gradient all-reduce over NCCL when N > 1) -> AdamW step, on one batch of synthetic Qwen2-VL-7B
-features: BASELINE config 2 per GPU (64 sequences, valid length U{1..256}, 3584 -> 4096); N GPUs = 64 sequences per rank
-(weak scaling; N = 8 is config 3's global batch of 512). A token = one valid (unpadded) row.
+One step (cfg2 / cfg5) = pack (features, ragged -> cu_seqlens) -> aligner forward (bf16 autocast regime) -> masked MSE against T5
+targets -> aligner backward -> gradient exchange between ranks when N > 1 -> AdamW, on one batch of synthetic Qwen2-VL-7B
+features. cfg2: BASELINE config 2 per GPU (64 sequences, valid length U{1..256}, 3584 -> 4096); N GPUs = 64 sequences per rank
+(weak scaling; N = 8 is config 3's global batch of 512). cfg5: BASELINE config 5 per GPU (128 sequences, length U{1..1024}).
+cfg4: BASELINE config 4 per GPU (inference: 32 samples x two images -> 2 x 32 Q-Former tokens -> aligner -> ragged composition with
+T5 text embeddings -> padded prompt). A token = one valid (unpadded) row.
 
-The JSON line: `value` = tokens/s with inputs resident in HBM (CUDA events, max over ranks); `e2e` = the same step fed
-from pinned host buffers through the public API, H2D copies and a D2H read of the loss inside the timed region;
-`roofline` = the dominant kernel (largest share of device time) from per-launch CUDA events in a separate profiled pass
-of the same steps; `cpu_baseline` = the oracle's port of the reference module on this box's host cores.
+The JSON line: `value` = tokens/s with inputs resident in HBM (CUDA events, max over ranks); `e2e` = the same step fed from pinned
+host buffers through the public API, H2D copies and a D2H read of the loss inside the timed region; `roofline` = the dominant
+kernel (largest share of device time) from per-launch CUDA events in a separate profiled pass of the same steps; `cpu_baseline` =
+the oracle's port of the reference module on this box's host cores; `eager_bar` = the reference module itself (eager PyTorch,
+bf16 autocast, cuBLASLt) on this GPU, the same-box bar; `dp_parity` (N > 1) = a numerical check of the multi-GPU path.
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import statistics
@@ -29,19 +33,35 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-DIN, D = 3584, 4096
-SEQS_PER_GPU, MAX_LEN = 64, 256
-FLOP_PER_TOKEN = 4 * DIN * D + 6 * D * D  # fwd 2 GEMMs + bwd 3 GEMMs (no dx), SURVEY.md section 8d
-NUM_BATCHES = 4  # distinct input batches cycled through, so no step re-reads the previous step's inputs from L2
+D = 4096
+WORKLOADS = {
+    # name: (din, sequences per GPU, max valid length, distinct batches cycled)
+    "cfg2": (3584, 64, 256, 4),
+    "cfg5": (3584, 128, 1024, 2),
+    "cfg4": (768, 32, 128, 4),
+}
 METRIC, UNIT = "aligner_train_tokens_per_sec", "tokens/s"
+
+
+def flop_per_token(din):
+    return 4 * din * D + 6 * D * D  # fwd 2 GEMMs + bwd 3 GEMMs (no dx), SURVEY.md section 8d
 
 
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
         p = json.load(open(path))
-        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "sm_max_mhz": p.get("sm_max_mhz"), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+def load_synth():
+    """The synthetic generator, loaded by PATH: importing the package would map libthinkdiff_b200.so, which the CPU arm must not."""
+    spec = importlib.util.spec_from_file_location("td_synth", os.path.join(ROOT, "thinkdiff_mlre_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -95,30 +115,51 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process (and the pinned host buffers it is about to allocate: first touch) to the CPUs NVML reports as local to
+    GPU `index`, so every rank's H2D copies start from its own NUMA node. Returns the number of CPUs kept, or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ----------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_run(steps: int, warmup: int, max_tokens: int = 2048):
+def cpu_reference_run(steps: int, warmup: int, din: int, seqs: int, max_len: int, max_tokens: int = 2048):
     """The reference's CPU path: the oracle's port of build_vision_projector('mlp2x_gelu_t5_norm') (the reference is
     Python/PyTorch; its own modules cannot travel to the GPU box), fp32, all host threads, on a bounded sample of the
-    config-2 batch (the first sequences up to `max_tokens` valid tokens): forward + MSE + backward + AdamW."""
+    workload's batch (the first sequences up to `max_tokens` valid tokens): forward + MSE + backward + AdamW."""
     import torch
 
     from oracle import aligner_ref, pack_ref
-    from thinkdiff_mlre_b200.train_step import make_reference_optimizer, synthetic_lvlm_batch
 
+    synth = load_synth()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    b = synthetic_lvlm_batch(SEQS_PER_GPU, MAX_LEN, DIN, D, seed=1234, pin=False)
-    lens, keep = b.lens.tolist(), 0
+    flat, start, lens_t, target = synth.lvlm_batch_tensors(seqs, max_len, din, D, seed=1234)
+    lens, keep = lens_t.tolist(), 0
     while keep < len(lens) and sum(lens[: keep + 1]) <= max_tokens:
         keep += 1
     keep = max(keep, 1)
-    bits, tbits = b.flat.view(torch.int16).numpy(), b.extras["flat_target"].view(torch.int16).numpy()
-    x, _ = pack_ref.pack_from_flat(bits, b.src_row_start.tolist()[:keep], lens[:keep])      # the collater's job, on the CPU
-    t, _ = pack_ref.pack_from_flat(tbits, b.src_row_start.tolist()[:keep], lens[:keep])
+    bits, tbits = flat.view(torch.int16).numpy(), target.view(torch.int16).numpy()
+    x, _ = pack_ref.pack_from_flat(bits, start.tolist()[:keep], lens[:keep])      # the collater's job, on the CPU
+    t, _ = pack_ref.pack_from_flat(tbits, start.tolist()[:keep], lens[:keep])
     x = torch.from_numpy(x).view(torch.bfloat16).float()
     t = torch.from_numpy(t).view(torch.bfloat16).float()
-    m = aligner_ref.RefAligner(DIN, D)
-    m.load_state_dict(aligner_ref.init_params_numpy(DIN, D, seed=0))
+    m = aligner_ref.RefAligner(din, D)
+    m.load_state_dict(aligner_ref.init_params_numpy(din, D, seed=0))
     opt = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=0.05)
     tokens = x.shape[0]
 
@@ -137,7 +178,7 @@ def cpu_reference_run(steps: int, warmup: int, max_tokens: int = 2048):
         step()
     dt = time.perf_counter() - t0
     return {"value": tokens * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {keep} sequences of the config-2 batch = {tokens} valid tokens, fp32, fwd+MSE+bwd+AdamW, {steps} steps after {warmup} warm-up",
+            "sample": f"first {keep} sequences of the batch = {tokens} valid tokens, fp32, fwd+MSE+bwd+AdamW, {steps} steps after {warmup} warm-up",
             "ms_per_step": dt / steps * 1e3, "tokens_per_step": tokens}
 
 
@@ -145,22 +186,184 @@ def run_reference_arm(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    din, seqs, max_len, _ = WORKLOADS["cfg2" if args.workload == "cfg4" else args.workload]
     steps = min(args.steps, 8)
-    r = cpu_reference_run(steps, min(args.warmup, 2))
+    r = cpu_reference_run(steps, min(args.warmup, 2), din, seqs, max_len)
     line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": steps,
             "warmup": min(args.warmup, 2), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus),
+            "config": workload_config(args.workload, args.gpus),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
-def workload_config(n):
-    return {"workload": "ThinkDiff-LVLM aligner train step (BASELINE config 2 per GPU; N=8 = config 3 global batch 512)",
-            "seqs_per_gpu": SEQS_PER_GPU, "global_batch": SEQS_PER_GPU * n, "max_len": MAX_LEN, "ragged": "len ~ U{1..256}",
-            "din": DIN, "d": D, "loss": "masked_mse", "optimizer": "AdamW wd=0.05", "parallelism": f"dp{n}",
-            "l2_policy": f"{NUM_BATCHES} distinct input batches cycled; per-step working set (~1.3 GB) exceeds the 126 MB L2"}
+def workload_config(name, n):
+    din, seqs, max_len, nb = WORKLOADS[name]
+    what = {"cfg2": "ThinkDiff-LVLM aligner train step (BASELINE config 2 per GPU; N=8 = config 3 global batch 512)",
+            "cfg5": "long-context ThinkDiff-LVLM aligner train step (BASELINE config 5 per GPU: 128 sequences, len <= 1024; N=8 = global batch 1024)",
+            "cfg4": "ThinkDiff-CLIP two-image + text composition, inference (BASELINE config 4 per GPU: 32 samples; N=8 = batch 256)"}[name]
+    cfg = {"workload": what, "name": name, "seqs_per_gpu": seqs, "global_batch": seqs * n, "max_len": max_len, "ragged": f"len ~ U{{1..{max_len}}}",
+           "din": din, "d": D, "parallelism": f"dp{n}",
+           "l2_policy": f"{nb} distinct input batches cycled; the per-step working set exceeds the 126 MB L2"}
+    if name != "cfg4":
+        cfg.update(loss="masked_mse", optimizer="AdamW wd=0.05")
+    return cfg
+
+
+# ----------------------------------------------------------------------------------------------- eager bar (same box)
+def eager_bar(dev, din, seqs, max_len, nb, steps, warmup, rank_seed):
+    """The kernel-level bar on the same GPU: the reference's aligner as the reference runs it -- eager
+    nn.Sequential(Linear, GELU, Linear, T5LayerNorm) under bf16 autocast on the ZERO-PADDED [B, L_max, Din] batch
+    (thinkdiff/models/mllama_vllm_t5_embed_decoder_2.py:58-63, :585; collater padding ...mllama_embed_2.py:124-127), masked MSE
+    on the valid rows, backward(), torch fused AdamW (runners/runner_base.py:122-127): cuBLASLt GEMMs + unfused ATen kernels, no
+    kernel of this repo. Also with the packed rows as input (same module, no pad rows). Same batches, same token accounting."""
+    import torch
+    from torch import nn
+
+    synth = load_synth()
+    try:
+        from transformers.models.t5.modeling_t5 import T5LayerNorm as Norm
+    except Exception:
+        class Norm(nn.Module):  # transformers' T5LayerNorm.forward, restated
+            def __init__(self, d, eps=1e-6):
+                super().__init__()
+                self.weight, self.variance_epsilon = nn.Parameter(torch.ones(d)), eps
+
+            def forward(self, h):
+                var = h.to(torch.float32).pow(2).mean(-1, keepdim=True)
+                h = h * torch.rsqrt(var + self.variance_epsilon)
+                if self.weight.dtype in (torch.float16, torch.bfloat16):
+                    h = h.to(self.weight.dtype)
+                return self.weight * h
+
+    out = {}
+    for layout in ("padded", "packed"):
+        torch.manual_seed(0)
+        model = nn.Sequential(nn.Linear(din, D), nn.GELU(), nn.Linear(D, D), Norm(D)).to(dev)
+        decay = [p for n, p in model.named_parameters() if p.ndim >= 2]
+        no_decay = [p for n, p in model.named_parameters() if p.ndim < 2]
+        opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.05}, {"params": no_decay, "weight_decay": 0.0}], lr=1e-4, fused=True)
+        batches = []
+        for j in range(nb):
+            flat, start, lens_t, target = synth.lvlm_batch_tensors(seqs, max_len, din, D, seed=rank_seed + 1000 * j)
+            lens, l_max = lens_t.tolist(), int(lens_t.max())
+            x = torch.zeros((seqs, l_max, din), dtype=torch.bfloat16)
+            t = torch.zeros((seqs, l_max, D), dtype=torch.bfloat16)
+            mask = torch.zeros((seqs, l_max), dtype=torch.bool)
+            for i, (s, n) in enumerate(zip(start.tolist(), lens)):  # the reference collater's pad / stack / mask
+                x[i, :n], t[i, :n], mask[i, :n] = flat[s : s + n], target[s : s + n], True
+            if layout == "packed":
+                batches.append((x[mask].to(dev), t[mask].to(dev), None, int(lens_t.sum())))
+            else:
+                batches.append((x.to(dev), t.to(dev), mask.to(dev), int(lens_t.sum())))
+
+        def step(x, t, mask, _):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = model(x)
+            if mask is None:
+                loss = torch.nn.functional.mse_loss(y.float(), t.float())
+            else:
+                loss = torch.nn.functional.mse_loss(y[mask].float(), t[mask].float())
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return loss
+
+        for i in range(max(warmup, 3)):
+            step(*batches[i % nb])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tokens = 0
+        e0.record()
+        for i in range(steps):
+            step(*batches[i % nb])
+            tokens += batches[i % nb][3]
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        out[layout] = {"value": tokens / (ms * 1e-3), "ms_per_step": ms / steps}
+        del model, opt, batches
+        torch.cuda.empty_cache()
+    return {"value": out["padded"]["value"], "unit": UNIT, "ms_per_step": out["padded"]["ms_per_step"], "steps": steps,
+            "what": "reference nn.Sequential aligner, eager PyTorch under bf16 autocast on the zero-padded batch + masked MSE + backward + torch fused AdamW (cuBLASLt + ATen), same GPU, same batches",
+            "packed_rows_variant": {"value": out["packed"]["value"], "ms_per_step": out["packed"]["ms_per_step"],
+                                    "what": "same module fed the packed valid rows (no pad rows computed)"}}
+
+
+# ----------------------------------------------------------------------------------------------- multi-GPU parity
+def dp_parity_check(td, dist, dev, world, rank, mode):
+    """Numerical check of the multi-GPU path bench.py times, on small dims, outside the timed region:
+    (a) the sharded / peer pipelined run == the plain all-reduce + replicated FusedAdamW run after K steps (<= 1e-6),
+    (b) the exchanged gradient of one step == the mean over ranks of the per-rank gradients of an eager fp32-master / bf16-autocast
+        PyTorch aligner on each rank's own shard (DDP's mean of per-rank means, runner_base.py:90-92; <= 2e-2),
+    (c) every replica holds bit-identical parameters."""
+    import torch
+    from torch import nn
+
+    din, d, seqs, max_len, steps = 192, 512, 4, 50, 4
+    torch.manual_seed(11)
+    ref_sd = None
+
+    def run(kind):
+        nonlocal ref_sd
+        torch.manual_seed(11)
+        m = td.ThinkDiffAligner(din, d).to(dev)
+        if ref_sd is None:
+            ref_sd = {k: v.clone() for k, v in m.state_dict().items()}
+        m.load_state_dict(ref_sd)
+        if kind == "plain":
+            m.enable_data_parallel(defer_wait=True)
+        else:
+            m.enable_data_parallel(defer_wait=True, sharded=True, peer=kind == "peer")
+        step = td.AlignerTrainStep(m, td.FusedAdamW(m, lr=1e-3), pipelined=True)
+        for j in range(steps):
+            b = td.synthetic_lvlm_batch(seqs, max_len, din, d, seed=100 * j + rank, pin=False)
+            step.step_device(b.flat.to(dev), b.src_row_start.to(dev), b.lens.to(dev), b.total_rows, b.l_max, b.extras["flat_target"].to(dev))
+        step.flush()
+        torch.cuda.synchronize()
+        return [p.detach().clone() for p in m.parameters()], m
+
+    plain, _ = run("plain")
+    tested, _ = run(mode)
+    max_rel = 0.0
+    for a, b in zip(plain, tested):
+        max_rel = max(max_rel, float((a - b).abs().max() / (a.abs().max() + 1e-30)))
+    # (c) replicas identical
+    replicas_equal = True
+    for p in tested:
+        ref = p.clone()
+        dist.broadcast(ref, src=0)
+        replicas_equal = replicas_equal and bool(torch.equal(ref, p))
+    flag = torch.tensor([1.0 if replicas_equal else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    replicas_equal = bool(flag.item() == 1.0)
+    # (b) one step's exchanged gradient vs the eager PyTorch reference module, mean over ranks
+    m = td.ThinkDiffAligner(din, d).to(dev)
+    m.load_state_dict(ref_sd)
+    m.enable_data_parallel()
+    b = td.synthetic_lvlm_batch(seqs, max_len, din, d, seed=7 + rank, pin=False)
+    cu = td.ops.cu_seqlens(b.lens.to(dev))
+    x, idx = td.ops.pack_varlen(b.flat.to(dev), b.src_row_start.to(dev), cu, b.total_rows, want_index=True)
+    tgt = b.extras["flat_target"].to(dev)
+    m.mse_loss_backward_packed(x, tgt, idx)
+    torch.cuda.synchronize()
+    ours = [p.grad.detach().float().clone() for p in m.parameters()]
+    eager = nn.Sequential(nn.Linear(din, d), nn.GELU(), nn.Linear(d, d), type(m[3])(d, 1e-6)).to(dev)
+    eager.load_state_dict(ref_sd)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = eager(x)
+    torch.nn.functional.mse_loss(y.float(), tgt[idx].float()).backward()
+    grad_rel = 0.0
+    for g, p in zip(ours, eager.parameters()):
+        r = p.grad.detach().float().clone()
+        dist.all_reduce(r)
+        r /= world
+        grad_rel = max(grad_rel, float((g - r).norm() / (r.norm() + 1e-30)))
+    res = {"ok": bool(max_rel <= 1e-6 and grad_rel <= 2e-2 and replicas_equal), "mode": mode, "max_rel_vs_allreduce_adamw": max_rel,
+           "grad_rel_vs_eager_mean_of_ranks": grad_rel, "replicas_equal": replicas_equal, "steps": steps, "dims": [din, d]}
+    del m, eager
+    return res
 
 
 # ----------------------------------------------------------------------------------------------- B200 arm
@@ -170,17 +373,23 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-eager-bar", action="store_true")
+    ap.add_argument("--no-dp-parity", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after backward instead of overlapped")
     ap.add_argument("--no-pipeline", action="store_true", help="apply every parameter update inside its own step, on the compute stream")
-    ap.add_argument("--peer", action="store_true", help="N > 1, EXPERIMENTAL: gradient exchange over NVLink peer memory from the GEMM epilogues, no NCCL kernels on the step (thinkdiff_mlre_b200/peer.py)")
-    ap.add_argument("--no-shard", action="store_true", help="N > 1: all-reduce + replicated AdamW instead of reduce-scatter + row-sharded AdamW + all-gather")
+    ap.add_argument("--dp", default="auto", choices=["auto", "peer", "sharded", "allreduce"],
+                    help="N > 1 gradient exchange: peer = reduce-scatter fused into the weight-gradient GEMM epilogues over NVLink peer memory "
+                         "(no collective kernels on the step); sharded = NCCL reduce-scatter + row-sharded AdamW + all-gather; allreduce = NCCL "
+                         "bucketed all-reduce + replicated AdamW. auto = peer")
     ap.add_argument("--profile-out", default="", help="write the per-kernel table (JSON) here")
+    ap.add_argument("--timeline-out", default="", help="write a per-stream device timeline of a few steady-state steps (JSON) here")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: this repo's one-pass AdamW (+ bf16 copies, per-bucket overlap); torch: torch.optim.AdamW(fused=True)")
     ap.add_argument("--loss-path", default="fused", choices=["fused", "module"],
-                    help="fused: aligner.mse_loss_packed (y/dy stay on chip); module: forward() -> masked MSE -> backward()")
+                    help="fused: fused norm + MSE + norm backward (y/dy stay on chip); module: forward() -> masked MSE -> backward()")
     args = ap.parse_args()
     # stdout carries exactly ONE line (the JSON); anything a library prints there meanwhile (e.g. NCCL's version
     # banner) is diverted to stderr
@@ -196,6 +405,11 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args, emit)
 
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = bind_to_gpu_numa_node(local)  # before any pinned allocation
+
     import torch
     import torch.distributed as dist
 
@@ -203,9 +417,6 @@ def main():
     from thinkdiff_mlre_b200 import _lib as L
     from thinkdiff_mlre_b200.train_step import make_reference_optimizer
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != max(args.gpus, 1) and rank == 0:
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch N>1 with torch.distributed.run", file=sys.stderr)
     torch.cuda.set_device(local)
@@ -215,20 +426,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
     steps = args.steps
-
-    torch.manual_seed(0)  # identical init on every rank (DDP broadcasts rank 0's; same seed is equivalent)
-    aligner = td.ThinkDiffAligner(DIN, D).to(dev)
-    if world > 1:
-        sharded = args.optimizer == "fused" and args.loss_path == "fused" and not args.no_pipeline and not args.no_shard and D % world == 0
-        aligner.enable_data_parallel(overlap=not args.no_overlap, defer_wait=args.optimizer == "fused", sharded=sharded,
-                                     peer=bool(args.peer and sharded))
-    opt = td.FusedAdamW(aligner, lr=1e-4, weight_decay=0.05) if args.optimizer == "fused" else make_reference_optimizer(aligner)
-    pipelined = args.optimizer == "fused" and args.loss_path == "fused" and not args.no_pipeline
-    stepper = td.AlignerTrainStep(aligner, opt, fused_loss=args.loss_path == "fused", pipelined=pipelined)
-
-    host = [td.synthetic_lvlm_batch(SEQS_PER_GPU, MAX_LEN, DIN, D, seed=1234 + rank + 1000 * j) for j in range(NUM_BATCHES)]
-    resident = [(b.flat.to(dev), b.src_row_start.to(dev), b.lens.to(dev), b.total_rows, b.l_max, b.extras["flat_target"].to(dev)) for b in host]
-    tokens_per_step = [b.total_rows for b in host]
+    din, seqs, max_len, num_batches = WORKLOADS[args.workload]
+    peaks = measured_peaks()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -250,9 +449,30 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t)
 
+    if args.workload == "cfg4":
+        return run_cfg4(args, emit, td, L, dev, world, rank, local, sync_all, max_over_ranks, sum_over_ranks, peaks)
+
+    torch.manual_seed(0)  # identical init on every rank (DDP broadcasts rank 0's; same seed is equivalent)
+    aligner = td.ThinkDiffAligner(din, D).to(dev)
+    fused = args.optimizer == "fused" and args.loss_path == "fused"
+    pipelined = fused and not args.no_pipeline
+    dp_mode = None
+    if world > 1:
+        dp_mode = "peer" if args.dp == "auto" else args.dp
+        if not (pipelined and D % world == 0) and dp_mode in ("peer", "sharded"):
+            dp_mode = "allreduce"
+        aligner.enable_data_parallel(overlap=not args.no_overlap, defer_wait=args.optimizer == "fused", sharded=dp_mode in ("sharded", "peer"),
+                                     peer=dp_mode == "peer")
+    opt = td.FusedAdamW(aligner, lr=1e-4, weight_decay=0.05) if args.optimizer == "fused" else make_reference_optimizer(aligner)
+    stepper = td.AlignerTrainStep(aligner, opt, fused_loss=args.loss_path == "fused", pipelined=pipelined)
+
+    host = [td.synthetic_lvlm_batch(seqs, max_len, din, D, seed=1234 + rank + 1000 * j) for j in range(num_batches)]
+    resident = [(b.flat.to(dev), b.src_row_start.to(dev), b.lens.to(dev), b.total_rows, b.l_max, b.extras["flat_target"].to(dev)) for b in host]
+    tokens_per_step = [b.total_rows for b in host]
+
     # ---- device-resident timing ------------------------------------------------------------------
     for i in range(warmup):
-        stepper.step_device(*resident[i % NUM_BATCHES])
+        stepper.step_device(*resident[i % num_batches])
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = L.launch_count
@@ -261,54 +481,48 @@ def main():
         e0.record()
         t_host0 = time.perf_counter()
         for i in range(steps):
-            loss = stepper.step_device(*resident[i % NUM_BATCHES])
+            loss = stepper.step_device(*resident[i % num_batches])
         host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / steps  # CPU time to enqueue one step (no sync inside)
-        stepper.flush()  # pipelined mode: the last step's updates are part of the timed work
+        # pipelined mode: the last step's parameter updates (AdamW + exchange of the bf16 rows) are part of the timed work; the
+        # all-gather of the other ranks' fp32 MASTER rows, which only a checkpoint needs, is done after the timed region
+        stepper.flush(sync_masters=False)
         e1.record()
         sync_all()
+    stepper.flush()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = L.launch_count - launches0
-    tokens = sum_over_ranks(float(sum(tokens_per_step[i % NUM_BATCHES] for i in range(steps))))
+    tokens = sum_over_ranks(float(sum(tokens_per_step[i % num_batches] for i in range(steps))))
     value = tokens / (ms * 1e-3)
     final_loss = float(loss)
 
     # ---- end to end: pinned host buffers -> H2D -> step -> D2H loss, every step ---------------------
     e2e = None
     if not args.no_e2e:
+        # what the collater ships: only the kept rows of every sample (FlatCollater(truncate_on_host=True), the reference
+        # collater's [:split_point] done in the DataLoader worker) -- the device pack then re-packs contiguous rows
+        host_t = [td.synthetic_lvlm_batch(seqs, max_len, din, D, seed=1234 + rank + 1000 * j, truncated=True) for j in range(num_batches)]
         for i in range(3):
-            float(stepper.step_host(host[i % NUM_BATCHES], dev))
+            float(stepper.step_host(host_t[i % num_batches], dev))
         sync_all()
         e0.record()
-        nxt = stepper.prefetch(host[0], dev)  # inside the timed region: every step's H2D is paid for
+        nxt = stepper.prefetch(host_t[0], dev)  # inside the timed region: every step's H2D is paid for
         for i in range(steps):
             cur = nxt
             if i + 1 < steps:
-                nxt = stepper.prefetch(host[(i + 1) % NUM_BATCHES], dev)  # copy of step i+1 overlaps compute of step i
+                nxt = stepper.prefetch(host_t[(i + 1) % num_batches], dev)  # copy of step i+1 overlaps compute of step i
             loss_host = float(stepper.step_prefetched(cur))  # .item(): D2H read of the loss, as base_task.py:262
-        stepper.flush()
+        stepper.flush(sync_masters=False)
         e1.record()
         sync_all()
+        stepper.flush()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-        b0 = host[0]
+        tokens_e2e = sum_over_ranks(float(sum(host_t[i % num_batches].total_rows for i in range(steps))))
+        b0 = host_t[0]
         h2d = b0.flat.nbytes + b0.extras["flat_target"].nbytes + b0.src_row_start.nbytes + b0.lens.nbytes
-        if os.environ.get("TD_E2E_AB"):  # developer A/B: the same loop with 1 / 2 / 4 copy streams
-            for k in (1, 2, 4):
-                stepper.copy_streams = k
-                sync_all()
-                e0.record()
-                nxt = stepper.prefetch(host[0], dev)
-                for i in range(steps):
-                    cur = nxt
-                    if i + 1 < steps:
-                        nxt = stepper.prefetch(host[(i + 1) % NUM_BATCHES], dev)
-                    float(stepper.step_prefetched(cur))
-                stepper.flush()
-                e1.record()
-                sync_all()
-                print(f"e2e A/B: {k} copy stream(s) {e0.elapsed_time(e1) / steps:.3f} ms/step (default run {ms_e2e / steps:.3f})", file=sys.stderr)
-            stepper.copy_streams = 2
-        e2e = {"value": tokens / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-               "ms_per_step": ms_e2e / steps, "note": "every step: H2D of its flat bf16 features + T5 targets from pinned memory (row chunks on two copy streams, overlapping the previous step's compute) and loss.item()"}
+        e2e = {"value": tokens_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_e2e / steps, "h2d_gbs_per_rank": h2d / (ms_e2e / steps * 1e-3) / 1e9, "numa_bound_cpus": numa_cpus,
+               "note": "every step: H2D of the kept rows of its bf16 features + T5 targets from pinned memory (row chunks on two copy streams, overlapping the previous step's compute) and loss.item()"}
+        del host_t
 
     if os.environ.get("TD_HOST_PROFILE") and rank == 0:  # developer aid: where does the host time of a step go?
         import cProfile, io, pstats
@@ -316,7 +530,7 @@ def main():
         pr = cProfile.Profile()
         pr.enable()
         for i in range(100):
-            stepper.step_device(*resident[i % NUM_BATCHES])
+            stepper.step_device(*resident[i % num_batches])
         pr.disable()
         stepper.flush()
         buf = io.StringIO()
@@ -324,8 +538,31 @@ def main():
         print(buf.getvalue()[:5000], file=sys.stderr)
     elif os.environ.get("TD_HOST_PROFILE"):
         for i in range(100):
-            stepper.step_device(*resident[i % NUM_BATCHES])
+            stepper.step_device(*resident[i % num_batches])
         stepper.flush()
+
+    # ---- per-stream device timeline of steady-state steps (same pipelined step the timed region ran) ----------
+    if args.timeline_out:
+        for i in range(2):
+            stepper.step_device(*resident[i % num_batches])
+        L.profile_enable(True)
+        for i in range(4):
+            stepper.step_device(*resident[(i + 2) % num_batches])
+        stepper.flush(sync_masters=False)
+        sync_all()
+        recs = L.profile_timeline()
+        L.profile_enable(False)
+        stepper.flush()
+        streams = sorted({r[1] for r in recs})
+        tl = {"rank": rank, "n_gpus": world, "dp": dp_mode, "steps": 4, "unit": "ms since the first recorded launch",
+              "streams": {s: i for i, s in enumerate(streams)},
+              "launches": [{"tag": r[0], "stream": streams.index(r[1]), "t0": r[2], "t1": r[3]} for r in recs],
+              "note": "CUDA events around every launch of this library; events of different streams share the device clock. Gaps on the compute stream are waits (for a parameter update / a peer flag / a collective) or launch gaps."}
+        path = args.timeline_out.replace("%r", str(rank))
+        if rank == 0 or "%r" in args.timeline_out:
+            os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+            with open(path, "w") as f:
+                json.dump(tl, f)
 
     # ---- per-kernel device times (separate pass of the same steps; CUDA events around every launch) --
     psteps = min(steps, 20)
@@ -337,22 +574,27 @@ def main():
         prof_stepper = td.AlignerTrainStep(aligner, opt, fused_loss=True, pipelined=False)
         profile_pass = "sequential step: same kernels, same inputs, single stream (the timed region overlaps AdamW with the GEMMs)"
         for i in range(2):
-            prof_stepper.step_device(*resident[i % NUM_BATCHES])
+            prof_stepper.step_device(*resident[i % num_batches])
     L.profile_enable(True)
     for i in range(psteps):
-        prof_stepper.step_device(*resident[i % NUM_BATCHES])
+        prof_stepper.step_device(*resident[i % num_batches])
     prof_stepper.flush()
     torch.cuda.synchronize()
     prof = L.profile_report()
     L.profile_enable(False)
-    peaks = measured_peaks()
+    clk = clocks.summary()
+    at_max_clock = bool(clk.get("sm_mhz") and clk.get("sm_max_mhz") and clk["sm_mhz"] >= 0.97 * clk["sm_max_mhz"])
+    # a kernel timed while the SM clock holds its maximum is compared with the burst cuBLAS figure; under the power cap
+    # (seconds-long runs) the sustained figure is the comparable one. Both fractions are reported.
+    tc_peak = peaks["bf16_tflops"] if at_max_clock else peaks["bf16_tflops_sustained"]
     kernels = {}
     for tag, r in prof.items():
         per_launch_ms = r["ms"] / r["launches"]
         rate = r["work"] / (r["ms"] * 1e-3)
         if tag.startswith("gemm_"):
             kernels[tag] = {"launches_per_step": r["launches"] / psteps, "ms_per_launch": per_launch_ms, "bound": "tensor",
-                            "achieved": rate / 1e12, "unit": "TFLOP/s", "frac": rate / 1e12 / peaks["bf16_tflops_sustained"]}
+                            "achieved": rate / 1e12, "unit": "TFLOP/s", "frac": rate / 1e12 / tc_peak,
+                            "frac_burst": rate / 1e12 / peaks["bf16_tflops"], "frac_sustained": rate / 1e12 / peaks["bf16_tflops_sustained"]}
         else:
             kernels[tag] = {"launches_per_step": r["launches"] / psteps, "ms_per_launch": per_launch_ms, "bound": "hbm",
                             "achieved": rate / 1e9, "unit": "GB/s", "frac": rate / 1e9 / peaks["hbm_gbs"]}
@@ -362,54 +604,121 @@ def main():
     dom = max(kernels, key=lambda k: kernels[k]["share_of_kernel_time"])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from the committed ncu capture
-    if os.path.isfile(tpath):
+    if os.path.isfile(tpath) and args.workload == "cfg2":
         traffic = json.load(open(tpath)).get(dom)
     roofline = {"kernel": dom, "bound": kernels[dom]["bound"], "achieved": kernels[dom]["achieved"],
-                "peak": peaks["bf16_tflops_sustained"] if kernels[dom]["bound"] == "tensor" else peaks["hbm_gbs"],
+                "peak": tc_peak if kernels[dom]["bound"] == "tensor" else peaks["hbm_gbs"],
                 "unit": kernels[dom]["unit"], "frac": kernels[dom]["frac"], "traffic": traffic,
-                "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}); sustained bf16 figure: kernel timed inside a long step",
+                "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}): " + ("burst bf16 figure, the sampled SM clock held its maximum" if at_max_clock else "sustained bf16 figure, the SM clock sagged under the power cap"),
+                "frac_burst": kernels[dom].get("frac_burst"), "frac_sustained": kernels[dom].get("frac_sustained"),
                 "ms_per_launch": kernels[dom]["ms_per_launch"], "share_of_kernel_time": kernels[dom]["share_of_kernel_time"],
                 "profile_pass": profile_pass}
 
-    # the gradient all-reduce on its own (both buckets back to back, nothing else running): what overlap has to hide
-    ar_alone = None
-    if world > 1:
-        from thinkdiff_mlre_b200.aligner import GradBuckets
+    # ---- N > 1: numerical check of the path that was timed, outside the timed region -------------
+    dp_parity = None
+    if world > 1 and not args.no_dp_parity and dp_mode in ("peer", "sharded"):
+        dp_parity = dp_parity_check(td, dist, dev, world, rank, dp_mode)
 
-        gb = GradBuckets(DIN, D, dev)
-        gb.linear2.zero_(), gb.linear1.zero_()
-        for _ in range(3):
-            dist.all_reduce(gb.linear2), dist.all_reduce(gb.linear1)
-        sync_all()
-        e0.record()
-        for _ in range(10):
-            dist.all_reduce(gb.linear2), dist.all_reduce(gb.linear1)
-        e1.record()
-        sync_all()
-        ar_alone = max_over_ranks(e0.elapsed_time(e1)) / 10
-
-    cpu = None
+    cpu = bar = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(5, 2)
+        r = cpu_reference_run(5, 2, din, seqs, max_len)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0 and world == 1 and not args.no_eager_bar:
+        del resident
+        torch.cuda.empty_cache()
+        bar = eager_bar(dev, din, seqs, max_len, num_batches, min(steps, 20), 3, 1234 + rank)
+        bar["speedup_of_this_repo"] = value / bar["value"]
 
+    ok = True
     if rank == 0:
-        step_tflops = value / world * FLOP_PER_TOKEN / 1e12
+        step_tflops = value / world * flop_per_token(din) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": dict(workload_config(world), loss_path=args.loss_path, optimizer_impl=args.optimizer, pipelined_updates=pipelined, sharded_optimizer=bool(world > 1 and aligner._dp.sharded), peer_exchange=bool(world > 1 and aligner._dp.peer)), "clocks": clocks.summary(), "e2e": e2e,
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_peak": step_tflops / peaks["bf16_tflops_sustained"],
+            "data": "synthetic", "config": dict(workload_config(args.workload, world), loss_path=args.loss_path, optimizer_impl=args.optimizer, pipelined_updates=pipelined,
+                                                 dp_exchange=dp_mode, fp32_master_sync="after the timed region (bf16 compute copies and AdamW are inside it)" if dp_mode in ("peer", "sharded") else None),
+            "clocks": clk, "e2e": e2e,
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "eager_bar": bar, "dp_parity": dp_parity,
+            "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_peak": step_tflops / tc_peak,
+            "step_frac_of_bf16_burst": step_tflops / peaks["bf16_tflops"], "step_frac_of_bf16_sustained": step_tflops / peaks["bf16_tflops_sustained"],
             "step_frac_of_nominal_2250": step_tflops / 2250.0, "tokens_per_step": tokens / steps, "final_loss": final_loss,
-            "host_enqueue_ms_per_step": host_enqueue_ms, "allreduce_alone_ms": ar_alone, "kernels": kernels,
+            "host_enqueue_ms_per_step": host_enqueue_ms, "kernels": kernels,
         }
         if args.profile_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
             with open(args.profile_out, "w") as f:
                 json.dump({"kernels": kernels, "kernel_ms_per_step": total_ms, "ms_per_step": ms / steps, "peaks": peaks}, f, indent=1)
         emit(line)
+        ok = dp_parity is None or dp_parity["ok"]
     if world > 1:
+        dist.destroy_process_group()
+    if not ok:
+        print("bench.py: dp_parity FAILED", dp_parity, file=sys.stderr)
+        sys.exit(3)
+
+
+def run_cfg4(args, emit, td, L, dev, world, rank, local, sync_all, max_over_ranks, sum_over_ranks, peaks):
+    """BASELINE config 4 per GPU: inference. Two images per sample -> 2 x 32 Q-Former tokens [768] -> aligner (pure-bf16 regime,
+    scripts/test/test_blip_vision_t5_decoder_flux_text.py:104) -> ragged [img1 | img2 | text_i] composition with T5 text embeddings
+    (:184-208) -> zero-padded prompt_embeds + int64 mask. Tokens = packed rows (64 + T_i per sample)."""
+    import torch
+
+    din, seqs, max_len, nb = WORKLOADS["cfg4"]
+    steps, warmup = args.steps, max(args.warmup, 3)
+    torch.manual_seed(0)
+    aligner = td.ThinkDiffAligner(din, D).to(dev).to(torch.bfloat16).eval()
+    batches = []
+    for j in range(nb):
+        g = torch.Generator().manual_seed(4321 + rank + 1000 * j)
+        q = torch.randn((seqs, 64, din), generator=g).to(torch.bfloat16)
+        tl = torch.randint(1, max_len + 1, (seqs,), generator=g).tolist()
+        text = torch.randn((sum(tl), D), generator=g).to(torch.bfloat16)
+        batches.append((q.to(dev), text.to(dev), tl, seqs * 64 + sum(tl)))
+
+    def step(q, text, tl, _):
+        with torch.no_grad():
+            y = aligner(q)                                  # [B, 64, 4096] bf16
+            packed = td.compose_image_text(y, text, tl)     # ragged [64 + T_i] rows
+            return packed.to_padded()                       # [B, L_max, 4096] + int64 mask
+
+    for i in range(warmup):
+        step(*batches[i % nb])
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = L.launch_count
+    clocks = ClockSampler(local)
+    with clocks:
+        e0.record()
+        for i in range(steps):
+            step(*batches[i % nb])
+        e1.record()
+        sync_all()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    tokens = sum_over_ranks(float(sum(batches[i % nb][3] for i in range(steps))))
+    L.profile_enable(True)
+    for i in range(min(steps, 20)):
+        step(*batches[i % nb])
+    torch.cuda.synchronize()
+    prof = L.profile_report()
+    L.profile_enable(False)
+    kernels = {}
+    for tag, r in prof.items():
+        rate = r["work"] / (r["ms"] * 1e-3)
+        tensor = tag.startswith("gemm_")
+        kernels[tag] = {"launches_per_step": r["launches"] / min(steps, 20), "ms_per_launch": r["ms"] / r["launches"], "bound": "tensor" if tensor else "hbm",
+                        "achieved": rate / (1e12 if tensor else 1e9), "unit": "TFLOP/s" if tensor else "GB/s",
+                        "frac": rate / (1e12 * peaks["bf16_tflops"] if tensor else 1e9 * peaks["hbm_gbs"])}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches_per_step"])
+    if rank == 0:
+        emit({"metric": "aligner_compose_tokens_per_sec", "value": tokens / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+              "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+              "config": workload_config("cfg4", world), "clocks": clocks.summary(), "e2e": None, "gpu_launches": L.launch_count - launches0,
+              "roofline": {"kernel": dom, "bound": kernels[dom]["bound"], "achieved": kernels[dom]["achieved"], "unit": kernels[dom]["unit"],
+                           "peak": peaks["bf16_tflops"] if kernels[dom]["bound"] == "tensor" else peaks["hbm_gbs"], "frac": kernels[dom]["frac"], "traffic": None},
+              "cpu_baseline": None, "kernels": kernels, "tokens_per_step": tokens / steps})
+    if world > 1:
+        import torch.distributed as dist
+
         dist.destroy_process_group()
 
 

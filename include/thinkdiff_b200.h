@@ -29,9 +29,12 @@ enum { TD_OK_ = 0, TD_ERR_ARG_ = -1, TD_ERR_UNSUPPORTED_ = -2, TD_ERR_DRIVER_ = 
 enum { TD_BWD_PHASE_NORM_W2 = 1, TD_BWD_PHASE_GELU_W1 = 2, TD_BWD_PHASE_ALL = 3,
        /* td_aligner_bwd_dh2 only: the two halves of NORM_W2, so the small vectors' all-reduce can start before the dW2 GEMM */
        TD_BWD_PHASE_SMALL2_ONLY = 4, TD_BWD_PHASE_W2_ONLY = 8,
-       /* td_aligner_bwd_dh2_scatter only: the dh0 GEMM + db1 without dW1, and dW1 + dW2 as ONE grouped GEMM launch (480 tiles
-        * instead of 224 + 256: the un-split launches would leave the last wave of CTA pairs mostly idle) */
-       TD_BWD_PHASE_GELU_ONLY = 16, TD_BWD_PHASE_W12_GROUPED = 32 };
+       /* the dh0 GEMM + db1 without the dW1 GEMM */
+       TD_BWD_PHASE_GELU_ONLY = 16 };
+/* td_aligner_mse_fwd stages (bit mask) */
+enum { TD_FWD_STAGE_LINEAR1 = 1, TD_FWD_STAGE_REST = 2, TD_FWD_STAGE_ALL = 3,
+       /* leave the loss un-finished: td_aligner_bwd_dh2(loss_out = ...) sums the per-CTA partials in its own finisher launch */
+       TD_FWD_STAGE_DEFER_LOSS = 4 };
 
 const char* td_last_error(void);
 int32_t td_version(void);
@@ -43,6 +46,8 @@ int32_t td_device_check(void);
  * work = algorithmic FLOPs for gemm_* tags and algorithmic bytes for the row kernels. Enabling clears old records. */
 int32_t td_profile_enable(int32_t on);
 int32_t td_profile_report(char* buf /*[host]*/, int32_t buflen);
+/* One "tag,stream,start_ms,end_ms\n" line per recorded launch, relative to the first record: a per-stream device timeline. */
+int32_t td_profile_timeline(char* buf /*[host]*/, int32_t buflen);
 
 /* ---- (1) ragged pack / pad / mask ------------------------------------------------------------------------
  * Replaces the collater's pad/stack/mask loop, thinkdiff/datasets/datasets/llava_instruct_dataset_mllama_embed_2.py
@@ -94,18 +99,24 @@ int32_t td_aligner_bwd(const void* dy, int32_t dy_dtype, const void* x, const vo
  * (grad_scale_ptr: optional DEVICE scalar = the upstream gradient of the loss, e.g. GradScaler's scale; no host sync).
  * Same gradients as td_aligner_fwd -> td_masked_mse_fwd_bwd -> td_aligner_bwd (base_task.py:237-244 with an MSE loss).
  * `stages` lets the caller run Linear1 and the rest as two calls (same buffers), e.g. to apply the Linear2 parameter update
- * of the previous step in between while that bucket's all-reduce was still in flight. */
+ * of the previous step in between while that bucket's all-reduce was still in flight.
+ * td_aligner_bwd_dh2 extras: loss_out (optional) finishes a loss deferred with TD_FWD_STAGE_DEFER_LOSS; stats (optional, fp32
+ * [2], zeroed by the caller once per optimizer step) counts non-finite gradient values in stats[0] -- GradScaler's inf check,
+ * thinkdiff/tasks/base_task.py:241-258; accumulate != 0 adds into the gradient buffers instead of overwriting them
+ * (accum_grad_iters > 1, base_task.py:247). Launch order inside one call: dh0 GEMM, ONE finisher launch (db1 | dg, db2 | loss),
+ * dW1 GEMM, dW2 GEMM. */
 int64_t td_aligner_mse_fwd_workspace_bytes(int64_t M, int32_t Din, int32_t D);
 int64_t td_aligner_norm_partials_bytes(int64_t M, int32_t D);
 int32_t td_aligner_mse_fwd(const void* x, int64_t M, int32_t Din, int32_t D, const void* W1, const void* b1, const void* W2,
                            const void* b2, const float* g, float eps, const void* target, int32_t target_dtype,
                            const int64_t* target_row_index, void* h0, void* h1, void* dh2, void* norm_partials, float* loss,
                            void* workspace, int64_t workspace_bytes,
-                           int32_t stages /* 1 = Linear1+GELU, 2 = the rest, 3 = all */, td_stream_t stream);
+                           int32_t stages /* TD_FWD_STAGE_* */, td_stream_t stream);
 int32_t td_aligner_bwd_dh2(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
                            const void* norm_partials, int64_t M, int32_t Din, int32_t D, float grad_scale,
                            const float* grad_scale_ptr, float* dW1, float* db1, float* dW2, float* db2, float* dg,
-                           void* workspace, int64_t workspace_bytes, int32_t phases, td_stream_t stream);
+                           float* loss_out, float* stats, int32_t accumulate, void* workspace, int64_t workspace_bytes,
+                           int32_t phases, td_stream_t stream);
 
 /* Standalone T5LayerNorm forward / backward (transformers modeling_t5.py T5LayerNorm, imported at
  * ...embed_decoder_2.py:24). x bf16 [M, D]; y fp32 or bf16; dW/db are fp32 [D]; db = column sums of dx (may be NULL). */
@@ -116,26 +127,47 @@ int32_t td_rmsnorm_bwd(const void* dy, int32_t dy_dtype, const void* x, const fl
                        int32_t D, void* dx_bf16, float* dg, float* dxsum, void* workspace, int64_t workspace_bytes,
                        td_stream_t stream);
 
+/* Workspace of one GEMM launch for its stream-K tail (the output tiles left over after the last full wave of CTA pairs are
+ * cut along K; partial accumulators meet here). The td_aligner_* workspaces include it; the two entries below take it as an
+ * optional argument (NULL: the leftover tiles run as a last, partially filled wave). */
+int64_t td_gemm_workspace_bytes(void);
 /* Plain bf16 linear  out[M, N] = x[M, K] . W[N, K]^T (+ bias)  -- nn.Linear under autocast (F.linear). */
 int32_t td_linear_bf16(const void* x, int64_t M, int32_t K, const void* W, int32_t N, const void* bias, void* out,
-                       td_stream_t stream);
-/* Generic entry to the tcgen05 GEMM for tests: D[M,N] (fp32) = alpha * A.B^T with either operand K-major
- * ([rows, K]) or MN-major ([K, rows]); cta_pair selects cta_group::2; splits = 0 lets the library choose. */
+                       void* workspace, int64_t workspace_bytes, td_stream_t stream);
+/* Generic entry to the tcgen05 GEMM for tests: D[M,N] (fp32) (+)= alpha * A.B^T with either operand K-major
+ * ([rows, K]) or MN-major ([K, rows]); cta_pair selects cta_group::2; accumulate != 0 adds into D. */
 int32_t td_gemm_bf16_f32out(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb,
                             int32_t b_mn_major, int64_t M, int32_t N, int64_t K, float alpha, float* out,
-                            int32_t cta_pair, int32_t splits, td_stream_t stream);
+                            int32_t cta_pair, int32_t accumulate, void* workspace, int64_t workspace_bytes,
+                            td_stream_t stream);
 
 /* ---- optimizer: torch.optim.AdamW semantics (thinkdiff/runners/runner_base.py:122-127), one pass
  * that reads the (all-reduced) gradient, updates p / exp_avg / exp_avg_sq in place and writes the bf16 compute copy of p.
  * Arrays below are HOST arrays of `num_tensors` (1..3) entries holding device pointers / sizes; params_bf16 (or its
- * entries) may be NULL. `step` counts from 1; gradients are multiplied by grad_scale (1 / loss scale) first. */
+ * entries) may be NULL. `step` counts from 1; gradients are multiplied by grad_scale (1 / loss scale) first.
+ * step_ctl (optional, DEVICE, td_step_ctl_bytes): the device-resident control block of the step -- when given, the bias
+ * corrections, the unscale / clip factor and the skip decision are read from it (no host sync), `step` is ignored. */
 int32_t td_adamw_step(int32_t num_tensors, float* const* params /*[host]*/, const float* const* grads /*[host]*/,
                       float* const* exp_avg /*[host]*/, float* const* exp_avg_sq /*[host]*/,
                       void* const* params_bf16 /*[host]*/, const int64_t* numel /*[host]*/,
                       const float* weight_decay /*[host]*/, float lr, float beta1, float beta2, float eps, int64_t step,
-                      float grad_scale, td_stream_t stream);
+                      float grad_scale, const void* step_ctl, td_stream_t stream);
+/* Device-side GradScaler + step bookkeeping (torch.amp.GradScaler as installed at thinkdiff/runners/runner_base.py:131-139 and
+ * driven at thinkdiff/tasks/base_task.py:241-258, plus clip_grad_norm_): the control block holds {skip, gradient multiplier,
+ * bias corrections, applied-step count, loss scale, growth tracker, gradient norm}. td_step_ctl_update folds the step's
+ * statistics (stats[0] = non-finite count, stats[1] = sum of squares of the scaled gradients, both summed over ranks by the
+ * caller) into it: non-finite -> skip + scale *= backoff; else step += 1, new bias corrections, clip coefficient
+ * min(1, max_grad_norm / (norm + 1e-6)) when max_grad_norm > 0, and scale *= growth every growth_interval clean steps.
+ * The loss scale for the next backward is the float at byte offset TD_STEP_CTL_SCALE_OFFSET (pass it as grad_scale_ptr). */
+enum { TD_STEP_CTL_SCALE_OFFSET = 20 };
+int64_t td_step_ctl_bytes(void);
+int32_t td_step_ctl_init(void* step_ctl, float init_scale, int64_t applied_steps, td_stream_t stream);
+int32_t td_step_ctl_update(void* step_ctl, const float* stats, int32_t use_scaler, float growth_factor, float backoff_factor,
+                           int32_t growth_interval, float beta1, float beta2, float max_grad_norm, td_stream_t stream);
+/* stats[0] += number of non-finite values, stats[1] += sum of squares of grad[0..numel) (what unscale_ + clip_grad_norm_ read). */
+int32_t td_grad_stats(const float* grad, int64_t numel, float* stats, td_stream_t stream);
 
-/* ---- (e) data parallel over NVLink peer memory (EXPERIMENTAL in round 1: compiled, not yet validated on hardware) --------
+/* ---- (e) data parallel over NVLink peer memory ----------------------------------------------------------------------------
  * Replaces DDP's NCCL all-reduce of the aligner gradients + the replicated optimizer step
  * (thinkdiff/runners/runner_base.py:88-92, :98-127; thinkdiff/tasks/base_task.py:247-258) with a reduce-scatter fused into
  * the weight-gradient GEMM epilogues: rank o owns rows [o D/world, (o+1) D/world) of W1 and W2; every rank's GEMM stores
@@ -161,24 +193,20 @@ int32_t td_sum_slots(const float* slots, int64_t slot_stride, int32_t n_slots, f
 int32_t td_adamw_slots_step(float* param, const float* grad_slots, int64_t slot_stride, int32_t n_slots, float* exp_avg,
                             float* exp_avg_sq, void* const* params_bf16 /*[host]*/, int32_t n_dst, int64_t numel,
                             float weight_decay, float lr, float beta1, float beta2, float eps, int64_t step,
-                            float grad_scale, td_stream_t stream);
+                            float grad_scale, const void* step_ctl, td_stream_t stream);
 /* td_aligner_bwd_dh2 with the two weight gradients row-scattered: dW?_dst[o] = [D / world, cols] fp32 block for the rows
- * rank o owns. The weight-gradient GEMMs run un-split (bit-reproducible) with coalesced 128-byte stores. */
+ * rank o owns. Every output element is stored exactly once (bit-reproducible) with coalesced 128-byte stores. */
 int32_t td_aligner_bwd_dh2_scatter(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
                                    const void* norm_partials, int64_t M, int32_t Din, int32_t D, float grad_scale,
                                    const float* grad_scale_ptr, float* const* dW1_dst /*[host]*/, float* db1,
-                                   float* const* dW2_dst /*[host]*/, float* db2, float* dg, int32_t world, void* workspace,
-                                   int64_t workspace_bytes, int32_t phases, td_stream_t stream);
+                                   float* const* dW2_dst /*[host]*/, float* db2, float* dg, float* loss_out, float* stats,
+                                   int32_t world, void* workspace, int64_t workspace_bytes, int32_t phases,
+                                   td_stream_t stream);
 /* Test entry for the scatter epilogue: out[M, N] = alpha * A^T.B with A [K, M], B [K, N] (both MN-major, the weight-gradient
  * shape), rows [o M/world, (o+1) M/world) written to dst[o] ([M / world, N] fp32). */
 int32_t td_gemm_tn_scatter(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int32_t N, int64_t K,
-                           float alpha, float* const* dst /*[host]*/, int32_t world, td_stream_t stream);
-
-/* Test entry for the grouped launch: both products above in one kernel (shared M and K; problem 1's tensor maps are read from
- * device memory). */
-int32_t td_gemm_tn_scatter_pair(const void* A1, int64_t lda1, const void* B1, int64_t ldb1, int32_t N1, float* const* dst1 /*[host]*/,
-                                const void* A2, int64_t lda2, const void* B2, int64_t ldb2, int32_t N2, float* const* dst2 /*[host]*/,
-                                int64_t M, int64_t K, float alpha, int32_t world, td_stream_t stream);
+                           float alpha, float* const* dst /*[host]*/, int32_t world, void* workspace, int64_t workspace_bytes,
+                           td_stream_t stream);
 
 /* ---- (3) masked losses, forward + gradient in one pass -----------------------------------------------------
  * Cross entropy replaces `CrossEntropyLoss(ignore_index=-100)(lm_logits.view(-1, V), labels.view(-1))`

@@ -20,9 +20,10 @@ def _arr(tensors):
     return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
+@pytest.mark.parametrize("stream_k", [False, True])
 @pytest.mark.parametrize("world", [1, 2, 8])
 @pytest.mark.parametrize("shape", [(512, 192, 300), (512, 512, 1000), (4096, 4096, 2048)])
-def test_scatter_gemm_matches_unsplit_gemm_bit_exactly(world, shape):
+def test_scatter_gemm_matches_local_gemm_bit_exactly(world, shape, stream_k):
     from thinkdiff_mlre_b200 import _lib as L
     from thinkdiff_mlre_b200 import ops
 
@@ -30,33 +31,13 @@ def test_scatter_gemm_matches_unsplit_gemm_bit_exactly(world, shape):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = torch.randn((K, M), generator=g, device="cuda").to(torch.bfloat16)  # MN-major operands: [K, rows]
     B = torch.randn((K, N), generator=g, device="cuda").to(torch.bfloat16)
-    want = ops.gemm_f32out(A, B, True, True, alpha=0.5, cta_pair=True, splits=1)
+    want = ops.gemm_f32out(A, B, True, True, alpha=0.5, cta_pair=True, stream_k=stream_k)
     parts = [torch.full((M // world, N), float("nan"), device="cuda") for _ in range(world)]
-    L.check(L.lib().td_gemm_tn_scatter(L.ptr(A), M, L.ptr(B), N, M, N, K, 0.5, _arr(parts), world, L.stream_ptr()), "td_gemm_tn_scatter")
+    ws, ws_bytes = ops.gemm_workspace(A.device, stream_k)
+    L.check(L.lib().td_gemm_tn_scatter(L.ptr(A), M, L.ptr(B), N, M, N, K, 0.5, _arr(parts), world, L.ptr(ws), ws_bytes, L.stream_ptr()),
+            "td_gemm_tn_scatter")
     torch.cuda.synchronize()
-    assert torch.equal(torch.cat(parts), want)
-
-
-@pytest.mark.parametrize("world", [1, 8])
-def test_grouped_scatter_pair_matches_two_unsplit_gemms_bit_exactly(world):
-    from thinkdiff_mlre_b200 import _lib as L
-    from thinkdiff_mlre_b200 import ops
-
-    M, N1, N2, K = 4096, 3584, 4096, 1500  # the two weight gradients of the headline config, short token dimension
-    g = torch.Generator(device="cuda").manual_seed(5)
-    A1 = torch.randn((K, M), generator=g, device="cuda").to(torch.bfloat16)
-    B1 = torch.randn((K, N1), generator=g, device="cuda").to(torch.bfloat16)
-    A2 = torch.randn((K, M), generator=g, device="cuda").to(torch.bfloat16)
-    B2 = torch.randn((K, N2), generator=g, device="cuda").to(torch.bfloat16)
-    want1 = ops.gemm_f32out(A1, B1, True, True, alpha=0.25, cta_pair=True, splits=1)
-    want2 = ops.gemm_f32out(A2, B2, True, True, alpha=0.25, cta_pair=True, splits=1)
-    d1 = [torch.full((M // world, N1), float("nan"), device="cuda") for _ in range(world)]
-    d2 = [torch.full((M // world, N2), float("nan"), device="cuda") for _ in range(world)]
-    L.check(L.lib().td_gemm_tn_scatter_pair(L.ptr(A1), M, L.ptr(B1), N1, N1, _arr(d1), L.ptr(A2), M, L.ptr(B2), N2, N2, _arr(d2), M, K,
-                                            0.25, world, L.stream_ptr()), "td_gemm_tn_scatter_pair")
-    torch.cuda.synchronize()
-    assert torch.equal(torch.cat(d1), want1)
-    assert torch.equal(torch.cat(d2), want2)
+    assert torch.equal(torch.cat(parts), want)  # same schedule, same accumulation order: same bits as the local-output GEMM
 
 
 def test_flags_post_sum_and_adamw_slots_loopback():
@@ -91,10 +72,10 @@ def test_flags_post_sum_and_adamw_slots_loopback():
     ref_bf16 = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
     for step in (1, 2):
         L.check(L.lib().td_adamw_slots_step(L.ptr(pa), L.ptr(slots), n, world, L.ptr(ma), L.ptr(va), _arr(dst), 3, n, 0.05, 1e-3, 0.9,
-                                            0.999, 1e-8, step, 0.5, L.stream_ptr()), "td_adamw_slots_step")
+                                            0.999, 1e-8, step, 0.5, None, L.stream_ptr()), "td_adamw_slots_step")
         one = lambda t: (C.c_void_p * 1)(t.data_ptr())  # noqa: E731
         L.check(L.lib().td_adamw_step(1, one(pb), one(want), one(mb), one(vb), one(ref_bf16), (C.c_int64 * 1)(n), (C.c_float * 1)(0.05),
-                                      1e-3, 0.9, 0.999, 1e-8, step, 0.5, L.stream_ptr()), "td_adamw_step")
+                                      1e-3, 0.9, 0.999, 1e-8, step, 0.5, None, L.stream_ptr()), "td_adamw_step")
     torch.cuda.synchronize()
     assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb)
     for t in dst:
@@ -149,10 +130,8 @@ def _run(world, mode):
     return {r: (params, losses) for r, params, losses in res}
 
 
-@pytest.mark.parametrize("grouped", ["0", "1"])
-def test_peer_training_world1_equals_plain_pipeline(grouped, monkeypatch):
+def test_peer_training_world1_equals_plain_pipeline():
     """Degenerate single-rank case: every kernel of the peer path runs (scatter epilogue, flags, slot AdamW), no IPC."""
-    monkeypatch.setenv("TD_PEER_GROUPED", grouped)  # inherited by the spawned worker
     plain, peer = _run(1, "plain"), _run(1, "peer")
     for a, b in zip(plain[0][0], peer[0][0]):
         np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-8)

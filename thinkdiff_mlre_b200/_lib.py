@@ -12,7 +12,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("THINKDIFF_B200_LIB", os.path.join(_HERE, "libthinkdiff_b200.so"))  # override: A/B builds
 
 F32, BF16 = 0, 1
-BWD_NORM_W2, BWD_GELU_W1, BWD_ALL, BWD_SMALL2_ONLY, BWD_W2_ONLY, BWD_GELU_ONLY, BWD_W12_GROUPED = 1, 2, 3, 4, 8, 16, 32
+BWD_NORM_W2, BWD_GELU_W1, BWD_ALL, BWD_SMALL2_ONLY, BWD_W2_ONLY, BWD_GELU_ONLY = 1, 2, 3, 4, 8, 16
+FWD_LINEAR1, FWD_REST, FWD_ALL, FWD_DEFER_LOSS = 1, 2, 3, 4
+STEP_CTL_SCALE_OFFSET = 20
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -23,6 +25,7 @@ SIGNATURES = {
     "td_device_check": (_i32, []),
     "td_profile_enable": (_i32, [_i32]),
     "td_profile_report": (_i32, [C.c_char_p, _i32]),
+    "td_profile_timeline": (_i32, [C.c_char_p, _i32]),
     "td_cu_seqlens": (_i32, [_vp, _i32, _vp, _vp]),
     "td_pack_varlen": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp]),
     "td_pack_varlen_indexed": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp]),
@@ -35,13 +38,18 @@ SIGNATURES = {
     "td_aligner_mse_fwd_workspace_bytes": (_i64, [_i64, _i32, _i32]),
     "td_aligner_norm_partials_bytes": (_i64, [_i64, _i32]),
     "td_aligner_mse_fwd": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
-    "td_aligner_bwd_dh2": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "td_aligner_bwd_dh2": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _vp]),
     "td_rmsnorm_fwd": (_i32, [_vp, _vp, _f32, _i64, _i32, _vp, _i32, _vp, _vp]),
     "td_rmsnorm_bwd_workspace_bytes": (_i64, [_i64, _i32]),
     "td_rmsnorm_bwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
-    "td_linear_bf16": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
-    "td_gemm_bf16_f32out": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i32, _i64, _f32, _vp, _i32, _i32, _vp]),
-    "td_adamw_step": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_f32), _f32, _f32, _f32, _f32, _i64, _f32, _vp]),
+    "td_gemm_workspace_bytes": (_i64, []),
+    "td_linear_bf16": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "td_gemm_bf16_f32out": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i32, _i64, _f32, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "td_adamw_step": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_f32), _f32, _f32, _f32, _f32, _i64, _f32, _vp, _vp]),
+    "td_step_ctl_bytes": (_i64, []),
+    "td_step_ctl_init": (_i32, [_vp, _f32, _i64, _vp]),
+    "td_step_ctl_update": (_i32, [_vp, _vp, _i32, _f32, _f32, _i32, _f32, _f32, _f32, _vp]),
+    "td_grad_stats": (_i32, [_vp, _i64, _vp, _vp]),
     "td_peer_alloc": (_i32, [_i64, C.POINTER(_vp), C.c_char_p]),
     "td_peer_free": (_i32, [_vp]),
     "td_peer_open": (_i32, [C.c_char_p, C.POINTER(_vp)]),
@@ -50,10 +58,9 @@ SIGNATURES = {
     "td_peer_wait": (_i32, [_vp, _i32, _i32, _f32, _vp]),
     "td_peer_post": (_i32, [_vp, _vp, _i32, _i64, _vp]),
     "td_sum_slots": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp]),
-    "td_adamw_slots_step": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _f32, _vp]),
-    "td_aligner_bwd_dh2_scatter": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _vp]),
-    "td_gemm_tn_scatter": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _i64, _f32, _vp, _i32, _vp]),
-    "td_gemm_tn_scatter_pair": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _i64, _f32, _i32, _vp]),
+    "td_adamw_slots_step": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _f32, _vp, _vp]),
+    "td_aligner_bwd_dh2_scatter": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _vp]),
+    "td_gemm_tn_scatter": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _i64, _f32, _vp, _i32, _vp, _i64, _vp]),
     "td_loss_workspace_bytes": (_i64, [_i64]),
     "td_masked_mse_fwd_bwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _i64, _vp]),
     "td_masked_ce_fwd_bwd": (_i32, [_vp, _i32, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _i64, _vp]),
@@ -125,6 +132,17 @@ def dtype_code(t) -> int:
 
 def profile_enable(on: bool) -> None:
     check(lib().td_profile_enable(int(on)), "td_profile_enable")
+
+
+def profile_timeline() -> list:
+    """[(tag, stream, start_ms, end_ms)] for every launch recorded since profile_enable(True), relative to the first one."""
+    buf = C.create_string_buffer(1 << 20)
+    check(lib().td_profile_timeline(buf, len(buf)), "td_profile_timeline")
+    out = []
+    for line in buf.value.decode().splitlines():
+        tag, stream, t0, t1 = line.split(",")
+        out.append((tag, stream, float(t0), float(t1)))
+    return out
 
 
 def profile_report() -> dict:

@@ -60,9 +60,11 @@ class DataParallelState:
     remaining backward GEMMs run on the compute stream.
     """
 
-    def __init__(self, group=None, overlap: bool = True, defer_wait: bool = False, sharded: bool = False, peer: bool = False):
+    def __init__(self, group=None, overlap: bool = True, defer_wait: bool = False, sharded: bool = False, peer: bool = False,
+                 peer_timeout_s: float = 600.0):
         import torch.distributed as dist
 
+        self.peer_timeout_s = float(peer_timeout_s)  # a rank that stalls longer than this (checkpointing, validation) traps the others
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group)
@@ -162,42 +164,26 @@ class _AlignerFn(torch.autograd.Function):
         bwd = ops.AlignerBackward(x2d, (h0, h1, h2, rstd), W2b, gf, dy.contiguous(), grad_scale=scale)
         gb = GradBuckets(Din, D, dev, small_separate=dp is not None and dp.sharded and dp.world > 1)
         module._grad_flats = gb.flats()
-        _reduce_and_return(module, gb, lambda: bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg), lambda: bwd.gelu_and_linear1(gb.dW1, gb.db1))
+        phase2 = lambda: bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg)  # noqa: E731
+        phase1 = lambda: bwd.gelu_and_linear1(gb.dW1, gb.db1)  # noqa: E731
+        if dp is not None and dp.sharded and dp.world > 1:
+            _sharded_schedule(module, gb, [("linear1", phase1), ("linear2", phase2)] if module._bwd_order == "linear1_first"
+                              else [("linear2", phase2), ("linear1", phase1)])
+        else:
+            _bucket_schedule(module, gb, phase2, phase1)
         return (None, *gb.in_parameter_order(), None, None)
 
 
-def _reduce_and_return(module, gb, run_phase1, run_phase2, split2=None):
-    """Shared backward schedule: phase 1 (Linear2 / norm gradients) -> start its all-reduce -> phase 2 (Linear1
-    gradients, overlapping the first all-reduce) -> all-reduce the second bucket -> stream-level waits (or, with
-    ``defer_wait``, leave the waits to the consumer of each bucket)."""
+def _bucket_schedule(module, gb, run_linear2, run_linear1):
+    """Backward schedule with two flat buckets: first phase -> start its all-reduce -> second phase (overlapping the first
+    all-reduce) -> all-reduce the second bucket -> stream-level waits (or, with ``defer_wait``, leave the waits to the consumer
+    of each bucket). ``module._bwd_order`` picks which bucket goes first: "linear2_first" is the gradient-ready order of a
+    plain backward, "linear1_first" is used by the pipelined train step, where the Linear2 bucket is the one whose update can
+    be deferred furthest into the next step (W2 is first read by GEMM2)."""
     dp = module._dp
-    # (name, bucket, launcher) in execution order; "linear1_first" is used by the pipelined train step, where the
-    # Linear2 bucket is the one whose update can be deferred furthest into the next step (W2 is first read by GEMM2)
-    order = [("linear2", gb.linear2, run_phase1), ("linear1", gb.linear1, run_phase2)]
+    order = [("linear2", gb.linear2, run_linear2), ("linear1", gb.linear1, run_linear1)]
     if module._bwd_order == "linear1_first":
         order.reverse()
-    if dp is not None and dp.world > 1 and dp.sharded:
-        # fresh view objects: a collective's Work handle keeps a reference to its tensors, and autograd only adopts a
-        # returned gradient as .grad (instead of cloning it) while nobody else references that tensor object
-        big = {"linear2": gb.linear2.view(gb.dW2.shape), "linear1": gb.linear1.view(gb.dW1.shape)}
-        module.wait_grads()
-        works = {}
-        if split2 is not None and order[0][0] == "linear1":
-            # Linear1 first, then the small vectors, then dW2: the 48 KB all-reduce of [db2 | dg | db1] is queued BEFORE the
-            # dW2 GEMM exists, so the next step's first GEMM (which needs b1) never waits for the last reduce-scatter
-            order[0][2]()
-            works["linear1.big"] = dp.reduce_scatter_rows_async(big["linear1"])
-            split2[0]()
-            works["small"] = dp.all_reduce_async(gb.small[:])
-            split2[1]()
-            works["linear2.big"] = dp.reduce_scatter_rows_async(big["linear2"])
-        else:
-            for name, _, launch in order:  # each matrix's reduce-scatter starts as soon as its GEMM is enqueued
-                launch()
-                works[name + ".big"] = dp.reduce_scatter_rows_async(big[name])
-            works["small"] = dp.all_reduce_async(gb.small[:])  # [db2 | dg | db1], 48 KB
-        module._pending = works
-        return
     works = {}
     order[0][2]()
     if module._record_phase_events:  # lets a side stream start on this bucket while the other phase still runs
@@ -221,6 +207,53 @@ def _reduce_and_return(module, gb, run_phase1, run_phase2, split2=None):
                 w.wait()  # the compute stream orders after the NCCL stream; the host does not block
 
 
+def _sharded_schedule(module, gb, phases, small_after_first: bool = False):
+    """Sharded (ZeRO-1 style) data parallel: each weight-gradient matrix is reduce-scattered as soon as its GEMM is enqueued;
+    the three small vectors share one 48 KB all-reduce -- queued right after the first phase when that phase already produced
+    them (``small_after_first``: the next step's first GEMM needs b1 and must never wait for the last reduce-scatter)."""
+    dp = module._dp
+    # fresh view objects: a collective's Work handle keeps a reference to its tensors, and autograd only adopts a
+    # returned gradient as .grad (instead of cloning it) while nobody else references that tensor object
+    big = {"linear2": gb.linear2.view(gb.dW2.shape), "linear1": gb.linear1.view(gb.dW1.shape)}
+    module.wait_grads()
+    works = {}
+    for i, (name, launch) in enumerate(phases):
+        launch()
+        works[name + ".big"] = dp.reduce_scatter_rows_async(big[name])
+        if i == 0 and small_after_first:
+            works["small"] = dp.all_reduce_async(gb.small[:])
+    if "small" not in works:
+        works["small"] = dp.all_reduce_async(gb.small[:])  # [db2 | dg | db1], 48 KB
+    module._pending = works
+
+
+def _mse_backward(module, bwd, din: int, d: int, device):
+    """Backward of the fused MSE path from an ``ops.AlignerBackwardFromDh2``: runs the phases in the module's schedule, starts the
+    gradient exchange, and returns the five gradients in parameter order (None for matrices that only exist in peer memory)."""
+    dp = module._dp
+    if dp is not None and dp.peer:
+        return _peer_backward(module, bwd, d, device)
+    sharded = dp is not None and dp.sharded and dp.world > 1
+    gb = GradBuckets(din, d, device, small_separate=sharded)
+    module._grad_flats = gb.flats()
+    if module._bwd_order == "linear1_first":
+        # Linear1 first: dh0 GEMM, ONE finisher for all three small vectors (+ the deferred loss), dW1 GEMM; then the dW2 GEMM
+        first = lambda: bwd.gelu_linear1_and_small(gb.dW1, gb.db1, gb.db2, gb.dg)  # noqa: E731
+        second = lambda: bwd.linear2_only(gb.dW2)  # noqa: E731
+        if sharded:
+            _sharded_schedule(module, gb, [("linear1", first), ("linear2", second)], small_after_first=True)
+        else:
+            _bucket_schedule(module, gb, second, first)
+    else:
+        phase2 = lambda: bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg)  # noqa: E731
+        phase1 = lambda: bwd.gelu_and_linear1(gb.dW1, gb.db1)  # noqa: E731
+        if sharded:
+            _sharded_schedule(module, gb, [("linear2", phase2), ("linear1", phase1)])
+        else:
+            _bucket_schedule(module, gb, phase2, phase1)
+    return gb.in_parameter_order()
+
+
 class _AlignerMSEFn(torch.autograd.Function):
     """loss = mean((aligner(x) - target)^2) with y / dy never materialised (td_aligner_mse_fwd / td_aligner_bwd_dh2)."""
 
@@ -241,13 +274,7 @@ class _AlignerMSEFn(torch.autograd.Function):
         dp = module._dp
         scale = 1.0 / dp.world if dp is not None else 1.0
         bwd = ops.AlignerBackwardFromDh2(x2d, (h0, h1, dh2, partials), W2b, grad_loss, grad_scale=scale)
-        if dp is not None and dp.peer:
-            return (None, None, *_peer_backward(module, bwd, W2b.shape[0], x2d.device), None, None)
-        gb = GradBuckets(x2d.shape[1], W2b.shape[0], x2d.device, small_separate=dp is not None and dp.sharded and dp.world > 1)
-        module._grad_flats = gb.flats()
-        _reduce_and_return(module, gb, lambda: bwd.norm_and_linear2(gb.dW2, gb.db2, gb.dg), lambda: bwd.gelu_and_linear1(gb.dW1, gb.db1),
-                           split2=(lambda: bwd.norm_small(gb.db2, gb.dg), lambda: bwd.linear2_only(gb.dW2)))
-        return (None, None, *gb.in_parameter_order(), None, None)
+        return (None, None, *_mse_backward(module, bwd, x2d.shape[1], W2b.shape[0], x2d.device), None, None)
 
 
 def _peer_backward(module, bwd, d: int, device):
@@ -262,23 +289,12 @@ def _peer_backward(module, bwd, d: int, device):
     small = torch.empty(3 * d, dtype=torch.float32, device=device)  # [db2 | dg | db1], GradBuckets' small layout
     db2, dg, db1 = small[:d], small[d : 2 * d], small[2 * d :]
     module._grad_flats = {"small": small}
-    if module._peer_grouped:
-        # one grouped launch for both weight gradients (480 tiles over 74 CTA pairs instead of 224 and 256 on their own)
-        bwd.gelu_only(db1, px.world)
-        bwd.norm_small(db2, dg)
-        px.post_small(small)
-        px.signal(ROW_SMALL, e)
-        bwd.grouped_scatter(px.dw_dst(1), px.dw_dst(2), px.world)
-        px.signal(ROW_GRAD1, e)
-        px.signal(ROW_GRAD2, e)
-    else:
-        bwd.gelu_and_linear1_scatter(px.dw_dst(1), db1, px.world)
-        px.signal(ROW_GRAD1, e)
-        bwd.norm_small(db2, dg)
-        px.post_small(small)
-        px.signal(ROW_SMALL, e)
-        bwd.linear2_only_scatter(px.dw_dst(2), px.world)
-        px.signal(ROW_GRAD2, e)
+    bwd.gelu_linear1_small_scatter(px.dw_dst(1), db1, db2, dg, px.world)
+    px.signal(ROW_GRAD1, e)
+    px.post_small(small)
+    px.signal(ROW_SMALL, e)
+    bwd.linear2_only_scatter(px.dw_dst(2), px.world)
+    px.signal(ROW_GRAD2, e)
     return None, db1, None, db2, dg
 
 
@@ -297,6 +313,7 @@ class ThinkDiffAligner(nn.Sequential):
         self._cache_key = None
         self._cache = None      # persistent bf16 compute copies of (W1, b1, W2, b2)
         self._bf16_fresh = False  # set by FusedAdamW: the copies were written by the optimizer step itself
+        self._cache_from_training = False  # the copies were cast by a training-mode forward (never reused for inference)
         self._pending = {}      # bucket name -> in-flight all-reduce (defer_wait mode)
         self._grad_flats = None  # the flat gradient buckets of the last backward ({"linear2": ..., "linear1": ...})
         self._bwd_order = "linear2_first"   # or "linear1_first" (pipelined train step)
@@ -307,7 +324,6 @@ class ThinkDiffAligner(nn.Sequential):
         self._dp: DataParallelState | None = None
         self._peer = None                   # PeerExchange (peer data parallel), created on first use
         self._peer_epoch = 0                # number of peer-mode backward passes so far = the value the flags carry
-        self._peer_grouped = os.environ.get("TD_PEER_GROUPED", "0") == "1"  # dW1 + dW2 as one grouped GEMM launch
         self.fp32_mode = "bf16x3"
 
     # -- reference-compatible config property (IdentityMap has one; harmless here)
@@ -317,8 +333,11 @@ class ThinkDiffAligner(nn.Sequential):
 
     # -- data parallel (replaces DDP for this module)
     def enable_data_parallel(self, group=None, overlap: bool = True, defer_wait: bool = False, sharded: bool = False,
-                             peer: bool = False):
-        self._dp = DataParallelState(group, overlap, defer_wait, sharded, peer)
+                             peer: bool = False, peer_timeout_s: float = 600.0):
+        """``peer_timeout_s``: how long a peer-mode wait may see no progress before it traps (sticky CUDA error on this rank).
+        Every rank must keep stepping (or call ``AlignerTrainStep.flush()`` + a barrier) -- a rank that leaves the loop for
+        longer than this, e.g. to write a checkpoint, takes the others down with it."""
+        self._dp = DataParallelState(group, overlap, defer_wait, sharded, peer, peer_timeout_s)
         return self
 
     def _ensure_peer(self):
@@ -330,7 +349,7 @@ class ThinkDiffAligner(nn.Sequential):
             w1, w2 = self[0].weight, self[2].weight
             if w1.dtype != torch.float32:
                 raise TypeError("peer data parallel is a training mode: parameters must be float32 masters")
-            px = PeerExchange(self.mm_hidden_size, self.hidden_size, self._dp.group, w1.device)
+            px = PeerExchange(self.mm_hidden_size, self.hidden_size, self._dp.group, w1.device, timeout_s=self._dp.peer_timeout_s)
             self._cache = (px.w1_bf16, torch.empty_like(self[0].bias, dtype=torch.bfloat16), px.w2_bf16,
                            torch.empty_like(self[2].bias, dtype=torch.bfloat16))
             self._cache_key, self._bf16_fresh = None, False
@@ -399,11 +418,17 @@ class ThinkDiffAligner(nn.Sequential):
         key = tuple((p.data_ptr(), p._version) for p in ps)
         fresh = self._bf16_fresh and key == self._cache_key
         self._bf16_fresh = False
-        if not fresh and not (allow_cache and key == self._cache_key):
+        # a copy cast during training may be stale even if the key still matches: torch's fused optimizers update parameters
+        # in place WITHOUT bumping Tensor._version. Only copies made in eval mode (or written by FusedAdamW) are reused.
+        reuse = allow_cache and key == self._cache_key and not self._cache_from_training
+        if not fresh and not reuse:
             with torch.no_grad():
                 for p, b in zip(ps, bufs):
                     ops.cast_to_bf16(p.detach().contiguous(), out=b)
             self._cache_key = key
+            self._cache_from_training = self.training
+        elif fresh:
+            self._cache_from_training = False  # FusedAdamW wrote the copies in the same pass as the update
         return bufs
 
     def _regime(self, x):
@@ -466,6 +491,49 @@ class ThinkDiffAligner(nn.Sequential):
         w1, b1, w2, b2, g = self[0].weight, self[0].bias, self[2].weight, self[2].bias, self[3].weight
         with torch.autocast("cuda", enabled=False):
             return _AlignerMSEFn.apply(x2d, target.contiguous(), w1, b1, w2, b2, g, self, target_row_index)
+
+    @torch.no_grad()
+    def mse_loss_backward_packed(self, x_packed: torch.Tensor, target: torch.Tensor, target_row_index: torch.Tensor | None = None,
+                                 upstream: torch.Tensor | None = None, stats: torch.Tensor | None = None,
+                                 accumulate_into=None, set_grads: bool = True) -> torch.Tensor:
+        """``mse_loss_packed(...)`` followed by ``loss.backward()`` as ONE direct call sequence, without autograd: forward GEMMs,
+        fused norm + loss + norm backward, backward GEMMs, gradient exchange (whatever ``enable_data_parallel`` set up). The
+        gradients land in the flat buckets (``self._grad_flats``; with ``set_grads`` the parameters' ``.grad`` become views of
+        them, as autograd would leave them) and the loss is returned as a device scalar. This is what ``AlignerTrainStep`` runs:
+        same kernels and arithmetic as the autograd path, one launch fewer (the loss is finished by the backward's finisher)
+        and no autograd bookkeeping on the host. ``upstream``: device scalar multiplied into every gradient (a GradScaler's
+        scale); ``stats``: fp32 [2] non-finite counter; ``accumulate_into``: ``GradBuckets`` of an earlier micro-batch to add
+        into (gradient accumulation; not with sharded / peer data parallel)."""
+        if self[0].weight.dtype != torch.float32:
+            raise TypeError("mse_loss_backward_packed is the training path: parameters must be float32 masters")
+        if x_packed.dim() != 2 or x_packed.shape[1] != self.mm_hidden_size or x_packed.shape[0] == 0:
+            raise ValueError(f"x_packed must be [M > 0, {self.mm_hidden_size}], got {tuple(x_packed.shape)}")
+        x2d = x_packed.to(torch.bfloat16).contiguous()
+        if target.dtype not in (torch.float32, torch.bfloat16):
+            target = target.float()
+        W1b, b1b, W2b, b2b = self._bf16_params()
+        g = self[3].weight
+        gf = g.detach() if g.dtype == torch.float32 else g.detach().float()
+        loss, saved = ops.aligner_mse_fwd(x2d, W1b, b1b, W2b, b2b, gf, self.eps, target.contiguous(), self._between_fwd_stages,
+                                          target_row_index, defer_loss=True)
+        dp = self._dp
+        scale = 1.0 / dp.world if dp is not None else 1.0
+        bwd = ops.AlignerBackwardFromDh2(x2d, saved, W2b, upstream, grad_scale=scale, loss_out=loss, stats=stats,
+                                         accumulate=accumulate_into is not None)
+        if accumulate_into is not None:
+            if dp is not None and dp.world > 1 and (dp.sharded or dp.peer):
+                raise NotImplementedError("gradient accumulation with sharded / peer data parallel")
+            gb = accumulate_into
+            self._grad_flats = gb.flats()
+            bwd.gelu_linear1_and_small(gb.dW1, gb.db1, gb.db2, gb.dg)
+            bwd.linear2_only(gb.dW2)
+            grads = gb.in_parameter_order()
+        else:
+            grads = _mse_backward(self, bwd, x2d.shape[1], W2b.shape[0], x2d.device)
+        if set_grads:
+            for p, gr in zip((self[0].weight, self[0].bias, self[2].weight, self[2].bias, self[3].weight), grads):
+                p.grad = gr
+        return loss
 
     def forward_packed(self, x_packed: torch.Tensor, cu_seqlens: torch.Tensor | None = None) -> torch.Tensor:
         """Ragged entry point: ``x_packed[M, Din]`` (rows of all sequences back to back, ``cu_seqlens`` int32 [B+1]).

@@ -17,6 +17,7 @@
 #include <cstdio>
 
 #include "gemm_sm100.cuh"
+#include "rowops_sm100.cuh"
 
 namespace td {
 
@@ -94,14 +95,20 @@ struct AdamSlotsParams {
   PeerPtrs p_bf16; int n_dst;
   long long n;
   float weight_decay, lr, beta1, beta2, eps, bias_c1, sqrt_bias_c2, grad_scale;
+  const StepCtl* ctl;  // optional device-side step control (see rowops_sm100.cuh)
 };
 
 __global__ void __launch_bounds__(256) adamw_slots_kernel(const AdamSlotsParams a) {
   const long long n4 = a.n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long slot4 = a.slot_stride >> 2;
+  float bias_c1 = a.bias_c1, sqrt_bias_c2 = a.sqrt_bias_c2, grad_scale = a.grad_scale;
+  if (a.ctl != nullptr) {
+    if (a.ctl->skip) return;  // skipped step: every rank's bf16 rows stay as they are
+    bias_c1 = a.ctl->bias_c1; sqrt_bias_c2 = a.ctl->sqrt_bias_c2; grad_scale *= a.ctl->grad_mult;
+  }
   const float decay = 1.0f - a.lr * a.weight_decay;
-  const float step_size = a.lr / a.bias_c1;
+  const float step_size = a.lr / bias_c1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 p = reinterpret_cast<float4*>(a.p)[i];
     float4 m = reinterpret_cast<float4*>(a.m)[i];
@@ -114,11 +121,11 @@ __global__ void __launch_bounds__(256) adamw_slots_kernel(const AdamSlotsParams 
     float pp[4] = {p.x, p.y, p.z, p.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, mm[4] = {m.x, m.y, m.z, m.w}, vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float g = gg[q] * a.grad_scale;
+      const float g = gg[q] * grad_scale;
       pp[q] *= decay;
       mm[q] = a.beta1 * mm[q] + (1.0f - a.beta1) * g;
       vv[q] = a.beta2 * vv[q] + (1.0f - a.beta2) * g * g;
-      const float denom = sqrtf(vv[q]) / a.sqrt_bias_c2 + a.eps;
+      const float denom = sqrtf(vv[q]) / sqrt_bias_c2 + a.eps;
       pp[q] -= step_size * (mm[q] / denom);
     }
     reinterpret_cast<float4*>(a.p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);

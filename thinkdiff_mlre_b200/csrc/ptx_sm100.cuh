@@ -106,6 +106,28 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
+// ---------------------------------------------------------------- global-memory flags (stream-K fix-up, peer exchange)
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Wait until another CTA of this grid has stored a non-zero value (release) to *p. Same 4 s trap as the mbarrier waits.
+__device__ __forceinline__ void spin_until_set(const int* p) {
+  if (ld_acquire_gpu(p) != 0) return;
+  const uint64_t t0 = global_timer_ns();
+  while (ld_acquire_gpu(p) == 0) {
+    __nanosleep(64);
+    if (global_timer_ns() - t0 > TD_MBAR_TIMEOUT_NS) {
+      printf("td: stream-K flag timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- cluster
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -144,6 +166,12 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// Same box, added element-wise into global memory (fp32 tensor map): out += box.
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
                "r"(smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }

@@ -353,9 +353,25 @@ rmsnorm_bwd_kernel(const void* __restrict__ dy_in, const __nv_bfloat16* __restri
 struct AdamSegment {
   float* p; const float* g; float* m; float* v; __nv_bfloat16* p_bf16; long long n; float weight_decay;
 };
+// Device-resident control block of one optimizer step (written by step_ctl_kernel): lets GradScaler's inf check / skipped
+// step, the unscale factor, the global-norm clip and the bias corrections reach the update kernels without a host sync.
+//   torch.amp.GradScaler semantics (thinkdiff/runners/runner_base.py:131-139, tasks/base_task.py:241-258): if any gradient
+//   is non-finite the step is skipped for EVERY parameter and the step count does not advance; scale *= backoff, else after
+//   growth_interval clean steps scale *= growth.
+struct StepCtl {
+  int skip;               // 1: non-finite gradient somewhere -> no parameter changes this step
+  float grad_mult;        // (1 / loss scale) * clip coefficient, multiplied into every gradient
+  float bias_c1;          // 1 - beta1^t
+  float sqrt_bias_c2;     // sqrt(1 - beta2^t)
+  float step;             // t, the number of applied updates including this one (float: exact up to 2^24)
+  float scale;            // current loss scale (the backward's upstream scalar reads this)
+  int growth_tracker;     // clean steps since the last scale change
+  float grad_norm;        // global gradient norm of this step after unscaling (0 when clipping is off)
+};
 struct AdamParams {
   AdamSegment seg[3];
   float lr, beta1, beta2, eps, bias_c1, sqrt_bias_c2, grad_scale;
+  const StepCtl* ctl;  // optional: overrides bias_c1 / sqrt_bias_c2 / grad_scale and may skip the update
 };
 
 __global__ void __launch_bounds__(256)
@@ -363,8 +379,13 @@ adamw_kernel(const AdamParams a) {
   const AdamSegment s = a.seg[blockIdx.y];
   const long long n4 = s.n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
+  float bias_c1 = a.bias_c1, sqrt_bias_c2 = a.sqrt_bias_c2, grad_scale = a.grad_scale;
+  if (a.ctl != nullptr) {
+    if (a.ctl->skip) return;  // parameters, moments and the bf16 copies all stay as they are
+    bias_c1 = a.ctl->bias_c1; sqrt_bias_c2 = a.ctl->sqrt_bias_c2; grad_scale *= a.ctl->grad_mult;
+  }
   const float decay = 1.0f - a.lr * s.weight_decay;
-  const float step_size = a.lr / a.bias_c1;
+  const float step_size = a.lr / bias_c1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 p = reinterpret_cast<float4*>(s.p)[i];
     const float4 g4 = __ldg(reinterpret_cast<const float4*>(s.g) + i);
@@ -373,11 +394,11 @@ adamw_kernel(const AdamParams a) {
     float pp[4] = {p.x, p.y, p.z, p.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, mm[4] = {m.x, m.y, m.z, m.w}, vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float g = gg[q] * a.grad_scale;
+      const float g = gg[q] * grad_scale;
       pp[q] *= decay;
       mm[q] = a.beta1 * mm[q] + (1.0f - a.beta1) * g;
       vv[q] = a.beta2 * vv[q] + (1.0f - a.beta2) * g * g;
-      const float denom = sqrtf(vv[q]) / a.sqrt_bias_c2 + a.eps;
+      const float denom = sqrtf(vv[q]) / sqrt_bias_c2 + a.eps;
       pp[q] -= step_size * (mm[q] / denom);
     }
     reinterpret_cast<float4*>(s.p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
@@ -388,124 +409,220 @@ adamw_kernel(const AdamParams a) {
   }
 }
 
+// One thread: fold this step's gradient statistics into the control block.
+//   stats[0] = number of non-finite gradient values seen (summed over ranks), stats[1] = sum of squares of the SCALED gradients
+//   (only when clipping). use_scaler = 0: scale stays 1 and nothing is ever skipped (but a clip still applies).
+__global__ void step_ctl_kernel(StepCtl* ctl, const float* __restrict__ stats, int use_scaler, float growth, float backoff,
+                                int growth_interval, float beta1, float beta2, float max_norm) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float found = stats != nullptr ? stats[0] : 0.f;
+  const bool bad = use_scaler && !(found == 0.f);  // NaN counts as found
+  const float scale = use_scaler ? ctl->scale : 1.0f;
+  const float inv_scale = 1.0f / scale;
+  float mult = inv_scale, norm = 0.f;
+  if (max_norm > 0.f && stats != nullptr) {
+    norm = sqrtf(stats[1]) * inv_scale;
+    const float coef = max_norm / (norm + 1e-6f);  // torch.nn.utils.clip_grad_norm_
+    mult *= coef < 1.0f ? coef : 1.0f;
+    if (!(norm == norm) || norm > 3.0e38f) { /* non-finite norm: torch multiplies by NaN; a scaler would have skipped */ }
+  }
+  ctl->grad_norm = norm;
+  ctl->grad_mult = mult;
+  ctl->skip = bad ? 1 : 0;
+  if (!bad) {
+    const float t = ctl->step + 1.0f;
+    ctl->step = t;
+    ctl->bias_c1 = float(1.0 - pow((double)beta1, (double)t));
+    ctl->sqrt_bias_c2 = float(sqrt(1.0 - pow((double)beta2, (double)t)));
+  }
+  if (use_scaler) {  // GradScaler.update()
+    if (bad) {
+      ctl->scale = scale * backoff;
+      ctl->growth_tracker = 0;
+    } else if (++ctl->growth_tracker == growth_interval) {
+      ctl->scale = scale * growth;
+      ctl->growth_tracker = 0;
+    }
+  }
+}
+
+// stats[0] += #non-finite, stats[1] += sum of squares over a flat fp32 buffer (grid-stride; one atomic pair per CTA).
+__global__ void __launch_bounds__(256)
+grad_stats_kernel(const float* __restrict__ g, long long n, float* __restrict__ stats) {
+  __shared__ float s_sq[8], s_bad[8];
+  float sq = 0.f, bad = 0.f;
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      sq = fmaf(e[q], e[q], sq);
+      bad += (fabsf(e[q]) <= 3.4028234e38f) ? 0.f : 1.f;  // false for inf and NaN
+    }
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    sq = fmaf(g[i], g[i], sq);
+    bad += (fabsf(g[i]) <= 3.4028234e38f) ? 0.f : 1.f;
+  }
+  sq = warp_sum(sq); bad = warp_sum(bad);
+  if ((threadIdx.x & 31) == 0) { s_sq[threadIdx.x >> 5] = sq; s_bad[threadIdx.x >> 5] = bad; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < 8; ++i) { a += s_sq[i]; b += s_bad[i]; }
+    if (b != 0.f) atomicAdd(stats, b);
+    atomicAdd(stats + 1, a);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ fused norm + MSE + norm-backward
 // Training against T5 targets never needs y or dy in memory: with y = g * h2 * rstd,
 //   diff = y - t;  loss += diff^2;  dy = (2 / (M D)) diff;  then the T5LayerNorm backward of dy, all per row in registers.
-// Same CTA organisation as rmsnorm_bwd_kernel (thread = 8 columns, R rows per block reduction). dh2 / dg / db2 are written
-// for a unit upstream gradient; the backward GEMMs multiply by the (device-resident) upstream scalar.
-// HBM traffic per token: h2 8 KB + target 8 KB (bf16) read, dh2 8 KB written -- instead of the 96 KB of the three
-// separate passes (norm fwd 24 KB, MSE 40 KB, norm bwd 32 KB).
+// Thread t of a 512-thread CTA owns columns [8t, 8t+8) (so the per-column sums for dg / db2 live in 16 registers); the CTA walks
+// its slab of rows two at a time. Each iteration needs ONE block reduction (s_r = sum_D(g dy h2) per row): warps publish their
+// partial sums in a parity-double-buffered array, one __syncthreads, every thread adds the 16 partials itself. The loads of the
+// next PF iterations are already in flight (packed bf16 in registers) while an iteration computes, so the kernel streams:
+// HBM traffic per token is h2 8 KB + target 8 KB (bf16) read, dh2 8 KB written -- instead of the 96 KB of the three separate
+// passes (norm fwd 24 KB, MSE 40 KB, norm bwd 32 KB). dh2 / dg / db2 are written for a unit upstream gradient; the backward
+// GEMMs and the finisher multiply by the (device-resident) upstream scalar.
+constexpr int kNormMseMaxRows = 1024;  // rows whose rstd / target row are staged per block (usually the CTA's whole slab)
+
 template <bool T_BF16>
-__global__ void __launch_bounds__(kNormBwdThreads, 2)
+struct NormMseRow {
+  uint4 h;
+  uint4 t0;
+  uint4 t1;  // second half of the 8 target values when the target is fp32
+};
+
+template <bool T_BF16>
+__global__ void __launch_bounds__(kNormBwdThreads, 1)
 norm_mse_bwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restrict__ ssq_part, int P, float eps,
                     const float* __restrict__ g, const void* __restrict__ t_in,
                     const long long* __restrict__ t_row_index, int M, int D, int rows_per_cta, float dy_coef,
                     __nv_bfloat16* __restrict__ dh2, float* __restrict__ dg_part, float* __restrict__ db2_part,
                     float* __restrict__ loss_part) {
   constexpr int R = kNormBwdRows;
-  __shared__ float red[R][kNormBwdThreads / 32];
-  __shared__ float tot[R];
-  __shared__ float lred[kNormBwdThreads / 32];
-  constexpr int kRstdBlock = 512;        // rows whose rstd is computed at once (one latency round per block)
-  __shared__ float rs_sm[kRstdBlock];
-  __shared__ long long ti_sm[kRstdBlock];  // target row of every row of the block (staged: no dependent global loads later)
+  constexpr int PF = T_BF16 ? 2 : 1;  // iterations of loads in flight beyond the one being computed
+  constexpr int NB = PF + 1;
+  constexpr int NW = kNormBwdThreads / 32;
+  __shared__ float red[2][R][NW];
+  __shared__ float lred[NW];
+  __shared__ float rs_sm[kNormMseMaxRows];
+  __shared__ long long ti_sm[kNormMseMaxRows];  // target row of every row of the block (staged: no dependent global loads later)
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const bool col_ok = t * 8 < D;
   const int row_begin = blockIdx.x * rows_per_cta;
   const int row_end = min(M, row_begin + rows_per_cta);
-  // rstd = rsqrt(mean(h2^2) + eps) from the GEMM2 epilogue's partial sums ssq_part[P][M], for a block of rows at a time:
-  // warp w handles rows w, w + 16, ... of the block (lane p reads partial p), so the whole block costs one load round trip
-  auto block_rstd = [&](int b0) {
-    const int b1 = min(row_end, b0 + kRstdBlock);
-    for (int i = t; i < b1 - b0; i += kNormBwdThreads)
-      ti_sm[i] = t_row_index != nullptr ? __ldg(t_row_index + b0 + i) : (long long)(b0 + i);
-    for (int row = b0 + w; row < b1; row += kNormBwdThreads / 32) {
-      float ssq = 0.f;
-      for (int p = lane; p < P; p += 32) ssq += ssq_part[(long long)p * M + row];
-      ssq = warp_sum(ssq);
-      if (lane == 0) rs_sm[row - b0] = rsqrtf(ssq / float(D) + eps);
-    }
-  };
   float gg[8], adg[8], adb[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) { gg[q] = col_ok ? g[t * 8 + q] : 0.f; adg[q] = 0.f; adb[q] = 0.f; }
   const float inv_d = 1.0f / float(D);
   float loss_acc = 0.f;
 
-  int blk0 = row_begin - kRstdBlock;  // kRstdBlock % R == 0
-  for (int r0 = row_begin; r0 < row_end; r0 += R) {
-    float dyv[R][8], hv[R][8], part[R], rs[R];
-    if (r0 >= blk0 + kRstdBlock) {  // uniform across the CTA
-      __syncthreads();              // everyone is done reading the previous block's rstd
-      blk0 = r0;
-      block_rstd(blk0);
-      __syncthreads();
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int row = r0 + r;
-      const bool ok = col_ok && row < row_end;
-      uint4 hu = make_uint4(0, 0, 0, 0);
-      float tv[8];
-      if (ok) hu = ld_stream(reinterpret_cast<const uint4*>(h2 + (long long)row * D) + t);
-      const long long trow = ok ? ti_sm[row - blk0] : 0ll;
-      if constexpr (T_BF16) {
-        uint4 tu = make_uint4(0, 0, 0, 0);
-        if (ok) tu = ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(t_in) + trow * D) + t);
-        const uint32_t tw[4] = {tu.x, tu.y, tu.z, tu.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { tv[2 * q] = bf16lo(tw[q]); tv[2 * q + 1] = bf16hi(tw[q]); }
-      } else {
-        uint4 t0 = make_uint4(0, 0, 0, 0), t1 = t0;
-        if (ok) {
-          const uint4* tp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(t_in) + trow * D) + 2 * t;
-          t0 = ld_stream(tp);
-          t1 = ld_stream(tp + 1);
-        }
-        tv[0] = __uint_as_float(t0.x); tv[1] = __uint_as_float(t0.y); tv[2] = __uint_as_float(t0.z); tv[3] = __uint_as_float(t0.w);
-        tv[4] = __uint_as_float(t1.x); tv[5] = __uint_as_float(t1.y); tv[6] = __uint_as_float(t1.z); tv[7] = __uint_as_float(t1.w);
-      }
-      rs[r] = (row < row_end) ? rs_sm[row - blk0] : 0.f;
-      const uint32_t hw[4] = {hu.x, hu.y, hu.z, hu.w};
-      float s = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { hv[r][2 * q] = bf16lo(hw[q]); hv[r][2 * q + 1] = bf16hi(hw[q]); }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float diff = ok ? gg[q] * (hv[r][q] * rs[r]) - tv[q] : 0.f;
-        loss_acc = fmaf(diff, diff, loss_acc);
-        dyv[r][q] = dy_coef * diff;
-        s = fmaf(gg[q] * dyv[r][q], hv[r][q], s);
-      }
-      part[r] = warp_sum(s);
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) red[r][w] = part[r];
+  for (int b0 = row_begin; b0 < row_end; b0 += kNormMseMaxRows) {
+    const int b1 = min(row_end, b0 + kNormMseMaxRows);
+    // rstd = rsqrt(mean(h2^2) + eps) from the GEMM2 epilogue's partial sums ssq_part[P][M]: warp w handles rows w, w + 16, ...
+    // of the block (lane p reads partial p), so the whole block costs one load round trip
+    __syncthreads();  // the previous block's rs_sm / ti_sm / red are no longer read
+    for (int i = t; i < b1 - b0; i += kNormBwdThreads)
+      ti_sm[i] = t_row_index != nullptr ? __ldg(t_row_index + b0 + i) : (long long)(b0 + i);
+    for (int row = b0 + w; row < b1; row += NW) {
+      float ssq = 0.f;
+      for (int pp = lane; pp < P; pp += 32) ssq += ssq_part[(long long)pp * M + row];
+      ssq = warp_sum(ssq);
+      if (lane == 0) rs_sm[row - b0] = rsqrtf(ssq / float(D) + eps);
     }
     __syncthreads();
-    if (w < R) {
-      float v = lane < kNormBwdThreads / 32 ? red[w][lane] : 0.f;
-      v = warp_sum(v);
-      if (lane == 0) tot[w] = v;
-    }
-    __syncthreads();
+
+    NormMseRow<T_BF16> buf[NB][R];
+    auto issue = [&](NormMseRow<T_BF16> (&dst)[R], int r0) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int row = r0 + r;
-      if (row < row_end && col_ok) {
-        const float rstd = rs[r];
-        const float c = tot[r] * inv_d * rstd * rstd * rstd;
-        float o[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          o[q] = bf16_round(rstd * gg[q] * dyv[r][q] - hv[r][q] * c);
-          adb[q] += o[q];
-          adg[q] = fmaf(dyv[r][q] * hv[r][q], rstd, adg[q]);
+      for (int r = 0; r < R; ++r) {
+        const int row = r0 + r;
+        dst[r].h = make_uint4(0, 0, 0, 0); dst[r].t0 = dst[r].h; dst[r].t1 = dst[r].h;
+        if (col_ok && row < b1) {
+          dst[r].h = ld_stream(reinterpret_cast<const uint4*>(h2 + (long long)row * D) + t);
+          const long long trow = ti_sm[row - b0];
+          if constexpr (T_BF16) {
+            dst[r].t0 = ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(t_in) + trow * D) + t);
+          } else {
+            const uint4* tp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(t_in) + trow * D) + 2 * t;
+            dst[r].t0 = ld_stream(tp);
+            dst[r].t1 = ld_stream(tp + 1);
+          }
         }
-        st_stream(reinterpret_cast<uint4*>(dh2 + (long long)row * D) + t,
-                  make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                             pack_bf16x2(o[6], o[7])));
+      }
+    };
+#pragma unroll
+    for (int u = 0; u < PF; ++u) issue(buf[u], b0 + u * R);
+
+    int it = 0;
+    for (int r0 = b0; r0 < b1; r0 += R * NB) {
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const int rr = r0 + u * R;  // first row of this iteration (uniform across the CTA)
+        if (rr < b1) {
+          issue(buf[(u + PF) % NB], rr + PF * R);  // refill the buffer consumed in the previous iteration
+          float dyv[R][8], hv[R][8], part[R], rs[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int row = rr + r;
+            const bool ok = col_ok && row < b1;
+            float tv[8];
+            const NormMseRow<T_BF16>& in = buf[u][r];
+            if constexpr (T_BF16) {
+              const uint32_t tw[4] = {in.t0.x, in.t0.y, in.t0.z, in.t0.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { tv[2 * q] = bf16lo(tw[q]); tv[2 * q + 1] = bf16hi(tw[q]); }
+            } else {
+              tv[0] = __uint_as_float(in.t0.x); tv[1] = __uint_as_float(in.t0.y); tv[2] = __uint_as_float(in.t0.z); tv[3] = __uint_as_float(in.t0.w);
+              tv[4] = __uint_as_float(in.t1.x); tv[5] = __uint_as_float(in.t1.y); tv[6] = __uint_as_float(in.t1.z); tv[7] = __uint_as_float(in.t1.w);
+            }
+            rs[r] = (row < b1) ? rs_sm[row - b0] : 0.f;
+            const uint32_t hw[4] = {in.h.x, in.h.y, in.h.z, in.h.w};
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { hv[r][2 * q] = bf16lo(hw[q]); hv[r][2 * q + 1] = bf16hi(hw[q]); }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float diff = ok ? gg[q] * (hv[r][q] * rs[r]) - tv[q] : 0.f;
+              loss_acc = fmaf(diff, diff, loss_acc);
+              dyv[r][q] = dy_coef * diff;
+              s = fmaf(gg[q] * dyv[r][q], hv[r][q], s);
+            }
+            part[r] = warp_sum(s);
+          }
+          const int par = it & 1;
+          if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) red[par][r][w] = part[r];
+          }
+          __syncthreads();  // the only block barrier of the iteration (the other parity is rewritten one barrier later)
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int row = rr + r;
+            float tot = 0.f;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) tot += red[par][r][i];  // broadcast reads, same order in every thread
+            if (row < b1 && col_ok) {
+              const float rstd = rs[r];
+              const float c = tot * inv_d * rstd * rstd * rstd;
+              float o[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                o[q] = bf16_round(rstd * gg[q] * dyv[r][q] - hv[r][q] * c);
+                adb[q] += o[q];
+                adg[q] = fmaf(dyv[r][q] * hv[r][q], rstd, adg[q]);
+              }
+              st_stream(reinterpret_cast<uint4*>(dh2 + (long long)row * D) + t,
+                        make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                                   pack_bf16x2(o[6], o[7])));
+            }
+          }
+          ++it;
+        }
       }
     }
   }
@@ -522,14 +639,74 @@ norm_mse_bwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restric
   __syncthreads();
   if (t == 0) {
     float tot_loss = 0.f;
-    for (int i = 0; i < kNormBwdThreads / 32; ++i) tot_loss += lred[i];
+    for (int i = 0; i < NW; ++i) tot_loss += lred[i];
     loss_part[blockIdx.x] = tot_loss;
   }
 }
 
-// out[n] = scale * sum_p part[p][n]   (fixed order -> deterministic). One CTA per 32 columns; warp w adds rows
-// p = w, w + 8, ... (4 independent loads in flight), then the 8 warp sums are combined in warp order.
-// blockIdx.y selects one of up to two (part, out) pairs so that dg and db2 finish in one launch.
+// Fixed-order finishers of the two-level reductions, one launch for everything a backward phase needs:
+//   job j < njobs : out[n] (+)= scale * (use_scale_ptr ? *scale_ptr : 1) * sum_p part[p][n]  -- column sums (dg, db2 from the norm kernel's per-CTA
+//                   partials, db1 from the dh0 GEMM's per-warp-slab partials). One CTA per 32 columns; warp w adds rows
+//                   p = w, w + 8, ... (4 independent loads in flight), then the 8 warp sums are combined in warp order.
+//   job njobs     : loss = sum(loss_part) / loss_div  (only when loss_out != nullptr)
+// Non-finite results bump stats[0] (GradScaler's inf check, see StepCtl).
+struct FinishJob { const float* part; float* out; int P; int use_scale_ptr; };
+struct FinishParams {
+  FinishJob job[3];
+  int njobs, N;
+  float scale;
+  const float* scale_ptr;
+  int accumulate;  // 1: out += (gradient accumulation over micro-batches)
+  float* stats;    // optional
+  const float* loss_part; int loss_P; float* loss_out; float loss_div;
+};
+
+__global__ void __launch_bounds__(256)
+finish_kernel(const FinishParams f) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (int(blockIdx.y) == f.njobs) {  // the loss job
+    if (blockIdx.x != 0 || f.loss_out == nullptr) return;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < f.loss_P; i += blockDim.x) acc += f.loss_part[i];
+    acc = warp_sum(acc);
+    if (lane == 0) red[w][0] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int i = 0; i < 8; ++i) tot += red[i][0];
+      f.loss_out[0] = tot / f.loss_div;
+    }
+    return;
+  }
+  const FinishJob j = f.job[blockIdx.y];
+  const int col = blockIdx.x * 32 + lane;
+  const int N = f.N, P = j.P;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (col < N) {
+    int p = w;
+    for (; p + 24 < P; p += 32) {
+      a0 += j.part[(long long)p * N + col];
+      a1 += j.part[(long long)(p + 8) * N + col];
+      a2 += j.part[(long long)(p + 16) * N + col];
+      a3 += j.part[(long long)(p + 24) * N + col];
+    }
+    for (; p < P; p += 8) a0 += j.part[(long long)p * N + col];
+  }
+  red[w][lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (w == 0 && col < N) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += red[i][lane];
+    float v = f.scale * ((j.use_scale_ptr && f.scale_ptr) ? __ldg(f.scale_ptr) : 1.f) * acc;
+    if (f.stats != nullptr && !(fabsf(v) <= 3.4028234e38f)) atomicAdd(f.stats, 1.0f);
+    if (f.accumulate) v += j.out[col];
+    j.out[col] = v;
+  }
+}
+
+// Single-job form kept for the module-boundary backward (td_rmsnorm_bwd / td_aligner_bwd).
 __global__ void __launch_bounds__(256)
 colsum_finish_kernel(const float* __restrict__ part0, float* __restrict__ out0, const float* __restrict__ part1,
                      float* __restrict__ out1, int P, int N, float scale, const float* __restrict__ scale_ptr = nullptr) {

@@ -7,6 +7,8 @@
 #include "rowops_sm100.cuh"
 #include "peer_sm100.cuh"
 
+#include <cmath>
+
 using namespace td;
 
 namespace {
@@ -26,15 +28,9 @@ struct Carver {
 };
 
 int check_device() {
-  static int ok = -1;
-  if (ok < 0) {
-    int dev = 0, major = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
-      TD_FAIL(TD_ERR_UNSUPPORTED, "no usable CUDA device");
-    ok = (major == 10) ? 1 : 0;
-  }
-  if (!ok) TD_FAIL(TD_ERR_UNSUPPORTED, "libthinkdiff_b200 needs an sm_100 (B200) device; there is no fallback path");
+  DeviceState* d = device_state();
+  if (!d) TD_FAIL(TD_ERR_UNSUPPORTED, "no usable CUDA device");
+  if (d->cc_major != 10) TD_FAIL(TD_ERR_UNSUPPORTED, "libthinkdiff_b200 needs an sm_100 (B200) device; there is no fallback path");
   return TD_OK;
 }
 #define TD_DEVICE_OR_RETURN()      \
@@ -59,6 +55,16 @@ inline int norm_bwd_grid(long long M, int* rows_per_cta) {
   return int((M + rpc - 1) / rpc);
 }
 
+inline int norm_mse_grid(long long M, int* rows_per_cta) {
+  // fused norm + MSE + norm-backward: one 512-thread CTA per SM, each with one contiguous slab of rows
+  int ctas = device_sm_count();
+  long long rpc = (M + ctas - 1) / ctas;
+  rpc = (rpc + kNormBwdRows - 1) / kNormBwdRows * kNormBwdRows;
+  if (rpc < kNormBwdRows) rpc = kNormBwdRows;
+  *rows_per_cta = int(rpc);
+  return int((M + rpc - 1) / rpc);
+}
+
 inline bool dims_ok(int Din, int D) { return Din > 0 && D > 0 && Din % 64 == 0 && D % 64 == 0 && D <= 8 * kNormBwdThreads; }
 
 }  // namespace
@@ -72,15 +78,17 @@ int32_t td_device_check(void) { return check_device(); }
 // ------------------------------------------------------------------------------------------------ profiling
 int32_t td_profile_enable(int32_t on) {
   Profiler& p = Profiler::get();
+  std::lock_guard<std::mutex> lock(p.mu);
   for (auto& r : p.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   p.recs.clear();
-  p.on = on != 0;
+  p.on.store(on != 0);
   return TD_OK;
 }
 
 // Writes "tag,launches,total_ms,total_work\n" lines (work = FLOPs for gemm_* tags, algorithmic bytes otherwise).
 int32_t td_profile_report(char* buf, int32_t buflen) {
   Profiler& p = Profiler::get();
+  std::lock_guard<std::mutex> lock(p.mu);
   struct Agg { const char* tag; int n; double ms, work; };
   std::vector<Agg> agg;
   for (auto& r : p.recs) {
@@ -99,6 +107,27 @@ int32_t td_profile_report(char* buf, int32_t buflen) {
     off += w;
   }
   if (buflen > 0) buf[off < buflen ? off : buflen - 1] = 0;
+  return TD_OK;
+}
+
+// Writes one "tag,stream,start_ms,end_ms\n" line per recorded launch, times relative to the first record: the events of
+// different streams are stamped by the same device clock, so this is a per-stream timeline of the library's kernels.
+int32_t td_profile_timeline(char* buf, int32_t buflen) {
+  Profiler& p = Profiler::get();
+  std::lock_guard<std::mutex> lock(p.mu);
+  int off = 0;
+  if (buflen > 0) buf[0] = 0;
+  if (p.recs.empty()) return TD_OK;
+  cudaEvent_t base = p.recs[0].e0;
+  for (auto& r : p.recs) {
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) TD_FAIL(TD_ERR_DRIVER, "td_profile_timeline: event sync failed");
+    float t0 = 0.f, t1 = 0.f;
+    cudaEventElapsedTime(&t0, base, r.e0);
+    cudaEventElapsedTime(&t1, base, r.e1);
+    int w = snprintf(buf + off, buflen > off ? buflen - off : 0, "%s,%p,%.4f,%.4f\n", r.tag, (void*)r.stream, t0, t1);
+    if (w < 0 || off + w >= buflen) TD_FAIL(TD_ERR_ARG, "td_profile_timeline: buffer too small");
+    off += w;
+  }
   return TD_OK;
 }
 
@@ -242,8 +271,15 @@ int32_t td_rmsnorm_bwd(const void* dy, int32_t dy_dtype, const void* x, const fl
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM entries
-int32_t td_linear_bf16(const void* x, int64_t M, int32_t K, const void* W, int32_t N, const void* bias, void* out,
-                       td_stream_t stream) {
+int64_t td_gemm_workspace_bytes(void) { return (int64_t)align_up(gemm_sk_workspace_bytes(), 256); }
+
+namespace {
+// the stream-K workspace is optional at the test / utility entries: without it the leftover tiles run as a last partial wave
+inline void* sk_ws_or_null(void* ws, int64_t ws_bytes) { return (ws && ws_bytes >= td_gemm_workspace_bytes()) ? ws : nullptr; }
+}  // namespace
+
+int32_t td_linear_bf16(const void* x, int64_t M, int32_t K, const void* W, int32_t N, const void* bias, void* out, void* ws,
+                       int64_t ws_bytes, td_stream_t stream) {
   TD_DEVICE_OR_RETURN();
   if (M < 0 || K <= 0 || N <= 0 || K % 8 || N % 32) TD_FAIL(TD_ERR_UNSUPPORTED, "td_linear_bf16: need K %% 8 == 0, N %% 32 == 0");
   if (M == 0) return TD_OK;
@@ -251,38 +287,55 @@ int32_t td_linear_bf16(const void* x, int64_t M, int32_t K, const void* W, int32
   memset(&p, 0, sizeof(p));
   p.M = int(M); p.N = N; p.K = K;
   p.out0 = out; p.ld_out = N; p.bias = static_cast<const __nv_bfloat16*>(bias); p.alpha = 1.f;
-  return launch_gemm<2, false, false, EPI_BF16>({x, K, false}, {W, K, false}, p, 1, (cudaStream_t)stream);
+  return launch_gemm<2, false, false, EPI_BF16>({x, K, false}, {W, K, false}, p, sk_ws_or_null(ws, ws_bytes), (cudaStream_t)stream, "gemm_linear");
 }
 
 int32_t td_gemm_bf16_f32out(const void* A, int64_t lda, int32_t a_mn, const void* B, int64_t ldb, int32_t b_mn, int64_t M,
-                            int32_t N, int64_t K, float alpha, float* out, int32_t cta_pair, int32_t splits,
-                            td_stream_t stream) {
+                            int32_t N, int64_t K, float alpha, float* out, int32_t cta_pair, int32_t accumulate, void* ws,
+                            int64_t ws_bytes, td_stream_t stream) {
   TD_DEVICE_OR_RETURN();
   if (M <= 0 || N <= 0 || K <= 0) TD_FAIL(TD_ERR_ARG, "td_gemm_bf16_f32out: empty problem");
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = int(M); p.N = N; p.K = int(K);
-  p.out0 = out; p.ld_out = N; p.alpha = alpha;
+  p.out0 = out; p.ld_out = N; p.alpha = alpha; p.accumulate = accumulate != 0;
   cudaStream_t st = (cudaStream_t)stream;
+  void* sk = sk_ws_or_null(ws, ws_bytes);
   GemmOperand a{A, lda, a_mn != 0}, b{B, ldb, b_mn != 0};
   const int sel = (cta_pair ? 4 : 0) | (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
   switch (sel) {
-    case 0: return launch_gemm<1, false, false, EPI_F32>(a, b, p, splits, st);
-    case 1: return launch_gemm<1, false, true, EPI_F32>(a, b, p, splits, st);
-    case 2: return launch_gemm<1, true, false, EPI_F32>(a, b, p, splits, st);
-    case 3: return launch_gemm<1, true, true, EPI_F32>(a, b, p, splits, st);
-    case 4: return launch_gemm<2, false, false, EPI_F32>(a, b, p, splits, st);
-    case 5: return launch_gemm<2, false, true, EPI_F32>(a, b, p, splits, st);
-    case 6: return launch_gemm<2, true, false, EPI_F32>(a, b, p, splits, st);
-    default: return launch_gemm<2, true, true, EPI_F32>(a, b, p, splits, st);
+    case 0: return launch_gemm<1, false, false, EPI_F32>(a, b, p, sk, st);
+    case 1: return launch_gemm<1, false, true, EPI_F32>(a, b, p, sk, st);
+    case 2: return launch_gemm<1, true, false, EPI_F32>(a, b, p, sk, st);
+    case 3: return launch_gemm<1, true, true, EPI_F32>(a, b, p, sk, st);
+    case 4: return launch_gemm<2, false, false, EPI_F32>(a, b, p, sk, st);
+    case 5: return launch_gemm<2, false, true, EPI_F32>(a, b, p, sk, st);
+    case 6: return launch_gemm<2, true, false, EPI_F32>(a, b, p, sk, st);
+    default: return launch_gemm<2, true, true, EPI_F32>(a, b, p, sk, st);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ aligner forward
+namespace {
+struct FwdWorkspace {
+  float* ssq_part;
+  void* sk;
+  size_t bytes;
+};
+FwdWorkspace carve_fwd(void* ws, int64_t M, int32_t D) {
+  Carver c(ws);
+  FwdWorkspace w;
+  const size_t nparts = 2 * ((size_t)(D + kBlockN - 1) / kBlockN);  // two column halves per N tile
+  w.ssq_part = c.take<float>(nparts * (size_t)(M > 0 ? M : 1));
+  w.sk = c.take<uint8_t>(gemm_sk_workspace_bytes());
+  w.bytes = c.off;
+  return w;
+}
+}  // namespace
+
 int64_t td_aligner_fwd_workspace_bytes(int64_t M, int32_t Din, int32_t D) {
   (void)Din;
-  const size_t nparts = 2 * ((size_t)(D + kBlockN - 1) / kBlockN);  // two column halves per N tile
-  return (int64_t)align_up(sizeof(float) * nparts * (size_t)(M > 0 ? M : 1), 256);
+  return (int64_t)carve_fwd(nullptr, M, D).bytes;
 }
 
 int32_t td_aligner_fwd(const void* x, int64_t M, int32_t Din, int32_t D, const void* W1, const void* b1, const void* W2,
@@ -295,7 +348,7 @@ int32_t td_aligner_fwd(const void* x, int64_t M, int32_t Din, int32_t D, const v
   if (!x || !W1 || !W2 || !g || !h1 || !h2 || !y) TD_FAIL(TD_ERR_ARG, "td_aligner_fwd: null pointer");
   if (ws_bytes < td_aligner_fwd_workspace_bytes(M, Din, D)) TD_FAIL(TD_ERR_ARG, "td_aligner_fwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  float* ssq_part = static_cast<float*>(ws);
+  FwdWorkspace w = carve_fwd(ws, M, D);
   // sum-of-squares partials: one per 128-column half tile that exists (the last N tile may be half empty)
   const int nblk = (D + kEpiColsPerWarp - 1) / kEpiColsPerWarp;
 
@@ -303,22 +356,22 @@ int32_t td_aligner_fwd(const void* x, int64_t M, int32_t Din, int32_t D, const v
   memset(&p, 0, sizeof(p));
   p.M = int(M); p.N = D; p.K = Din; p.ld_out = D; p.alpha = 1.f;
   p.out0 = h0; p.out1 = h1; p.bias = static_cast<const __nv_bfloat16*>(b1);
-  int rc = launch_gemm<2, false, false, EPI_BIAS_GELU>({x, Din, false}, {W1, Din, false}, p, 1, st, "gemm_fwd1_bias_gelu");
+  int rc = launch_gemm<2, false, false, EPI_BIAS_GELU>({x, Din, false}, {W1, Din, false}, p, w.sk, st, "gemm_fwd1_bias_gelu");
   if (rc) return rc;
 
   memset(&p, 0, sizeof(p));
   p.M = int(M); p.N = D; p.K = D; p.ld_out = D; p.alpha = 1.f;
-  p.out0 = h2; p.bias = static_cast<const __nv_bfloat16*>(b2); p.red0 = ssq_part;
-  rc = launch_gemm<2, false, false, EPI_BIAS_SSQ>({h1, D, false}, {W2, D, false}, p, 1, st, "gemm_fwd2_bias_ssq");
+  p.out0 = h2; p.bias = static_cast<const __nv_bfloat16*>(b2); p.red0 = w.ssq_part;
+  rc = launch_gemm<2, false, false, EPI_BIAS_SSQ>({h1, D, false}, {W2, D, false}, p, w.sk, st, "gemm_fwd2_bias_ssq");
   if (rc) return rc;
 
   const int grid = grid_for_rows(M, 8, 8);
   ProfScope prof("rmsnorm_fwd", double(M) * D * (y_dtype == TD_DTYPE_BF16 ? 4.0 : 6.0), st);
   if (y_dtype == TD_DTYPE_BF16)
-    rmsnorm_fwd_kernel<true><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(h2), ssq_part, nblk, g, eps, int(M),
+    rmsnorm_fwd_kernel<true><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(h2), w.ssq_part, nblk, g, eps, int(M),
                                                    D, y, rstd);
   else
-    rmsnorm_fwd_kernel<false><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(h2), ssq_part, nblk, g, eps, int(M),
+    rmsnorm_fwd_kernel<false><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(h2), w.ssq_part, nblk, g, eps, int(M),
                                                     D, y, rstd);
   TD_CUDA(cudaGetLastError());
   return TD_OK;
@@ -332,6 +385,7 @@ struct BwdWorkspace {
   void* norm_ws;
   float* db1_part;
   int db1_rows;
+  void* sk;
   size_t bytes;
 };
 BwdWorkspace carve_bwd(void* ws, int64_t M, int32_t D) {
@@ -343,18 +397,30 @@ BwdWorkspace carve_bwd(void* ws, int64_t M, int32_t D) {
   w.norm_ws = c.take<uint8_t>((size_t)td_rmsnorm_bwd_workspace_bytes((int64_t)m, D));
   w.db1_rows = int((m + kBlockM - 1) / kBlockM + 1) * 4;  // one partial row per 32-row warp slab (+1 pair padding)
   w.db1_part = c.take<float>((size_t)w.db1_rows * D);
+  w.sk = c.take<uint8_t>(gemm_sk_workspace_bytes());
   w.bytes = c.off;
   return w;
 }
-}  // namespace
 
-int64_t td_aligner_bwd_workspace_bytes(int64_t M, int32_t Din, int32_t D) {
-  (void)Din;
-  return (int64_t)carve_bwd(nullptr, M, D).bytes;
+// The norm kernel of the fused path leaves [grid][D] dg partials, [grid][D] db2 partials and [grid] loss partials behind.
+struct NormPartials {
+  float* dg_part;
+  float* db_part;
+  float* loss_part;
+  int grid, rows_per_cta;
+  size_t bytes;
+};
+NormPartials carve_norm_partials(void* buf, int64_t M, int32_t D) {
+  NormPartials n;
+  n.grid = norm_mse_grid(M > 0 ? M : 1, &n.rows_per_cta);
+  Carver c(buf);
+  n.dg_part = c.take<float>((size_t)n.grid * D);
+  n.db_part = c.take<float>((size_t)n.grid * D);
+  n.loss_part = c.take<float>((size_t)n.grid);
+  n.bytes = c.off;
+  return n;
 }
 
-namespace {
-// Backward from dh2 (already in the workspace or caller-provided): dW2 GEMM | dh0 GEMM + db1 + dW1 GEMM.
 // Row-sharded destinations of the two weight gradients (data parallel over peer memory): dW?[o] = where the rows owned by
 // rank o go (a [D / world, cols] fp32 block in rank o's memory, this rank's slot). world == 0: plain local outputs.
 struct ScatterDst {
@@ -363,129 +429,77 @@ struct ScatterDst {
   float* dW2[kMaxPeers] = {};
 };
 
-int launch_dw_gemm(GemmOperand a, GemmOperand b, GemmParams& p, float* const* dst, int world, cudaStream_t st, const char* tag) {
-  if (world <= 0) return launch_gemm<2, true, true, EPI_F32>(a, b, p, 0, st, tag);
-  GemmScatterParams sp;
-  memset(&sp, 0, sizeof(sp));
-  static_cast<GemmParams&>(sp) = p;
-  for (int o = 0; o < world; ++o) sp.scatter_dst[o] = dst[o];
-  sp.scatter_rows = p.M / world;
-  return launch_gemm<2, true, true, EPI_F32_SCATTER>(a, b, sp, 1, st, tag);
-}
-
-// Device + pinned-host rings for tensor maps that a kernel reads from global memory (the second problem of a grouped launch).
-// 256 slots: far more than the launches that can be in flight.
-struct MapRing {
-  CUtensorMap* dev = nullptr;
-  CUtensorMap* host = nullptr;
-  std::atomic<unsigned> seq{0};
-  static constexpr unsigned kSlots = 256;
-  bool ok() {
-    if (!dev) {
-      if (cudaMalloc(&dev, sizeof(CUtensorMap) * 2 * kSlots) != cudaSuccess) return false;
-      if (cudaHostAlloc(&host, sizeof(CUtensorMap) * 2 * kSlots, cudaHostAllocDefault) != cudaSuccess) return false;
-    }
-    return true;
-  }
+struct BwdExtras {
+  float* stats = nullptr;   // inf-check counter (StepCtl)
+  int accumulate = 0;       // add into the gradient buffers (micro-batch accumulation); local outputs only
+  float* loss_out = nullptr;  // finish the fused path's deferred loss in the backward's finisher launch
+  const NormPartials* np = nullptr;
+  float loss_div = 1.f;
 };
-inline MapRing& map_ring() { static MapRing r; return r; }
 
-// dW1 and dW2 of one step as ONE launch of the scatter GEMM (shared M = weight rows, K = tokens; problem 0 tiles first).
-int launch_dw_pair_scatter(GemmOperand a1, GemmOperand b1, int N1, float* const* dst1, const float* alpha_ptr1,
-                           GemmOperand a2, GemmOperand b2, int N2, float* const* dst2, const float* alpha_ptr2,
-                           int rows, int K, float alpha, int world, cudaStream_t stream) {
-  using S = GemmSmem<2>;
-  if (rows <= 0 || N1 <= 0 || N2 <= 0 || K <= 0) TD_FAIL(TD_ERR_ARG, "grouped weight-gradient GEMM: empty problem");
-  if (N1 % 32 || N2 % 32) TD_FAIL(TD_ERR_UNSUPPORTED, "grouped weight-gradient GEMM: N must be a multiple of 32");
-  if (world < 1 || world > kMaxPeers || rows % world) TD_FAIL(TD_ERR_ARG, "grouped weight-gradient GEMM: bad world size %d", world);
-  CUtensorMap m[4];
-  int rc;
-  if ((rc = make_operand_map(&m[0], a1.ptr, rows, K, a1.ld, true, kBlockM))) return rc;
-  if ((rc = make_operand_map(&m[1], b1.ptr, N1, K, b1.ld, true, kBlockN / 2))) return rc;
-  if ((rc = make_operand_map(&m[2], a2.ptr, rows, K, a2.ld, true, kBlockM))) return rc;
-  if ((rc = make_operand_map(&m[3], b2.ptr, N2, K, b2.ld, true, kBlockN / 2))) return rc;
-  MapRing& ring = map_ring();
-  if (!ring.ok()) TD_FAIL(TD_ERR_DRIVER, "cannot allocate the tensor-map ring");
-  const unsigned slot = ring.seq.fetch_add(1) % MapRing::kSlots;
-  memcpy(ring.host + 2 * slot, &m[2], 2 * sizeof(CUtensorMap));
-  TD_CUDA(cudaMemcpyAsync(ring.dev + 2 * slot, ring.host + 2 * slot, 2 * sizeof(CUtensorMap), cudaMemcpyHostToDevice, stream));
-
-  GemmScatterParams p;
-  memset(&p, 0, sizeof(p));
-  p.M = rows; p.N = N1; p.K = K; p.ld_out = N1; p.alpha = alpha; p.alpha_ptr = alpha_ptr1;
-  p.num_m_blocks = (rows + 2 * kBlockM - 1) / (2 * kBlockM);
-  p.num_n_blocks = (N1 + kBlockN - 1) / kBlockN;
-  p.num_k_blocks = (K + kBlockK - 1) / kBlockK;
-  p.splits = 1; p.k_blocks_per_split = p.num_k_blocks;
-  p.scatter_rows = rows / world;
-  p.maps2 = ring.dev + 2 * slot;
-  p.N2 = N2; p.num_n_blocks2 = (N2 + kBlockN - 1) / kBlockN; p.ld_out2 = N2; p.alpha_ptr2 = alpha_ptr2;
-  for (int o = 0; o < world; ++o) {
-    p.scatter_dst[o] = dst1[o];
-    p.scatter_dst2[o] = dst2[o];
-  }
-  const int workers = device_sm_count() / 2;
-  const long long tiles = (long long)p.num_m_blocks * (p.num_n_blocks + p.num_n_blocks2);
-  const int grid = int(tiles < workers ? tiles : workers) * 2;
-  auto kern = gemm_bf16_kernel<2, true, true, EPI_F32_SCATTER>;
-  TD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = S::kTotal;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  p.sched_counter = next_sched_counter();
-  if (!p.sched_counter) TD_FAIL(TD_ERR_DRIVER, "cannot allocate the tile-scheduler counters");
-  ProfScope prof("gemm_dW12_scatter", 2.0 * double(rows) * double(N1 + N2) * double(K), stream);
-  TD_CUDA(cudaLaunchKernelEx(&cfg, kern, m[0], m[1], p));
-  return TD_OK;
+int launch_dw_gemm(GemmOperand a, GemmOperand b, GemmParams& p, float* const* dst, int world, void* sk, cudaStream_t st, const char* tag) {
+  if (world <= 0) return launch_gemm<2, true, true, EPI_F32>(a, b, p, sk, st, tag);
+  if (p.M % world || (p.M / world) % 32) TD_FAIL(TD_ERR_UNSUPPORTED, "row-scattered GEMM: %d rows over %d ranks must give a multiple of 32 rows per rank", p.M, world);
+  for (int o = 0; o < world; ++o) p.scatter_dst[o] = dst[o];
+  p.scatter_rows = p.M / world;
+  return launch_gemm<2, true, true, EPI_F32_SCATTER>(a, b, p, sk, st, tag);
 }
 
+// Backward from dh2 (already in the workspace or caller-provided), in this order: dh0 GEMM (+ db1 partials) -> finisher
+// (db1 | dg, db2 | loss, whichever the phases ask for, ONE launch) -> dW1 GEMM -> dW2 GEMM.
 int bwd_from_dh2(const __nv_bfloat16* dh2, const void* x, const void* h0, const void* h1, const void* W2, int64_t M,
-                 int32_t Din, int32_t D, float scale, const float* scale_ptr, float* dW1, float* db1, float* dW2,
-                 BwdWorkspace& w, int32_t phases, cudaStream_t st, const ScatterDst* sc = nullptr) {
+                 int32_t Din, int32_t D, float scale, const float* scale_ptr, float* dW1, float* db1, float* dW2, float* db2,
+                 float* dg, BwdWorkspace& w, int32_t phases, cudaStream_t st, const ScatterDst* sc, const BwdExtras& ex) {
   GemmParams p;
   const int world = sc ? sc->world : 0;
-  if (phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_W2_ONLY)) {
-    // dW2[D, D] = scale * dh2^T . h1  (contraction over tokens; both operands MN-major)
-    memset(&p, 0, sizeof(p));
-    p.M = D; p.N = D; p.K = int(M); p.ld_out = D; p.alpha = scale; p.alpha_ptr = scale_ptr; p.out0 = dW2;
-    int rc = launch_dw_gemm({dh2, D, true}, {h1, D, true}, p, sc ? sc->dW2 : nullptr, world, st,
-                            world ? "gemm_dW2_scatter" : "gemm_dW2");
-    if (rc) return rc;
-  }
-  if (phases & (TD_BWD_PHASE_GELU_W1 | TD_BWD_PHASE_GELU_ONLY)) {
+  const bool do_gelu = (phases & (TD_BWD_PHASE_GELU_W1 | TD_BWD_PHASE_GELU_ONLY)) != 0;
+  const bool do_small2 = ex.np != nullptr && (phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_SMALL2_ONLY)) != 0;
+  if (do_gelu) {
     // dh0 = bf16( bf16(scale_ptr * dh2 . W2) * gelu'(h0) ), plus per-slab column sums for db1
     memset(&p, 0, sizeof(p));
     p.M = int(M); p.N = D; p.K = D; p.ld_out = D; p.alpha = 1.f; p.alpha_ptr = scale_ptr;
     p.out0 = w.dh0; p.aux0 = h0; p.red0 = w.db1_part;
-    int rc = launch_gemm<2, false, true, EPI_DGELU>({dh2, D, false}, {W2, D, true}, p, 1, st, "gemm_dh0_dgelu");
+    int rc = launch_gemm<2, false, true, EPI_DGELU>({dh2, D, false}, {W2, D, true}, p, w.sk, st, "gemm_dh0_dgelu");
     if (rc) return rc;
-    const int slabs = int((M + 2 * kBlockM - 1) / (2 * kBlockM)) * 2 * 4;  // pair tiles: 2 slabs x 4 warps each
-    colsum_finish_kernel<<<dim3((D + 31) / 32, 1), 256, 0, st>>>(w.db1_part, db1, nullptr, nullptr, slabs, D, scale);
-    TD_CUDA(cudaGetLastError());
-    if (phases & TD_BWD_PHASE_GELU_W1) {
-      // dW1[D, Din] = scale * dh0^T . x   (dh0 already carries the upstream scalar)
-      memset(&p, 0, sizeof(p));
-      p.M = D; p.N = Din; p.K = int(M); p.ld_out = Din; p.alpha = scale; p.out0 = dW1;
-      rc = launch_dw_gemm({w.dh0, D, true}, {x, Din, true}, p, sc ? sc->dW1 : nullptr, world, st,
-                          world ? "gemm_dW1_scatter" : "gemm_dW1");
-      if (rc) return rc;
+  }
+  if (do_gelu || do_small2 || ex.loss_out != nullptr) {
+    FinishParams f;
+    memset(&f, 0, sizeof(f));
+    f.N = D; f.scale = scale; f.accumulate = ex.accumulate; f.stats = ex.stats;
+    f.scale_ptr = scale_ptr;
+    if (do_small2) {
+      // dg / db2 = (grad_scale * upstream) * column sums of the partials the fused forward pass left behind
+      f.job[f.njobs++] = FinishJob{ex.np->dg_part, dg, ex.np->grid, 1};
+      f.job[f.njobs++] = FinishJob{ex.np->db_part, db2, ex.np->grid, 1};
+    }
+    if (do_gelu) {
+      // db1's partials already carry the upstream scalar (the dh0 GEMM applied it to dh1)
+      const int slabs = int((M + 2 * kBlockM - 1) / (2 * kBlockM)) * 2 * 4;  // pair tiles: 2 slabs x 4 warps each
+      f.job[f.njobs++] = FinishJob{w.db1_part, db1, slabs, 0};
+    }
+    if (ex.loss_out != nullptr && ex.np != nullptr) {
+      f.loss_part = ex.np->loss_part; f.loss_P = ex.np->grid; f.loss_out = ex.loss_out; f.loss_div = ex.loss_div;
+    }
+    if (f.njobs > 0 || f.loss_out != nullptr) {
+      finish_kernel<<<dim3((D + 31) / 32, f.njobs + (f.loss_out ? 1 : 0)), 256, 0, st>>>(f);
+      TD_CUDA(cudaGetLastError());
     }
   }
-  if (phases & TD_BWD_PHASE_W12_GROUPED) {
-    // both weight gradients in one launch (scatter mode only; dh0 is in the workspace from an earlier GELU phase)
-    if (!world) TD_FAIL(TD_ERR_ARG, "TD_BWD_PHASE_W12_GROUPED needs td_aligner_bwd_dh2_scatter");
-    int rc = launch_dw_pair_scatter({w.dh0, D, true}, {x, Din, true}, Din, sc->dW1, nullptr, {dh2, D, true}, {h1, D, true}, D,
-                                    sc->dW2, scale_ptr, D, int(M), scale, world, st);
+  if (phases & TD_BWD_PHASE_GELU_W1) {
+    // dW1[D, Din] = scale * dh0^T . x   (dh0 already carries the upstream scalar)
+    memset(&p, 0, sizeof(p));
+    p.M = D; p.N = Din; p.K = int(M); p.ld_out = Din; p.alpha = scale; p.out0 = dW1; p.stats = ex.stats; p.accumulate = ex.accumulate;
+    int rc = launch_dw_gemm({w.dh0, D, true}, {x, Din, true}, p, sc ? sc->dW1 : nullptr, world, w.sk, st,
+                            world ? "gemm_dW1_scatter" : "gemm_dW1");
+    if (rc) return rc;
+  }
+  if (phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_W2_ONLY)) {
+    // dW2[D, D] = scale * dh2^T . h1  (contraction over tokens; both operands MN-major)
+    memset(&p, 0, sizeof(p));
+    p.M = D; p.N = D; p.K = int(M); p.ld_out = D; p.alpha = scale; p.alpha_ptr = scale_ptr; p.out0 = dW2; p.stats = ex.stats;
+    p.accumulate = ex.accumulate;
+    int rc = launch_dw_gemm({dh2, D, true}, {h1, D, true}, p, sc ? sc->dW2 : nullptr, world, w.sk, st,
+                            world ? "gemm_dW2_scatter" : "gemm_dW2");
     if (rc) return rc;
   }
   return TD_OK;
@@ -506,6 +520,11 @@ int zero_grads(int32_t Din, int32_t D, float* dW1, float* db1, float* dW2, float
 }
 }  // namespace
 
+int64_t td_aligner_bwd_workspace_bytes(int64_t M, int32_t Din, int32_t D) {
+  (void)Din;
+  return (int64_t)carve_bwd(nullptr, M, D).bytes;
+}
+
 int32_t td_aligner_bwd(const void* dy, int32_t dy_dtype, const void* x, const void* h0, const void* h1, const void* h2,
                        const float* rstd, const void* W2, const float* g, int64_t M, int32_t Din, int32_t D,
                        float grad_scale, float* dW1, float* db1, float* dW2, float* db2, float* dg, void* ws,
@@ -525,17 +544,17 @@ int32_t td_aligner_bwd(const void* dy, int32_t dy_dtype, const void* x, const vo
     if (rc) return rc;
   }
   if ((phases & TD_BWD_PHASE_GELU_W1) && (!x || !h0 || !W2 || !dW1 || !db1)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd: null pointer (phase 2)");
-  return bwd_from_dh2(w.dh2, x, h0, h1, W2, M, Din, D, grad_scale, nullptr, dW1, db1, dW2, w, phases, st);
+  BwdExtras ex;  // (dg / db2 were finished by rmsnorm_bwd_impl: no norm partials here)
+  return bwd_from_dh2(w.dh2, x, h0, h1, W2, M, Din, D, grad_scale, nullptr, dW1, db1, dW2, db2, dg, w, phases, st, nullptr, ex);
 }
 
 // ------------------------------------------------------------------------------------------------ fused aligner + MSE
 int64_t td_aligner_mse_fwd_workspace_bytes(int64_t M, int32_t Din, int32_t D) {
   const size_t m = (size_t)(M > 0 ? M : 1);
-  return td_aligner_fwd_workspace_bytes(M, Din, D) + (int64_t)align_up(sizeof(__nv_bfloat16) * m * D, 256) +
-         (int64_t)align_up(sizeof(float) * ((size_t)device_sm_count() * 2 + 8), 256) + 256;
+  return td_aligner_fwd_workspace_bytes(M, Din, D) + (int64_t)align_up(sizeof(__nv_bfloat16) * m * D, 256) + 256;
 }
 
-int64_t td_aligner_norm_partials_bytes(int64_t M, int32_t D) { return td_rmsnorm_bwd_workspace_bytes(M > 0 ? M : 1, D); }
+int64_t td_aligner_norm_partials_bytes(int64_t M, int32_t D) { return (int64_t)carve_norm_partials(nullptr, M, D).bytes; }
 
 int32_t td_aligner_mse_fwd(const void* x, int64_t M, int32_t Din, int32_t D, const void* W1, const void* b1,
                            const void* W2, const void* b2, const float* g, float eps, const void* target,
@@ -545,50 +564,48 @@ int32_t td_aligner_mse_fwd(const void* x, int64_t M, int32_t Din, int32_t D, con
   TD_DEVICE_OR_RETURN();
   if (!dims_ok(Din, D)) TD_FAIL(TD_ERR_UNSUPPORTED, "td_aligner_mse_fwd: Din=%d, D=%d must be multiples of 64 (D <= 4096)", Din, D);
   if (M <= 0 || M > 0x7fffffffll / D) TD_FAIL(TD_ERR_ARG, "td_aligner_mse_fwd: M=%lld out of range (needs at least one token)", (long long)M);
-  if (!x || !W1 || !W2 || !g || !target || !h0 || !h1 || !dh2 || !norm_partials || !loss)
+  if (!x || !W1 || !W2 || !g || !target || !h0 || !h1 || !dh2 || !norm_partials)
     TD_FAIL(TD_ERR_ARG, "td_aligner_mse_fwd: null pointer");
+  if (!(stages & TD_FWD_STAGE_DEFER_LOSS) && !loss) TD_FAIL(TD_ERR_ARG, "td_aligner_mse_fwd: loss pointer is null");
   if (ws_bytes < td_aligner_mse_fwd_workspace_bytes(M, Din, D)) TD_FAIL(TD_ERR_ARG, "td_aligner_mse_fwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  Carver c(ws);
+  FwdWorkspace w = carve_fwd(ws, M, D);
+  Carver c(static_cast<uint8_t*>(ws) + w.bytes);
   const int nparts = (D + kEpiColsPerWarp - 1) / kEpiColsPerWarp;
-  float* ssq_part = c.take<float>((size_t)(2 * ((D + kBlockN - 1) / kBlockN)) * (size_t)M);
   __nv_bfloat16* h2 = c.take<__nv_bfloat16>((size_t)M * D);
-  int rpc;
-  const int grid = norm_bwd_grid(M, &rpc);
-  float* loss_part = c.take<float>((size_t)grid);
-  Carver pc(norm_partials);  // [grid][D] dg partials, then [grid][D] db2 partials: consumed by td_aligner_bwd_dh2
-  float* dg_part = pc.take<float>((size_t)grid * D);
-  float* db_part = pc.take<float>((size_t)grid * D);
+  NormPartials np = carve_norm_partials(norm_partials, M, D);  // consumed by td_aligner_bwd_dh2
 
   GemmParams p;
   int rc;
-  if (stages & 1) {  // Linear1 + GELU (reads W1, b1 only)
+  if (stages & TD_FWD_STAGE_LINEAR1) {  // Linear1 + GELU (reads W1, b1 only)
     memset(&p, 0, sizeof(p));
     p.M = int(M); p.N = D; p.K = Din; p.ld_out = D; p.alpha = 1.f;
     p.out0 = h0; p.out1 = h1; p.bias = static_cast<const __nv_bfloat16*>(b1);
-    rc = launch_gemm<2, false, false, EPI_BIAS_GELU>({x, Din, false}, {W1, Din, false}, p, 1, st, "gemm_fwd1_bias_gelu");
+    rc = launch_gemm<2, false, false, EPI_BIAS_GELU>({x, Din, false}, {W1, Din, false}, p, w.sk, st, "gemm_fwd1_bias_gelu");
     if (rc) return rc;
   }
-  if (!(stages & 2)) return TD_OK;
+  if (!(stages & TD_FWD_STAGE_REST)) return TD_OK;
   memset(&p, 0, sizeof(p));
   p.M = int(M); p.N = D; p.K = D; p.ld_out = D; p.alpha = 1.f;
-  p.out0 = h2; p.bias = static_cast<const __nv_bfloat16*>(b2); p.red0 = ssq_part;
-  rc = launch_gemm<2, false, false, EPI_BIAS_SSQ>({h1, D, false}, {W2, D, false}, p, 1, st, "gemm_fwd2_bias_ssq");
+  p.out0 = h2; p.bias = static_cast<const __nv_bfloat16*>(b2); p.red0 = w.ssq_part;
+  rc = launch_gemm<2, false, false, EPI_BIAS_SSQ>({h1, D, false}, {W2, D, false}, p, w.sk, st, "gemm_fwd2_bias_ssq");
   if (rc) return rc;
   const float dy_coef = 2.0f / (float(M) * float(D));
   const long long* tri = reinterpret_cast<const long long*>(target_row_index);
   {
     ProfScope prof("norm_mse_bwd_fused", double(M) * D * (4.0 + (target_dtype == TD_DTYPE_BF16 ? 2.0 : 4.0)), st);
     if (target_dtype == TD_DTYPE_BF16)
-      norm_mse_bwd_kernel<true><<<grid, kNormBwdThreads, 0, st>>>(h2, ssq_part, nparts, eps, g, target, tri, int(M), D, rpc, dy_coef,
-                                                                  static_cast<__nv_bfloat16*>(dh2), dg_part, db_part, loss_part);
+      norm_mse_bwd_kernel<true><<<np.grid, kNormBwdThreads, 0, st>>>(h2, w.ssq_part, nparts, eps, g, target, tri, int(M), D, np.rows_per_cta,
+                                                                     dy_coef, static_cast<__nv_bfloat16*>(dh2), np.dg_part, np.db_part, np.loss_part);
     else
-      norm_mse_bwd_kernel<false><<<grid, kNormBwdThreads, 0, st>>>(h2, ssq_part, nparts, eps, g, target, tri, int(M), D, rpc, dy_coef,
-                                                                   static_cast<__nv_bfloat16*>(dh2), dg_part, db_part, loss_part);
+      norm_mse_bwd_kernel<false><<<np.grid, kNormBwdThreads, 0, st>>>(h2, w.ssq_part, nparts, eps, g, target, tri, int(M), D, np.rows_per_cta,
+                                                                      dy_coef, static_cast<__nv_bfloat16*>(dh2), np.dg_part, np.db_part, np.loss_part);
   }
   TD_CUDA(cudaGetLastError());
-  loss_finish_kernel<<<1, 256, 0, st>>>(loss_part, grid, nullptr, float(D), loss, float(M));
-  TD_CUDA(cudaGetLastError());
+  if (!(stages & TD_FWD_STAGE_DEFER_LOSS)) {
+    loss_finish_kernel<<<1, 256, 0, st>>>(np.loss_part, np.grid, nullptr, float(D), loss, float(M));
+    TD_CUDA(cudaGetLastError());
+  }
   return TD_OK;
 }
 
@@ -597,31 +614,32 @@ namespace {
 int bwd_dh2_impl(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
                  const void* norm_partials, int64_t M, int32_t Din, int32_t D,
                  float grad_scale, const float* grad_scale_ptr, float* dW1, float* db1, float* dW2, float* db2,
-                 float* dg, void* ws, int64_t ws_bytes, int32_t phases, td_stream_t stream, const ScatterDst* sc) {
+                 float* dg, float* loss_out, float* stats, int32_t accumulate, void* ws, int64_t ws_bytes, int32_t phases,
+                 td_stream_t stream, const ScatterDst* sc) {
   TD_DEVICE_OR_RETURN();
   if (!dims_ok(Din, D)) TD_FAIL(TD_ERR_UNSUPPORTED, "td_aligner_bwd_dh2: Din=%d, D=%d must be multiples of 64 (D <= 4096)", Din, D);
   if (M <= 0 || M > 0x7fffffffll / D) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: M=%lld out of range", (long long)M);
   if (ws_bytes < td_aligner_bwd_workspace_bytes(M, Din, D)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: workspace too small");
+  if (accumulate && sc) TD_FAIL(TD_ERR_UNSUPPORTED, "td_aligner_bwd_dh2_scatter: gradient accumulation needs local outputs");
   cudaStream_t st = (cudaStream_t)stream;
   BwdWorkspace w = carve_bwd(ws, M, D);
   if ((phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_W2_ONLY)) && (!dh2 || !h1 || !dW2))
     TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (dW2)");
-  if (phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_SMALL2_ONLY)) {
-    if (!norm_partials || !db2 || !dg) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (dg / db2)");
-    int rpc;
-    const int grid = norm_bwd_grid(M, &rpc);
-    Carver pc(const_cast<void*>(norm_partials));
-    const float* dg_part = pc.take<float>((size_t)grid * D);
-    const float* db_part = pc.take<float>((size_t)grid * D);
-    // dg / db2 = (grad_scale * upstream) * column sums of the partials the fused forward pass left behind
-    colsum_finish_kernel<<<dim3((D + 31) / 32, 2), 256, 0, st>>>(dg_part, dg, db_part, db2, grid, D, grad_scale, grad_scale_ptr);
-    TD_CUDA(cudaGetLastError());
+  NormPartials np;
+  BwdExtras ex;
+  ex.stats = stats; ex.accumulate = accumulate;
+  if ((phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_SMALL2_ONLY)) || loss_out) {
+    if (!norm_partials) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: norm_partials is null");
+    if ((phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_SMALL2_ONLY)) && (!db2 || !dg)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (dg / db2)");
+    np = carve_norm_partials(const_cast<void*>(norm_partials), M, D);
+    ex.np = &np;
+    ex.loss_out = loss_out;
+    ex.loss_div = float(M) * float(D);
   }
   if ((phases & TD_BWD_PHASE_GELU_W1) && (!x || !h0 || !W2 || !dW1 || !db1)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (phase 2)");
   if ((phases & TD_BWD_PHASE_GELU_ONLY) && (!dh2 || !h0 || !W2 || !db1)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (dh0 / db1)");
-  if ((phases & TD_BWD_PHASE_W12_GROUPED) && (!dh2 || !x || !h1 || !dW1 || !dW2)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (grouped dW)");
   return bwd_from_dh2(static_cast<const __nv_bfloat16*>(dh2), x, h0, h1, W2, M, Din, D, grad_scale, grad_scale_ptr, dW1, db1,
-                      dW2, w, phases, st, sc);
+                      dW2, db2, dg, w, phases, st, sc, ex);
 }
 }  // namespace
 extern "C" {
@@ -629,22 +647,23 @@ extern "C" {
 int32_t td_aligner_bwd_dh2(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
                            const void* norm_partials, int64_t M, int32_t Din, int32_t D,
                            float grad_scale, const float* grad_scale_ptr, float* dW1, float* db1, float* dW2, float* db2,
-                           float* dg, void* ws, int64_t ws_bytes, int32_t phases, td_stream_t stream) {
-  return bwd_dh2_impl(dh2, x, h0, h1, W2, norm_partials, M, Din, D, grad_scale, grad_scale_ptr, dW1, db1, dW2, db2, dg, ws,
-                      ws_bytes, phases, stream, nullptr);
+                           float* dg, float* loss_out, float* stats, int32_t accumulate, void* ws, int64_t ws_bytes,
+                           int32_t phases, td_stream_t stream) {
+  return bwd_dh2_impl(dh2, x, h0, h1, W2, norm_partials, M, Din, D, grad_scale, grad_scale_ptr, dW1, db1, dW2, db2, dg, loss_out,
+                      stats, accumulate, ws, ws_bytes, phases, stream, nullptr);
 }
 
 int32_t td_aligner_bwd_dh2_scatter(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
                                    const void* norm_partials, int64_t M, int32_t Din, int32_t D, float grad_scale,
                                    const float* grad_scale_ptr, float* const* dW1_dst, float* db1, float* const* dW2_dst,
-                                   float* db2, float* dg, int32_t world, void* ws, int64_t ws_bytes, int32_t phases,
-                                   td_stream_t stream) {
+                                   float* db2, float* dg, float* loss_out, float* stats, int32_t world, void* ws,
+                                   int64_t ws_bytes, int32_t phases, td_stream_t stream) {
   if (world < 1 || world > kMaxPeers || D % world)
     TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2_scatter: world=%d must be 1..%d and divide D=%d", world, kMaxPeers, D);
   ScatterDst sc;
   sc.world = world;
-  const bool need1 = (phases & (TD_BWD_PHASE_GELU_W1 | TD_BWD_PHASE_W12_GROUPED)) != 0;
-  const bool need2 = (phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_W2_ONLY | TD_BWD_PHASE_W12_GROUPED)) != 0;
+  const bool need1 = (phases & TD_BWD_PHASE_GELU_W1) != 0;
+  const bool need2 = (phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_W2_ONLY)) != 0;
   for (int o = 0; o < world; ++o) {
     if ((need1 && (!dW1_dst || !dW1_dst[o])) || (need2 && (!dW2_dst || !dW2_dst[o])))
       TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2_scatter: null destination for rank %d", o);
@@ -653,16 +672,25 @@ int32_t td_aligner_bwd_dh2_scatter(const void* dh2, const void* x, const void* h
   }
   // the impl's null checks look at dW1 / dW2: hand it the first destination
   return bwd_dh2_impl(dh2, x, h0, h1, W2, norm_partials, M, Din, D, grad_scale, grad_scale_ptr, need1 ? sc.dW1[0] : nullptr,
-                      db1, need2 ? sc.dW2[0] : nullptr, db2, dg, ws, ws_bytes, phases, stream, &sc);
+                      db1, need2 ? sc.dW2[0] : nullptr, db2, dg, loss_out, stats, 0, ws, ws_bytes, phases, stream, &sc);
 }
 
 // ------------------------------------------------------------------------------------------------ optimizer
+namespace {
+// torch computes the bias corrections in double (1 - beta ** step); so do we, on the host
+inline void bias_corrections(float beta1, float beta2, int64_t step, float* c1, float* sqrt_c2) {
+  *c1 = float(1.0 - std::pow((double)beta1, (double)step));
+  *sqrt_c2 = float(std::sqrt(1.0 - std::pow((double)beta2, (double)step)));
+}
+}  // namespace
+
 int32_t td_adamw_step(int32_t num_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                       float* const* exp_avg_sq, void* const* params_bf16, const int64_t* numel, const float* weight_decay,
-                      float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale, td_stream_t stream) {
+                      float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale, const void* step_ctl,
+                      td_stream_t stream) {
   TD_DEVICE_OR_RETURN();
   if (num_tensors < 1 || num_tensors > 3) TD_FAIL(TD_ERR_ARG, "td_adamw_step: 1..3 tensors per call, got %d", num_tensors);
-  if (step < 1) TD_FAIL(TD_ERR_ARG, "td_adamw_step: step counts from 1");
+  if (step < 1 && !step_ctl) TD_FAIL(TD_ERR_ARG, "td_adamw_step: step counts from 1");
   AdamParams a;
   memset(&a, 0, sizeof(a));
   long long max_n = 0;
@@ -677,8 +705,8 @@ int32_t td_adamw_step(int32_t num_tensors, float* const* params, const float* co
     if (numel[i] > max_n) max_n = numel[i];
   }
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_scale = grad_scale;
-  a.bias_c1 = 1.0f - powf(beta1, float(step));
-  a.sqrt_bias_c2 = sqrtf(1.0f - powf(beta2, float(step)));
+  a.ctl = static_cast<const StepCtl*>(step_ctl);
+  bias_corrections(beta1, beta2, step < 1 ? 1 : step, &a.bias_c1, &a.sqrt_bias_c2);
   if (max_n == 0) return TD_OK;
   double total = 0;
   for (int i = 0; i < num_tensors; ++i) total += double(numel[i]);
@@ -686,6 +714,42 @@ int32_t td_adamw_step(int32_t num_tensors, float* const* params, const float* co
   const int gx = grid_for_rows(max_n / 4, 256, 8);
   ProfScope prof("adamw_bf16", 30.0 * total, st);
   adamw_kernel<<<dim3(gx, num_tensors), 256, 0, st>>>(a);
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+int64_t td_step_ctl_bytes(void) { return (int64_t)align_up(sizeof(StepCtl), 64); }
+
+int32_t td_step_ctl_init(void* step_ctl, float init_scale, int64_t step, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (!step_ctl || !(init_scale > 0.f) || step < 0) TD_FAIL(TD_ERR_ARG, "td_step_ctl_init: bad arguments");
+  StepCtl h;
+  memset(&h, 0, sizeof(h));
+  h.grad_mult = 1.0f / init_scale; h.scale = init_scale; h.step = float(step);
+  h.bias_c1 = 1.f; h.sqrt_bias_c2 = 1.f;
+  // (pageable source: the copy is staged by the runtime before the call returns)
+  TD_CUDA(cudaMemcpyAsync(step_ctl, &h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return TD_OK;
+}
+
+int32_t td_step_ctl_update(void* step_ctl, const float* stats, int32_t use_scaler, float growth_factor, float backoff_factor,
+                           int32_t growth_interval, float beta1, float beta2, float max_grad_norm, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (!step_ctl) TD_FAIL(TD_ERR_ARG, "td_step_ctl_update: null control block");
+  step_ctl_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(static_cast<StepCtl*>(step_ctl), stats, use_scaler, growth_factor, backoff_factor,
+                                                     growth_interval, beta1, beta2, max_grad_norm);
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+int32_t td_grad_stats(const float* grad, int64_t numel, float* stats, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (numel < 0 || !stats || (numel > 0 && !grad)) TD_FAIL(TD_ERR_ARG, "td_grad_stats: bad arguments");
+  if (reinterpret_cast<uintptr_t>(grad) & 15) TD_FAIL(TD_ERR_ARG, "td_grad_stats: buffer must be 16-byte aligned");
+  if (numel == 0) return TD_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof("grad_stats", 4.0 * double(numel), st);
+  grad_stats_kernel<<<grid_for_rows(numel / 4 + 1, 256, 8), 256, 0, st>>>(grad, numel, stats);
   TD_CUDA(cudaGetLastError());
   return TD_OK;
 }
@@ -786,12 +850,12 @@ int32_t td_sum_slots(const float* slots, int64_t slot_stride, int32_t n_slots, f
 int32_t td_adamw_slots_step(float* param, const float* grad_slots, int64_t slot_stride, int32_t n_slots, float* exp_avg,
                             float* exp_avg_sq, void* const* params_bf16, int32_t n_dst, int64_t numel, float weight_decay,
                             float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
-                            td_stream_t stream) {
+                            const void* step_ctl, td_stream_t stream) {
   TD_DEVICE_OR_RETURN();
   if (!param || !grad_slots || !exp_avg || !exp_avg_sq || numel < 0) TD_FAIL(TD_ERR_ARG, "td_adamw_slots_step: null pointer");
   if (numel % 4 || slot_stride % 4 || slot_stride < numel || n_slots < 1)
     TD_FAIL(TD_ERR_ARG, "td_adamw_slots_step: numel / slot_stride must be multiples of 4, slot_stride >= numel, n_slots >= 1");
-  if (step < 1) TD_FAIL(TD_ERR_ARG, "td_adamw_slots_step: step counts from 1");
+  if (step < 1 && !step_ctl) TD_FAIL(TD_ERR_ARG, "td_adamw_slots_step: step counts from 1");
   AdamSlotsParams a;
   memset(&a, 0, sizeof(a));
   int rc = fill_peers(a.p_bf16, params_bf16, n_dst, "td_adamw_slots_step");
@@ -799,8 +863,8 @@ int32_t td_adamw_slots_step(float* param, const float* grad_slots, int64_t slot_
   a.p = param; a.m = exp_avg; a.v = exp_avg_sq; a.slots = grad_slots; a.slot_stride = slot_stride; a.n_slots = n_slots;
   a.n_dst = n_dst; a.n = numel; a.weight_decay = weight_decay;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_scale = grad_scale;
-  a.bias_c1 = 1.0f - powf(beta1, float(step));
-  a.sqrt_bias_c2 = sqrtf(1.0f - powf(beta2, float(step)));
+  a.ctl = static_cast<const StepCtl*>(step_ctl);
+  bias_corrections(beta1, beta2, step < 1 ? 1 : step, &a.bias_c1, &a.sqrt_bias_c2);
   if (numel == 0) return TD_OK;
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof("adamw_slots", (28.0 + 4.0 * n_slots + 2.0 * n_dst) * double(numel), st);
@@ -810,7 +874,7 @@ int32_t td_adamw_slots_step(float* param, const float* grad_slots, int64_t slot_
 }
 
 int32_t td_gemm_tn_scatter(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int32_t N, int64_t K, float alpha,
-                           float* const* dst, int32_t world, td_stream_t stream) {
+                           float* const* dst, int32_t world, void* ws, int64_t ws_bytes, td_stream_t stream) {
   TD_DEVICE_OR_RETURN();
   if (world < 1 || world > kMaxPeers || M % world) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter: world=%d must be 1..%d and divide M", world, kMaxPeers);
   if (M <= 0 || M > 0x7fffffffll || K <= 0 || K > 0x7fffffffll) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter: size out of range");
@@ -820,19 +884,7 @@ int32_t td_gemm_tn_scatter(const void* A, int64_t lda, const void* B, int64_t ld
   for (int o = 0; o < world; ++o) {
     if (!dst || !dst[o]) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter: null destination for rank %d", o);
   }
-  return launch_dw_gemm({A, lda, true}, {B, ldb, true}, p, dst, world, (cudaStream_t)stream, "gemm_tn_scatter");
-}
-
-int32_t td_gemm_tn_scatter_pair(const void* A1, int64_t lda1, const void* B1, int64_t ldb1, int32_t N1, float* const* dst1,
-                                const void* A2, int64_t lda2, const void* B2, int64_t ldb2, int32_t N2, float* const* dst2,
-                                int64_t M, int64_t K, float alpha, int32_t world, td_stream_t stream) {
-  TD_DEVICE_OR_RETURN();
-  if (M <= 0 || M > 0x7fffffffll || K <= 0 || K > 0x7fffffffll) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter_pair: size out of range");
-  if (world < 1 || world > kMaxPeers || !dst1 || !dst2) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter_pair: bad world / destinations");
-  for (int o = 0; o < world; ++o)
-    if (!dst1[o] || !dst2[o]) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter_pair: null destination for rank %d", o);
-  return launch_dw_pair_scatter({A1, lda1, true}, {B1, ldb1, true}, N1, dst1, nullptr, {A2, lda2, true}, {B2, ldb2, true}, N2, dst2,
-                                nullptr, int(M), int(K), alpha, world, (cudaStream_t)stream);
+  return launch_dw_gemm({A, lda, true}, {B, ldb, true}, p, dst, world, sk_ws_or_null(ws, ws_bytes), (cudaStream_t)stream, "gemm_tn_scatter");
 }
 
 // ------------------------------------------------------------------------------------------------ losses

@@ -43,17 +43,18 @@ __global__ void ref_gemm(const __nv_bfloat16* A, const __nv_bfloat16* B, float* 
   D[(long long)m * N + n] = acc;
 }
 
+// ws == nullptr: leftover tiles run as a last partial wave; else the stream-K tail (see gemm_sm100.cuh)
 template <int CTAS, bool A_MN, bool B_MN>
 int run_f32(const __nv_bfloat16* A, const __nv_bfloat16* B, float* D, int M, int N, int K, long long lda,
-            long long ldb, int splits, cudaStream_t st) {
+            long long ldb, void* ws, cudaStream_t st) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
   p.out0 = D; p.ld_out = N; p.alpha = 1.0f;
-  return launch_gemm<CTAS, A_MN, B_MN, EPI_F32>({A, lda, A_MN}, {B, ldb, B_MN}, p, splits, st);
+  return launch_gemm<CTAS, A_MN, B_MN, EPI_F32>({A, lda, A_MN}, {B, ldb, B_MN}, p, ws, st);
 }
 
-typedef int (*RunFn)(const __nv_bfloat16*, const __nv_bfloat16*, float*, int, int, int, long long, long long, int,
+typedef int (*RunFn)(const __nv_bfloat16*, const __nv_bfloat16*, float*, int, int, int, long long, long long, void*,
                      cudaStream_t);
 
 struct Variant { const char* name; int ctas, a_mn, b_mn; RunFn fn; };
@@ -66,13 +67,17 @@ int main(int argc, char** argv) {
       {"cta1 A:MN B:MN", 1, 1, 1, run_f32<1, true, true>},   {"cta2 A:K  B:K ", 2, 0, 0, run_f32<2, false, false>},
       {"cta2 A:K  B:MN", 2, 0, 1, run_f32<2, false, true>},  {"cta2 A:MN B:MN", 2, 1, 1, run_f32<2, true, true>},
   };
+  // splits column: 0 = no stream-K workspace, 1 = with workspace (tail tiles cut along K)
   struct Shape { int M, N, K, splits; } shapes[] = {
-      {128, 256, 64, 1}, {128, 256, 256, 1}, {256, 512, 512, 1}, {328, 768, 1096, 1}, {1000, 1024, 2048, 1},
-      {512, 512, 4096, 2}, {4096, 4096, 2056, 3},
+      {128, 256, 64, 0}, {128, 256, 256, 1}, {256, 512, 512, 1}, {328, 768, 1096, 0}, {328, 768, 1096, 1}, {1000, 1024, 2048, 1},
+      {512, 512, 4096, 1}, {4096, 4096, 2056, 0}, {4096, 4096, 2056, 1}, {4096, 3584, 1000, 1}, {2600, 4096, 1024, 1},
   };
   int fails = 0;
   cudaStream_t st;
   CK(cudaStreamCreate(&st));
+  void* sk_ws = nullptr;
+  CK(cudaMalloc(&sk_ws, gemm_sk_workspace_bytes()));
+  CK(cudaMemset(sk_ws, 0xFF, gemm_sk_workspace_bytes()));
   for (auto& sh : shapes) {
     const int M = sh.M, N = sh.N, K = sh.K;
     if (quick && (long long)M * N * K > (1ll << 31)) continue;
@@ -92,7 +97,7 @@ int main(int argc, char** argv) {
       const long long lda = v.a_mn ? M : K, ldb = v.b_mn ? N : K;
       ref_gemm<<<dim3((N + 127) / 128, M), 128, 0, st>>>(A, B, R, M, N, K, lda, ldb, v.a_mn, v.b_mn);
       CK(cudaMemsetAsync(D, 0xFF, sizeof(float) * (size_t)M * N, st));  // NaN pattern: unwritten outputs show up
-      int rc = v.fn(A, B, D, M, N, K, lda, ldb, sh.splits, st);
+      int rc = v.fn(A, B, D, M, N, K, lda, ldb, sh.splits ? sk_ws : nullptr, st);
       if (rc) { printf("[%s] M=%d N=%d K=%d launch rc=%d: %s\n", v.name, M, N, K, rc, last_error_buf()); fails++; continue; }
       cudaError_t e = cudaStreamSynchronize(st);
       if (e != cudaSuccess) {
@@ -109,7 +114,7 @@ int main(int argc, char** argv) {
         if (d > max_err || d != d) max_err = d;
         if (fabs(hr[i]) > max_ref) max_ref = fabs(hr[i]);
       }
-      printf("[%s] M=%5d N=%5d K=%5d splits=%d  max_err=%.3e (max|ref|=%.2f) bad=%lld %s\n", v.name, M, N, K, sh.splits,
+      printf("[%s] M=%5d N=%5d K=%5d streamK=%d  max_err=%.3e (max|ref|=%.2f) bad=%lld %s\n", v.name, M, N, K, sh.splits,
              max_err, max_ref, bad, bad ? "FAIL" : "ok");
       if (bad) {
         fails++;
@@ -124,10 +129,8 @@ int main(int argc, char** argv) {
   if (!quick) {
     // timing at the aligner shapes (cfg 2: M = 8224 tokens)
     struct Perf { const char* what; int M, N, K, variant; } perf[] = {
-        {"fwd1  x.W1^T      ", 8224, 4096, 3584, 0}, {"fwd1  x.W1^T  pair", 8224, 4096, 3584, 3},
-        {"dh1   dh2.W2      ", 8224, 4096, 4096, 1}, {"dh1   dh2.W2  pair", 8224, 4096, 4096, 4},
-        {"dW2   dh2^T.h1    ", 4096, 4096, 8224, 2}, {"dW2   dh2^T.h1 pair", 4096, 4096, 8224, 5},
-        {"dW1   dh0^T.x     ", 4096, 3584, 8224, 2}, {"dW1   dh0^T.x  pair", 4096, 3584, 8224, 5},
+        {"fwd1  x.W1^T  pair", 8460, 4096, 3584, 3}, {"dh1   dh2.W2  pair", 8460, 4096, 4096, 4},
+        {"dW2   dh2^T.h1 pair", 4096, 4096, 8460, 5}, {"dW1   dh0^T.x  pair", 4096, 3584, 8460, 5},
     };
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -142,17 +145,17 @@ int main(int argc, char** argv) {
       fill_bf16<<<256, 256, 0, st>>>(A, (long long)M * K, 17u, 1.0f);
       fill_bf16<<<256, 256, 0, st>>>(B, (long long)N * K, 91u, 1.0f);
       const long long lda = v.a_mn ? M : K, ldb = v.b_mn ? N : K;
-      for (int splits = 1; splits <= 2; ++splits) {
-        for (int i = 0; i < 3; ++i) v.fn(A, B, D, M, N, K, lda, ldb, splits, st);
+      for (int splits = 0; splits <= 1; ++splits) {
+        for (int i = 0; i < 3; ++i) v.fn(A, B, D, M, N, K, lda, ldb, splits ? sk_ws : nullptr, st);
         CK(cudaEventRecord(e0, st));
         const int iters = 20;
-        for (int i = 0; i < iters; ++i) v.fn(A, B, D, M, N, K, lda, ldb, splits, st);
+        for (int i = 0; i < iters; ++i) v.fn(A, B, D, M, N, K, lda, ldb, splits ? sk_ws : nullptr, st);
         CK(cudaEventRecord(e1, st));
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { printf("perf kernel failed: %s\n", cudaGetErrorString(e)); return 3; }
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         ms /= iters;
-        printf("perf %s M=%d N=%d K=%d splits=%d: %.3f ms  %.1f TFLOP/s\n", pf.what, M, N, K, splits, ms,
+        printf("perf %s M=%d N=%d K=%d streamK=%d: %.3f ms  %.1f TFLOP/s\n", pf.what, M, N, K, splits, ms,
                2.0 * M * N * K / ms * 1e-9);
       }
       cudaFree(A); cudaFree(B); cudaFree(D);

@@ -7,9 +7,10 @@ and the six products of weight >= 2^-24 are kept:
 
     a.b ~= a1.b3 + a3.b1 + a2.b2 + a1.b2 + a2.b1 + a1.b1        (smallest terms first)
 
-The six products are ONE launch of the same tcgen05 kernel: the split terms are interleaved along the contraction
-dimension in 64-element chunks (K' = 6K), and the launch is split-K so each TMEM accumulation chain stays short. This is a parity regime, not a throughput
-path (6x the MMA work): the splitting and the bias / GELU / norm elementwise steps are plain fp32 torch ops, the
+The six products run on the same tcgen05 kernel: the split terms are interleaved along the contraction dimension in
+64-element chunks (K' = 6K) and the contraction is cut into up to 16 slices, one launch each, accumulated into the fp32
+output by the kernel's TMA reduce-add store -- so each TMEM accumulation chain stays short. This is a parity regime, not a
+throughput path (6x the MMA work): the splitting and the bias / GELU / norm elementwise steps are plain fp32 torch ops, the
 contractions run on ``td_gemm_bf16_f32out``.
 """
 from __future__ import annotations
@@ -56,12 +57,20 @@ def _expand(a: torch.Tensor, pattern, k_dim: int) -> torch.Tensor:
 
 def gemm_fp32(A, B, a_mn_major: bool, b_mn_major: bool) -> torch.Tensor:
     """fp32-accurate D = A.B^T; K-major operands are [rows, K], MN-major operands [K, rows]. The contraction is cut
-    into up to 16 split-K slices whose fp32 partial sums are combined with round-to-nearest adds (red.add), keeping
-    every tensor-core accumulation chain short."""
+    into up to 16 slices (whole groups of the six split terms) whose fp32 partial sums are combined with round-to-nearest
+    adds (the kernel's reduce-add store), keeping every tensor-core accumulation chain short."""
     Ae = _expand(A, _A_PATTERN, 0 if a_mn_major else 1)
     Be = _expand(B, _B_PATTERN, 0 if b_mn_major else 1)
-    groups = (Ae.shape[0] if a_mn_major else Ae.shape[1]) // (6 * _CHUNK)
-    return ops.gemm_f32out(Ae, Be, a_mn_major, b_mn_major, splits=max(1, min(16, groups)))
+    group = 6 * _CHUNK
+    groups = (Ae.shape[0] if a_mn_major else Ae.shape[1]) // group
+    slices = max(1, min(16, groups))
+    per = (groups + slices - 1) // slices * group
+    out = None
+    for k0 in range(0, groups * group, per):
+        a = Ae[k0 : k0 + per] if a_mn_major else Ae[:, k0 : k0 + per]
+        b = Be[k0 : k0 + per] if b_mn_major else Be[:, k0 : k0 + per]
+        out = ops.gemm_f32out(a, b, a_mn_major, b_mn_major, out=out)
+    return out
 
 
 def _gelu_grad(x):

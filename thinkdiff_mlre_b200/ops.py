@@ -142,11 +142,13 @@ class AlignerBackward:
         self._call(L.BWD_GELU_W1, dW1, db1, None, None, None)
 
 
-def aligner_mse_fwd(x, W1, b1, W2, b2, g, eps: float, target, between_stages=None, target_row_index=None):
+def aligner_mse_fwd(x, W1, b1, W2, b2, g, eps: float, target, between_stages=None, target_row_index=None, defer_loss: bool = False):
     """Fused training forward against T5 targets: returns (loss, saved) with saved = (h0, h1, dh2, norm_partials), where
     dh2 / norm_partials are the T5LayerNorm backward of the MSE gradient for a unit upstream gradient (norm_partials = the
-    per-CTA partial column sums for dg / db2). ``between_stages``: optional callable run after Linear1+GELU is enqueued and
-    before anything reads W2 / b2. ``target_row_index`` (int64 [M]): row of ``target`` that belongs to each row of x."""
+    per-CTA partial column sums for dg / db2, then the per-CTA loss partials). ``between_stages``: optional callable run after
+    Linear1+GELU is enqueued and before anything reads W2 / b2. ``target_row_index`` (int64 [M]): row of ``target`` that belongs
+    to each row of x. ``defer_loss``: leave the loss un-finished -- ``AlignerBackwardFromDh2(..., loss_out=loss)`` finishes it in
+    the backward's own finisher launch (one launch fewer per training step)."""
     _need_cuda(x, W1, W2, g, target, target_row_index)
     M, Din = x.shape
     D = W1.shape[0]
@@ -162,13 +164,14 @@ def aligner_mse_fwd(x, W1, b1, W2, b2, g, eps: float, target, between_stages=Non
     loss = torch.empty((), dtype=torch.float32, device=dev)
     ws_bytes = L.lib().td_aligner_mse_fwd_workspace_bytes(M, Din, D)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-    L.launch_count += 4
+    L.launch_count += 3 if defer_loss else 4
+    extra = L.FWD_DEFER_LOSS if defer_loss else 0
 
     def call(stages):
         L.check(
             L.lib().td_aligner_mse_fwd(L.ptr(_contig(x, "x")), M, Din, D, L.ptr(W1), L.ptr(b1), L.ptr(W2), L.ptr(b2), L.ptr(g), eps,
                                        L.ptr(_contig(target, "target")), L.dtype_code(target), L.ptr(target_row_index), L.ptr(h0),
-                                       L.ptr(h1), L.ptr(dh2), L.ptr(partials), L.ptr(loss), L.ptr(ws), ws_bytes, stages, L.stream_ptr()),
+                                       L.ptr(h1), L.ptr(dh2), L.ptr(partials), L.ptr(loss), L.ptr(ws), ws_bytes, stages | extra, L.stream_ptr()),
             "td_aligner_mse_fwd",
         )
 
@@ -182,23 +185,45 @@ def aligner_mse_fwd(x, W1, b1, W2, b2, g, eps: float, target, between_stages=Non
 
 
 class AlignerBackwardFromDh2:
-    """Two-phase backward of the fused MSE path: everything is multiplied by grad_scale * upstream (a device scalar)."""
+    """Phased backward of the fused MSE path: everything is multiplied by grad_scale * upstream (a device scalar).
+    One C call per method; inside a call the launch order is dh0 GEMM, ONE finisher launch (db1 | dg, db2 | loss), dW1 GEMM,
+    dW2 GEMM. ``loss_out``: finish a loss deferred by ``aligner_mse_fwd(defer_loss=True)`` in the first finisher launch.
+    ``stats`` (fp32 [2]): non-finite gradient counter (GradScaler); ``accumulate``: add into the gradient buffers."""
 
-    def __init__(self, x, saved, W2, upstream, grad_scale: float = 1.0):
+    def __init__(self, x, saved, W2, upstream, grad_scale: float = 1.0, loss_out=None, stats=None, accumulate: bool = False):
         self.x, (self.h0, self.h1, self.dh2, self.partials), self.W2 = x, saved, W2
         self.upstream = None if upstream is None else upstream.reshape(1).to(torch.float32).contiguous()
         self.M, self.Din = x.shape
         self.D = W2.shape[0]
         self.grad_scale = float(grad_scale)
+        self.loss_out, self.stats, self.accumulate = loss_out, stats, bool(accumulate)
         self.ws_bytes = L.lib().td_aligner_bwd_workspace_bytes(self.M, self.Din, self.D)
         self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=x.device)
 
+    def _take_loss(self):
+        lo, self.loss_out = self.loss_out, None  # finished by the first call that launches a finisher
+        return lo
+
+    def _count(self, phase):
+        n = 0
+        if phase & (L.BWD_GELU_W1 | L.BWD_GELU_ONLY):
+            n += 2  # dh0 GEMM + finisher
+        elif phase & (L.BWD_NORM_W2 | L.BWD_SMALL2_ONLY):
+            n += 1  # finisher
+        if phase & L.BWD_GELU_W1:
+            n += 1
+        if phase & (L.BWD_NORM_W2 | L.BWD_W2_ONLY):
+            n += 1
+        L.launch_count += n
+
     def _call(self, phase, dW1, db1, dW2, db2, dg):
-        L.launch_count += 2 if phase == L.BWD_NORM_W2 else 3
+        self._count(phase)
+        loss_out = self._take_loss() if phase & (L.BWD_GELU_W1 | L.BWD_GELU_ONLY | L.BWD_NORM_W2 | L.BWD_SMALL2_ONLY) else None
         L.check(
             L.lib().td_aligner_bwd_dh2(L.ptr(self.dh2), L.ptr(self.x), L.ptr(self.h0), L.ptr(self.h1), L.ptr(self.W2),
                                        L.ptr(self.partials), self.M, self.Din, self.D, self.grad_scale,
                                        L.ptr(self.upstream), L.ptr(dW1), L.ptr(db1), L.ptr(dW2), L.ptr(db2), L.ptr(dg),
+                                       L.ptr(loss_out), L.ptr(self.stats), int(self.accumulate),
                                        L.ptr(self.ws), self.ws_bytes, phase, L.stream_ptr()),
             "td_aligner_bwd_dh2",
         )
@@ -209,36 +234,35 @@ class AlignerBackwardFromDh2:
     def gelu_and_linear1(self, dW1, db1):
         self._call(L.BWD_GELU_W1, dW1, db1, None, None, None)
 
+    def gelu_linear1_and_small(self, dW1, db1, db2, dg):
+        """dh0 GEMM, one finisher for all three small vectors (+ the deferred loss), dW1 GEMM."""
+        self._call(L.BWD_GELU_W1 | L.BWD_SMALL2_ONLY, dW1, db1, None, db2, dg)
+
     def norm_small(self, db2, dg):
         self._call(L.BWD_SMALL2_ONLY, None, None, None, db2, dg)
 
-    def _call_scatter(self, phase, dW1_dst, db1, dW2_dst, world):
-        L.launch_count += {L.BWD_GELU_W1: 3, L.BWD_GELU_ONLY: 2}.get(phase, 1)
+    def linear2_only(self, dW2):
+        self._call(L.BWD_W2_ONLY, None, None, dW2, None, None)
+
+    def _call_scatter(self, phase, dW1_dst, db1, dW2_dst, db2, dg, world):
+        self._count(phase)
+        loss_out = self._take_loss() if phase & (L.BWD_GELU_W1 | L.BWD_GELU_ONLY | L.BWD_NORM_W2 | L.BWD_SMALL2_ONLY) else None
         L.check(
             L.lib().td_aligner_bwd_dh2_scatter(L.ptr(self.dh2), L.ptr(self.x), L.ptr(self.h0), L.ptr(self.h1), L.ptr(self.W2),
                                                L.ptr(self.partials), self.M, self.Din, self.D, self.grad_scale,
-                                               L.ptr(self.upstream), dW1_dst, L.ptr(db1), dW2_dst, None, None, world,
+                                               L.ptr(self.upstream), dW1_dst, L.ptr(db1), dW2_dst, L.ptr(db2), L.ptr(dg),
+                                               L.ptr(loss_out), L.ptr(self.stats), world,
                                                L.ptr(self.ws), self.ws_bytes, phase, L.stream_ptr()),
             "td_aligner_bwd_dh2_scatter",
         )
 
-    def gelu_and_linear1_scatter(self, dW1_dst, db1, world: int):
-        """Phase 2 with dW1's rows stored to their owner ranks (``dW1_dst``: host array of ``world`` device pointers)."""
-        self._call_scatter(L.BWD_GELU_W1, dW1_dst, db1, None, world)
+    def gelu_linear1_small_scatter(self, dW1_dst, db1, db2, dg, world: int):
+        """As ``gelu_linear1_and_small`` with dW1's rows stored to their owner ranks (``dW1_dst``: host array of ``world``
+        device pointers)."""
+        self._call_scatter(L.BWD_GELU_W1 | L.BWD_SMALL2_ONLY, dW1_dst, db1, None, db2, dg, world)
 
     def linear2_only_scatter(self, dW2_dst, world: int):
-        self._call_scatter(L.BWD_W2_ONLY, None, None, dW2_dst, world)
-
-    def gelu_only(self, db1, world: int = 1):
-        """dh0 GEMM (+ db1) without the dW1 GEMM; dh0 stays in the workspace for ``grouped_scatter``."""
-        self._call_scatter(L.BWD_GELU_ONLY, None, db1, None, world)
-
-    def grouped_scatter(self, dW1_dst, dW2_dst, world: int):
-        """dW1 and dW2 as ONE grouped GEMM launch, rows stored to their owner ranks."""
-        self._call_scatter(L.BWD_W12_GROUPED, dW1_dst, None, dW2_dst, world)
-
-    def linear2_only(self, dW2):
-        self._call(L.BWD_W2_ONLY, None, None, dW2, None, None)
+        self._call_scatter(L.BWD_W2_ONLY, None, None, dW2_dst, None, None, world)
 
 
 def rmsnorm_fwd(x: torch.Tensor, g: torch.Tensor, eps: float = 1e-6, out_bf16: bool = False):
@@ -266,27 +290,44 @@ def rmsnorm_bwd(dy, x, rstd, g):
     return dx, dg, dxsum
 
 
-def linear_bf16(x, W, bias=None):
+def gemm_workspace(device, stream_k: bool = True):
+    """(tensor, nbytes) workspace for the stream-K tail of one GEMM launch; (None, 0) disables the tail."""
+    if not stream_k:
+        return None, 0
+    n = L.lib().td_gemm_workspace_bytes()
+    return torch.empty((n,), dtype=torch.uint8, device=device), n
+
+
+def linear_bf16(x, W, bias=None, stream_k: bool = True):
     _need_cuda(x, W)
     M, K = x.shape
     N = W.shape[0]
     out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    ws, ws_bytes = gemm_workspace(x.device, stream_k)
     L.launch_count += 1
     L.check(L.lib().td_linear_bf16(L.ptr(_contig(x, "x")), M, K, L.ptr(_contig(W, "W")), N, L.ptr(bias), L.ptr(out),
-                                   L.stream_ptr()), "td_linear_bf16")
+                                   L.ptr(ws), ws_bytes, L.stream_ptr()), "td_linear_bf16")
     return out
 
 
-def gemm_f32out(A, B, a_mn_major: bool, b_mn_major: bool, alpha: float = 1.0, cta_pair: bool = True, splits: int = 0):
-    """Test entry: D[M, N] fp32 = alpha * A.B^T; K-major operand = [rows, K], MN-major operand = [K, rows]."""
+def gemm_f32out(A, B, a_mn_major: bool, b_mn_major: bool, alpha: float = 1.0, cta_pair: bool = True, stream_k: bool = True,
+                out=None):
+    """Test entry: D[M, N] fp32 = alpha * A.B^T; K-major operand = [rows, K], MN-major operand = [K, rows].
+    ``out``: accumulate into this tensor instead of returning a fresh one."""
     _need_cuda(A, B)
     M, K = (A.shape[1], A.shape[0]) if a_mn_major else A.shape
     N = B.shape[1] if b_mn_major else B.shape[0]
-    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    accumulate = out is not None
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    ws, ws_bytes = gemm_workspace(A.device, stream_k)
     L.launch_count += 1
-    L.check(L.lib().td_gemm_bf16_f32out(L.ptr(_contig(A, "A")), A.stride(0), int(a_mn_major), L.ptr(_contig(B, "B")),
-                                        B.stride(0), int(b_mn_major), M, N, K, alpha, L.ptr(out), int(cta_pair), splits,
-                                        L.stream_ptr()), "td_gemm_bf16_f32out")
+    for t, n in ((A, "A"), (B, "B")):  # a column slice of a K-major operand is fine: TMA only needs the row pitch
+        if t.dim() != 2 or t.stride(1) != 1:
+            raise ValueError(f"{n} must be 2-D with unit inner stride")
+    L.check(L.lib().td_gemm_bf16_f32out(L.ptr(A), A.stride(0), int(a_mn_major), L.ptr(B),
+                                        B.stride(0), int(b_mn_major), M, N, K, alpha, L.ptr(out), int(cta_pair), int(accumulate),
+                                        L.ptr(ws), ws_bytes, L.stream_ptr()), "td_gemm_bf16_f32out")
     return out
 
 

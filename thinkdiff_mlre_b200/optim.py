@@ -38,15 +38,16 @@ class FusedAdamW(torch.optim.Optimizer):
         named = self._named()
         keys = ThinkDiffAligner.BUCKETS[name]
         dp = a._dp
-        if dp is None or dp.world == 1 or a._grad_flats is None or a._grad_flats.get(name) is None:
+        if a._grad_flats is None or a._grad_flats.get(name) is None:
             return {k: named[k].grad for k in keys if named[k].grad is not None}
         views = dict(zip(keys, a.bucket_grads(name)))
-        for k, v in views.items():
-            g = named[k].grad
-            if g is not None and g.data_ptr() != v.data_ptr():
-                raise RuntimeError(
-                    f"{k}.grad does not alias the all-reduced gradient bucket: data-parallel FusedAdamW supports exactly one "
-                    "backward per optimizer step (no gradient accumulation)")
+        if dp is not None and dp.world > 1:
+            for k, v in views.items():
+                g = named[k].grad
+                if g is not None and g.data_ptr() != v.data_ptr():
+                    raise RuntimeError(
+                        f"{k}.grad does not alias the all-reduced gradient bucket: autograd accumulated or cloned it (two "
+                        "backward passes per step?) -- use AlignerTrainStep(accum_grad_iters=...) for gradient accumulation")
         return views
 
     def _named(self):
@@ -69,7 +70,7 @@ class FusedAdamW(torch.optim.Optimizer):
         return g
 
     @torch.no_grad()
-    def step_bucket(self, name: str, t: int | None = None, release_grads: bool = False):
+    def step_bucket(self, name: str, t: int | None = None, release_grads: bool = False, ctl=None):
         """Update the parameters of one gradient bucket ('linear2' = 2.weight, 2.bias, 3.weight; 'linear1' = 0.weight,
         0.bias), after ordering the stream behind that bucket's all-reduce. ``t`` = optimizer step number the gradients
         belong to (defaults to the current one); ``release_grads`` drops the ``.grad`` references afterwards."""
@@ -108,7 +109,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 arr([s["exp_avg"].data_ptr() for s in states]), arr([s["exp_avg_sq"].data_ptr() for s in states]),
                 arr([bf16[k].data_ptr() if k in bf16 else None for k in keys]),
                 (C.c_int64 * n)(*[p.numel() for p in ps]), (C.c_float * n)(*[g["weight_decay"] for g in groups]),
-                g0["lr"], g0["betas"][0], g0["betas"][1], g0["eps"], t, self.grad_scale, L.stream_ptr()),
+                g0["lr"], g0["betas"][0], g0["betas"][1], g0["eps"], t, self.grad_scale, L.ptr(ctl), L.stream_ptr()),
             "td_adamw_step",
         )
         if release_grads:
@@ -144,7 +145,7 @@ class FusedAdamW(torch.optim.Optimizer):
             L.lib().td_adamw_step(1, one(W.data[lo:hi].data_ptr()), one(grads[wkey][lo:hi].data_ptr()), one(st["exp_avg"].data_ptr()),
                                   one(st["exp_avg_sq"].data_ptr()), one(Wb[lo:hi].data_ptr()), (C.c_int64 * 1)((hi - lo) * W.shape[1]),
                                   (C.c_float * 1)(g["weight_decay"]), g["lr"], g["betas"][0], g["betas"][1], g["eps"], t,
-                                  self.grad_scale, L.stream_ptr()),
+                                  self.grad_scale, None, L.stream_ptr()),
             "td_adamw_step",
         )
         ag = dp.all_gather_rows_async(Wb)
@@ -236,7 +237,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 arr([s["exp_avg"].data_ptr() for s in states]), arr([s["exp_avg_sq"].data_ptr() for s in states]),
                 arr([bf16[k].data_ptr() if k in bf16 else None for k in keys]),
                 (C.c_int64 * n)(*[p.numel() for p in ps]), (C.c_float * n)(*[g["weight_decay"] for g in groups]),
-                g0["lr"], g0["betas"][0], g0["betas"][1], g0["eps"], t, self.grad_scale, L.stream_ptr()),
+                g0["lr"], g0["betas"][0], g0["betas"][1], g0["eps"], t, self.grad_scale, None, L.stream_ptr()),
             "td_adamw_step",
         )
 
@@ -251,14 +252,132 @@ class FusedAdamW(torch.optim.Optimizer):
         a._bf16_fresh = True
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, ctl=None):
+        """``ctl``: device control block of a ``DeviceGradScaler`` -- skip / unscale / clip / bias corrections are then read on
+        the device (the host-side step counter still advances; it is only used when ``ctl`` is None)."""
         loss = closure() if closure is not None else None
         self._t += 1
         order = ("linear1", "linear2") if self.aligner._bwd_order == "linear1_first" else ("linear2", "linear1")
-        self.step_bucket(order[0])  # its all-reduce finished first; this update overlaps the other bucket's all-reduce
-        self.step_bucket(order[1])
+        self.step_bucket(order[0], ctl=ctl)  # its all-reduce finished first; this update overlaps the other bucket's all-reduce
+        self.step_bucket(order[1], ctl=ctl)
         a = self.aligner
         ps = (a[0].weight, a[0].bias, a[2].weight, a[2].bias)
         a._cache_key = tuple((p.data_ptr(), p._version) for p in ps)
         a._bf16_fresh = True
         return loss
+
+    # -- checkpointing (the reference runner saves optimizer.state_dict() on rank 0 and restores it on every rank,
+    #    thinkdiff/runners/runner_base.py:613, :662)
+    def state_dict(self):
+        """torch.optim.AdamW-compatible state: full-shape ``exp_avg`` / ``exp_avg_sq`` and a ``step`` tensor per parameter. In
+        the sharded / peer modes every rank holds the moments of its own rows only, so this is a COLLECTIVE there (the row
+        blocks are all-gathered): call it on all ranks, as ``AlignerTrainStep.flush()``."""
+        dp = self.aligner._dp
+        shards = {}
+        for p, st in self.state.items():
+            if "shard_rows" in st:
+                shards[p] = st
+        if shards:
+            import torch.distributed as dist
+
+            for p, st in shards.items():
+                full = {}
+                for k in ("exp_avg", "exp_avg_sq"):
+                    buf = torch.empty(p.shape, dtype=torch.float32, device=p.device)
+                    dist.all_gather_into_tensor(buf, st[k].contiguous(), group=dp.group)
+                    full[k] = buf
+                st["_full"] = full
+        try:
+            sd = super().state_dict()
+        finally:
+            pass
+        # super() packed the per-parameter dicts by index: patch in full-shape moments, tensor steps, drop private keys
+        packed = sd["state"]
+        index = {}
+        i = 0
+        for g in self.param_groups:
+            for p in g["params"]:
+                index[id(p)] = i
+                i += 1
+        for p, st in self.state.items():
+            ent = dict(packed.get(index[id(p)], {}))
+            if "_full" in st:
+                ent.update(st["_full"])
+            ent.pop("_full", None)
+            ent.pop("shard_rows", None)
+            if "step" in ent and not torch.is_tensor(ent["step"]):
+                ent["step"] = torch.tensor(float(ent["step"]), dtype=torch.float32)
+            packed[index[id(p)]] = ent
+        for st in shards.values():
+            st.pop("_full", None)
+        sd["fused_adamw_step"] = self._t
+        return sd
+
+    def load_state_dict(self, state_dict):
+        """Accepts this class's state and ``torch.optim.AdamW``'s (tensor ``step``). The step counter resumes from the
+        checkpoint (bias corrections continue where they stopped); full-shape moments are re-sliced to this rank's rows in
+        the sharded / peer modes."""
+        sd = dict(state_dict)
+        t = sd.pop("fused_adamw_step", None)
+        super().load_state_dict(sd)
+        steps = []
+        dp = self.aligner._dp
+        sharded = dp is not None and dp.world > 1 and (dp.sharded or dp.peer)
+        for p, st in self.state.items():
+            if "step" in st:
+                steps.append(int(float(st["step"])))
+                st["step"] = int(float(st["step"]))
+            if sharded and p.dim() == 2 and "exp_avg" in st and st["exp_avg"].shape == p.shape:
+                lo, hi = dp.shard_rows(p.shape[0])
+                st["exp_avg"] = st["exp_avg"][lo:hi].clone()
+                st["exp_avg_sq"] = st["exp_avg_sq"][lo:hi].clone()
+                st["shard_rows"] = (lo, hi)
+        self._t = int(t) if t is not None else (max(steps) if steps else 0)
+
+
+class DeviceGradScaler:
+    """``torch.amp.GradScaler`` (installed by the reference runner whenever ``amp: True``, thinkdiff/runners/runner_base.py
+    :131-139) with its state on the device and no host synchronisation: the loss scale, the growth tracker, the applied-step
+    count and the per-step decisions live in one small control block (``td_step_ctl_*``) that the backward's epilogues and
+    the AdamW kernels read directly. ``enabled=False`` keeps the scale at 1 and never skips (used for clipping /
+    accumulation without a scaler)."""
+
+    def __init__(self, device, init_scale: float = 65536.0, growth_factor: float = 2.0, backoff_factor: float = 0.5,
+                 growth_interval: int = 2000, enabled: bool = True, applied_steps: int = 0):
+        self.enabled = bool(enabled)
+        self.growth_factor, self.backoff_factor, self.growth_interval = float(growth_factor), float(backoff_factor), int(growth_interval)
+        n = int(L.lib().td_step_ctl_bytes())
+        self._block = torch.zeros((n // 4,), dtype=torch.float32, device=device)
+        self.ctl = self._block
+        L.check(L.lib().td_step_ctl_init(L.ptr(self._block), init_scale if self.enabled else 1.0, int(applied_steps), L.stream_ptr()),
+                "td_step_ctl_init")
+        # the scale as a 1-element view: passed to the backward as its upstream scalar
+        self.scale_tensor = self._block[L.STEP_CTL_SCALE_OFFSET // 4 : L.STEP_CTL_SCALE_OFFSET // 4 + 1]
+        self.stats = torch.zeros((4,), dtype=torch.float32, device=device)
+
+    def begin_step(self):
+        self.stats.zero_()
+
+    def accumulate_stats(self, *grad_flats):
+        """Non-finite count and sum of squares of the (scaled, reduced) gradients of this step."""
+        for f in grad_flats:
+            L.launch_count += 1
+            L.check(L.lib().td_grad_stats(L.ptr(f), f.numel(), L.ptr(self.stats), L.stream_ptr()), "td_grad_stats")
+
+    def update(self, optimizer, max_grad_norm: float = 0.0):
+        """``scaler.unscale_`` + ``clip_grad_norm_`` + the skip decision of ``scaler.step`` + ``scaler.update``, one tiny kernel."""
+        g = optimizer.param_groups[0]
+        L.launch_count += 1
+        L.check(L.lib().td_step_ctl_update(L.ptr(self._block), L.ptr(self.stats), int(self.enabled), self.growth_factor,
+                                           self.backoff_factor, self.growth_interval, g["betas"][0], g["betas"][1],
+                                           float(max_grad_norm), L.stream_ptr()), "td_step_ctl_update")
+
+    # host-side views (these DO synchronise; for logging / tests / checkpoints)
+    def get_scale(self) -> float:
+        return float(self.scale_tensor)
+
+    def state(self) -> dict:
+        b = self._block.cpu()
+        i = b.view(torch.int32)
+        return {"skip": int(i[0]), "grad_mult": float(b[1]), "bias_c1": float(b[2]), "sqrt_bias_c2": float(b[3]), "step": float(b[4]),
+                "scale": float(b[5]), "growth_tracker": int(i[6]), "grad_norm": float(b[7])}

@@ -1,8 +1,5 @@
 """Data parallel over NVLink peer memory: the exchange buffers and flags behind ``enable_data_parallel(peer=True)``.
 
-EXPERIMENTAL in round 1 (compiled and unit-tested for layout on the CPU; the device path is not yet validated on hardware and is
-off by default -- ``bench.py --peer`` / ``TD_TEST_PEER=1`` opt in).
-
 Reference being replaced: DDP's bucketed NCCL all-reduce of the aligner gradients and the replicated ``optimizer.step()``
 (thinkdiff/runners/runner_base.py:88-92, :98-127; thinkdiff/tasks/base_task.py:247-258). Here no collective kernel runs on the
 step at all:
@@ -120,7 +117,7 @@ class _DeviceBytes:
 class PeerExchange:
     """This rank's exchange buffer + the mapped buffers of the other ranks, and the five tiny device operations on them."""
 
-    def __init__(self, din: int, d: int, group=None, device=None, timeout_s: float = 30.0):
+    def __init__(self, din: int, d: int, group=None, device=None, timeout_s: float = 600.0):
         import torch
         import torch.distributed as dist
 
@@ -211,7 +208,7 @@ class PeerExchange:
         L.launch_count += 1
         L.check(L.lib().td_adamw_slots_step(L.ptr(param_rows), C.c_void_p(self.grad_slots_ptr(which)), n, self.world, L.ptr(exp_avg),
                                             L.ptr(exp_avg_sq), self._w_dst[which], self.world, n, weight_decay, lr, betas[0], betas[1],
-                                            eps, int(step), grad_scale, L.stream_ptr()), "td_adamw_slots_step")
+                                            eps, int(step), grad_scale, None, L.stream_ptr()), "td_adamw_slots_step")
 
     def close(self):
         torch = self.torch

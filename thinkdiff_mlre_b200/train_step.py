@@ -30,20 +30,15 @@ def make_reference_optimizer(module, lr: float = 1e-4, weight_decay: float = 0.0
 
 
 def synthetic_lvlm_batch(num_seqs: int, max_len: int, din: int, d: int, seed: int, pin: bool = True,
-                         with_target: bool = True) -> FlatBatch:
-    """BASELINE config-2 style ragged batch: kept length ``len_i ~ U{1..max_len}`` (the injected
-    split point), source length ``L_i = len_i + 1 + (i mod 32)``, bf16 N(0,1) features ``[sum L_i, din]`` and, for the
-    MSE loss, bf16 N(0,1) targets ``[sum L_i, d]`` in the same ragged source layout. Host tensors (pinned)."""
-    g = torch.Generator().manual_seed(seed)
-    lens = torch.randint(1, max_len + 1, (num_seqs,), generator=g, dtype=torch.int32)
-    full = lens.to(torch.int64) + 1 + (torch.arange(num_seqs) % 32)
-    start = torch.zeros(num_seqs, dtype=torch.int64)
-    start[1:] = torch.cumsum(full[:-1], 0)
-    rows = int(full.sum())
-    flat = torch.randn((rows, din), generator=g, dtype=torch.float32).to(torch.bfloat16)
+                         with_target: bool = True, truncated: bool = False) -> FlatBatch:
+    """BASELINE config-2 style ragged batch (``synth.lvlm_batch_tensors``) as a ``FlatBatch`` of (pinned) host tensors.
+    ``truncated``: only the kept rows are in the flat source (``FlatCollater(truncate_on_host=True)`` layout)."""
+    from .synth import lvlm_batch_tensors
+
+    flat, start, lens, target = lvlm_batch_tensors(num_seqs, max_len, din, d, seed, with_target, truncated)
     extras = {}
     if with_target:
-        extras["flat_target"] = torch.randn((rows, d), generator=g, dtype=torch.float32).to(torch.bfloat16)
+        extras["flat_target"] = target
     if pin and torch.cuda.is_available():
         flat, start, lens = flat.pin_memory(), start.pin_memory(), lens.pin_memory()
         if with_target:
@@ -52,22 +47,50 @@ def synthetic_lvlm_batch(num_seqs: int, max_len: int, din: int, d: int, seed: in
 
 
 class AlignerTrainStep:
-    """One data-parallel training step of the aligner against T5-space targets (masked MSE)."""
+    """One data-parallel training step of the aligner against T5-space targets (masked MSE).
+
+    The fused-loss step runs WITHOUT autograd: ``aligner.mse_loss_backward_packed`` enqueues forward, loss, backward and the
+    gradient exchange directly (same kernels as ``mse_loss_packed(...).backward()``), so the host cost of a step is a dozen
+    C calls. ``grad_scaler`` (a ``DeviceGradScaler``), ``max_grad_norm`` and ``accum_grad_iters`` reproduce the reference loop's
+    ``scaler.scale(loss).backward()`` / ``scaler.unscale_`` + ``clip_grad_norm_`` / ``scaler.step`` / ``scaler.update`` every
+    ``accum_grad_iters`` iterations (thinkdiff/tasks/base_task.py:241-258) with every decision taken on the device."""
 
     def __init__(self, aligner: ThinkDiffAligner, optimizer=None, loss_scale: float = 1.0, fused_loss: bool = True,
-                 pipelined: bool = False):
+                 pipelined: bool = False, grad_scaler=None, max_grad_norm: float = 0.0, accum_grad_iters: int = 1):
         self.aligner = aligner
         self.optimizer = optimizer
         self.loss_scale = float(loss_scale)  # GradScaler-style static scale (backward is linear in it)
-        self.fused_loss = fused_loss         # True: aligner.mse_loss_packed (y / dy stay on chip); False: module boundary path
+        self.fused_loss = fused_loss         # True: fused norm + loss + norm-backward (y / dy stay on chip); False: module boundary path
         # pipelined (data parallel + FusedAdamW + fused loss): the parameter updates of step i are applied inside step
         # i+1, each just before its parameter is first read -- Linear1's after the next batch is packed, Linear2's
         # between the two forward GEMMs -- so both gradient all-reduces hide behind compute. Same arithmetic, same
         # order of updates as the sequential step; call flush() before reading parameters outside the loop.
         self.pipelined = pipelined
+        self.grad_scaler = grad_scaler
+        self.max_grad_norm = float(max_grad_norm)
+        self.accum_grad_iters = int(accum_grad_iters)
+        self._micro = 0          # micro-batches accumulated so far in the current optimizer step
+        self._accum = None       # GradBuckets being accumulated into
         self._pending_t = None
         self._sharded = False
         self._peer = False
+        self._upstream = None
+        controlled = grad_scaler is not None or self.max_grad_norm > 0.0 or self.accum_grad_iters > 1
+        if controlled:
+            from .optim import FusedAdamW
+
+            if not (isinstance(optimizer, FusedAdamW) and fused_loss):
+                raise ValueError("grad_scaler / max_grad_norm / accum_grad_iters need FusedAdamW and fused_loss=True")
+            if pipelined:
+                raise ValueError("grad_scaler / max_grad_norm / accum_grad_iters: the update needs the whole step's gradient "
+                                 "statistics first -- use pipelined=False")
+            dp = aligner._dp
+            if dp is not None and dp.world > 1 and (dp.sharded or dp.peer):
+                raise NotImplementedError("grad_scaler / clipping / accumulation with sharded or peer data parallel")
+            if grad_scaler is None:
+                from .optim import DeviceGradScaler
+
+                self.grad_scaler = DeviceGradScaler(next(aligner.parameters()).device, enabled=False)
         if aligner._dp is not None and aligner._dp.peer and not pipelined:
             raise ValueError("peer data parallel needs AlignerTrainStep(pipelined=True) with FusedAdamW (the owners' AdamW "
                              "kernels are what consume the gradient slots)")
@@ -85,6 +108,18 @@ class AlignerTrainStep:
             self._ag, self._upd_done = {}, {}
             aligner._record_phase_events = not (self._sharded or self._peer)
 
+    def _upstream_scalar(self, device):
+        """Device scalar multiplied into every gradient (static loss scale), or None."""
+        if self.loss_scale == 1.0:
+            return None
+        if self._upstream is None or self._upstream.device != device:
+            self._upstream = torch.full((1,), self.loss_scale, dtype=torch.float32, device=device)
+        return self._upstream
+
+    def _fwd_bwd(self, packed, target) -> torch.Tensor:
+        return self.aligner.mse_loss_backward_packed(packed.x, *target, upstream=self._upstream_scalar(packed.x.device),
+                                                     set_grads=not self.pipelined)
+
     def step_device(self, flat, src_row_start, lens_dev, total_rows: int, l_max: int, flat_target) -> torch.Tensor:
         """Inputs already resident in HBM. Returns the (unscaled) loss as a device scalar; nothing syncs the host."""
         if self.fused_loss:
@@ -98,20 +133,62 @@ class AlignerTrainStep:
             target = ops.pack_varlen(flat_target, src_row_start, packed.cu_seqlens, total_rows)
         if self.pipelined:
             return self._step_pipelined(packed, target)
+        if self.grad_scaler is not None:
+            return self._step_controlled(packed, target)
         if self.fused_loss:
-            loss = self.aligner.mse_loss_packed(packed.x, *target)
-            (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
+            loss = self._fwd_bwd(packed, target)
         else:
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 y = self.aligner.forward_packed(packed.x, packed.cu_seqlens)
             loss, dy = ops.masked_mse_fwd_bwd(y, target, None, self.loss_scale)
             y.backward(dy)
         if self.optimizer is not None:
-            if self.loss_scale != 1.0:
+            from .optim import FusedAdamW
+
+            if isinstance(self.optimizer, FusedAdamW):
+                self.optimizer.grad_scale = 1.0 / self.loss_scale
+            elif self.loss_scale != 1.0:
                 for group in self.optimizer.param_groups:
                     torch._foreach_mul_([p.grad for p in group["params"] if p.grad is not None], 1.0 / self.loss_scale)
             self.optimizer.step()
             self.optimizer.zero_grad(set_to_none=True)
+        return loss
+
+    def _step_controlled(self, packed, target) -> torch.Tensor:
+        """The reference loop with a GradScaler / gradient clipping / accumulation (base_task.py:241-258), decisions on the
+        device: backward with the scaler's current scale as upstream scalar; on the last micro-batch the gradient statistics
+        (non-finite count, norm) are folded into the step's control block and the AdamW kernels read skip / unscale / clip /
+        bias corrections from it."""
+        a, opt, sc = self.aligner, self.optimizer, self.grad_scaler
+        dp = a._dp
+        first = self._micro == 0
+        if first:
+            sc.begin_step()
+        last = self._micro + 1 == self.accum_grad_iters
+        if self.accum_grad_iters > 1:
+            # micro-batches accumulate locally (like DDP's no_sync); the all-reduce runs once, on the last one
+            if first:
+                from .aligner import GradBuckets
+
+                self._accum = GradBuckets(a.mm_hidden_size, a.hidden_size, packed.x.device)
+                for f in self._accum.flats().values():
+                    f.zero_()
+            loss = a.mse_loss_backward_packed(packed.x, *target, upstream=sc.scale_tensor, accumulate_into=self._accum)
+            if last and dp is not None and dp.world > 1:
+                a._pending = {"linear1": dp.all_reduce_async(self._accum.linear1), "linear2": dp.all_reduce_async(self._accum.linear2)}
+        else:
+            loss = a.mse_loss_backward_packed(packed.x, *target, upstream=sc.scale_tensor)
+        self._micro += 1
+        if not last:
+            return loss
+        self._micro = 0
+        a.wait_grads()  # the statistics are taken from the REDUCED gradients, so every rank reaches the same decision
+        flats = a._grad_flats
+        sc.accumulate_stats(flats["linear1"], flats["linear2"])
+        sc.update(opt, self.max_grad_norm)
+        opt.step(ctl=sc.ctl)
+        opt.zero_grad(set_to_none=True)
+        self._accum = None
         return loss
 
     def _wait_update(self, name: str):
@@ -130,12 +207,12 @@ class AlignerTrainStep:
             self._wait_update("linear1")                                  # W1 / b1 copies are current before GEMM1
             a._between_fwd_stages = lambda: self._wait_update("linear2")  # W2 / b2 / g before GEMM2
             a._bf16_managed = True
+        # (the previous step's gradient buckets stay alive in self._grads_hold until the end of this step: by then the compute
+        #  stream is ordered after both of that step's updates, which read them on the update stream)
         try:
-            loss = a.mse_loss_packed(packed.x, *target)
+            loss = self._fwd_bwd(packed, target)
         finally:
             a._between_fwd_stages = None
-        self._grads_hold = None  # the compute stream is now ordered after both updates of the previous step
-        (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
         t = opt.next_step_number()
         self._pending_t = t
         # enqueue both buckets' updates now, on the update stream: each waits (on the device) for its reduce-scatter,
@@ -176,12 +253,12 @@ class AlignerTrainStep:
 
             a._between_fwd_stages = before_gemm2
             a._bf16_managed = True
+        # (the previous step's gradient buckets stay alive in self._grads_hold until the end of this step: by then the compute
+        #  stream is ordered after both of that step's updates, which read them on the update stream)
         try:
-            loss = a.mse_loss_packed(packed.x, *target)
+            loss = self._fwd_bwd(packed, target)
         finally:
             a._between_fwd_stages = None
-        self._grads_hold = None
-        (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
         t = opt.next_step_number()
         self._pending_t = t
         e = a._peer_epoch
@@ -212,12 +289,12 @@ class AlignerTrainStep:
             self._wait_update("linear1")                                  # W1 / b1 (+ bf16 copies) before GEMM1 reads them
             a._between_fwd_stages = lambda: self._wait_update("linear2")  # W2 / b2 / g before GEMM2
             a._bf16_managed = True
+        # (the previous step's gradient buckets stay alive in self._grads_hold until the end of this step: by then the compute
+        #  stream is ordered after both of that step's updates, which read them on the update stream)
         try:
-            loss = a.mse_loss_packed(packed.x, *target)
+            loss = self._fwd_bwd(packed, target)
         finally:
             a._between_fwd_stages = None
-        self._grads_hold = None  # the compute stream is now ordered after both updates of the previous step
-        (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
         t = opt.next_step_number()
         self._pending_t = t
         # AdamW of each bucket on the update stream, as soon as that bucket's gradients exist (and, under data parallel,
@@ -235,8 +312,11 @@ class AlignerTrainStep:
         self._grads_hold = grads  # freed only after the compute stream has waited for the updates (next step / flush)
         return loss
 
-    def flush(self):
-        """Apply the parameter updates still pending from the last pipelined step (no-op otherwise)."""
+    def flush(self, sync_masters: bool = True):
+        """Apply the parameter updates still pending from the last pipelined step (no-op otherwise). In the sharded / peer modes
+        every rank only holds current fp32 MASTER rows for its own shard (the bf16 compute copies are complete everywhere):
+        ``sync_masters`` all-gathers the masters too (collective; needed before checkpointing or reading ``.weight``) --
+        pass False inside a training loop that only needs the updates applied."""
         if self._pending_t is not None:
             if self._peer:
                 from .peer import ROW_W1, ROW_W2
@@ -246,12 +326,12 @@ class AlignerTrainStep:
                 px.wait(ROW_W2, e)
                 self._wait_update("linear1")
                 self._grads_hold = None
-                self.aligner.sync_parameters()  # fp32 master rows of the other ranks (NCCL all-gather, off the hot path)
+                self._masters_stale = True
             elif self._sharded:
                 self._wait_update("linear1")
                 self._wait_update("linear2")
                 self._grads_hold = None
-                self.aligner.sync_parameters()  # fp32 master rows of the other ranks
+                self._masters_stale = True
             else:
                 self._wait_update("linear1")
                 self._wait_update("linear2")
@@ -259,6 +339,9 @@ class AlignerTrainStep:
             self.optimizer.mark_bf16_current()
             self._pending_t = None
             self.aligner._bf16_managed = False
+        if sync_masters and getattr(self, "_masters_stale", False):
+            self.aligner.sync_parameters()  # fp32 master rows of the other ranks (NCCL all-gather, off the hot path)
+            self._masters_stale = False
 
     # -- host-fed path with the copy of batch i+1 overlapping the compute of batch i (what the reference's PrefetchLoader
     #    does on a side stream, thinkdiff/datasets/datasets/dataloader_utils.py:45-118)
