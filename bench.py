@@ -115,25 +115,35 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def bind_to_gpu_numa_node(index: int):
-    """Pin this process (and the pinned host buffers it is about to allocate: first touch) to the CPUs NVML reports as local to
-    GPU `index`, so every rank's H2D copies start from its own NUMA node. Returns the number of CPUs kept, or None."""
-    try:
-        import pynvml
+class numa_local:
+    """While active, this process runs on the CPUs NVML reports as local to GPU `index`: pinned host buffers allocated inside
+    (first touch) land on the GPU's own NUMA node, so every rank's H2D copies start next to its PCIe root. `cpus` = how many
+    CPUs were kept (None: NVML or the affinity call is unavailable, nothing changed)."""
 
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        words = (os.cpu_count() + 63) // 64
-        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
-        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
-        allowed = os.sched_getaffinity(0)
-        cpus &= allowed
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return len(cpus)
-    except Exception:
-        pass
-    return None
+    def __init__(self, index: int):
+        self.index, self.cpus, self._saved = index, None, None
+
+    def __enter__(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+            cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+            allowed = os.sched_getaffinity(0)
+            cpus &= allowed
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                self._saved, self.cpus = allowed, len(cpus)
+        except Exception:
+            pass
+        return self
+
+    def __exit__(self, *a):
+        if self._saved is not None:
+            os.sched_setaffinity(0, self._saved)
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference arm
@@ -169,7 +179,7 @@ def cpu_reference_run(steps: int, warmup: int, din: int, seqs: int, max_len: int
         loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
-        return float(loss)
+        return float(loss.detach())
 
     for _ in range(warmup):
         step()
@@ -322,7 +332,10 @@ def dp_parity_check(td, dist, dev, world, rank, mode):
             step.step_device(b.flat.to(dev), b.src_row_start.to(dev), b.lens.to(dev), b.total_rows, b.l_max, b.extras["flat_target"].to(dev))
         step.flush()
         torch.cuda.synchronize()
-        return [p.detach().clone() for p in m.parameters()], m
+        params = [p.detach().clone() for p in m.parameters()]
+        if m._peer is not None:
+            m._peer.close()  # (collective: nobody still stores into a buffer that is about to be unmapped)
+        return params, m
 
     plain, _ = run("plain")
     tested, _ = run(mode)
@@ -408,8 +421,6 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    numa_cpus = bind_to_gpu_numa_node(local)  # before any pinned allocation
-
     import torch
     import torch.distributed as dist
 
@@ -424,6 +435,10 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    elif args.dp in ("peer", "sharded"):  # developer aid: the multi-GPU code path degenerated to one rank
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29577")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
     warmup = max(args.warmup, 3)
     steps = args.steps
     din, seqs, max_len, num_batches = WORKLOADS[args.workload]
@@ -457,7 +472,7 @@ def main():
     fused = args.optimizer == "fused" and args.loss_path == "fused"
     pipelined = fused and not args.no_pipeline
     dp_mode = None
-    if world > 1:
+    if world > 1 or args.dp in ("peer", "sharded"):
         dp_mode = "peer" if args.dp == "auto" else args.dp
         if not (pipelined and D % world == 0) and dp_mode in ("peer", "sharded"):
             dp_mode = "allreduce"
@@ -466,7 +481,9 @@ def main():
     opt = td.FusedAdamW(aligner, lr=1e-4, weight_decay=0.05) if args.optimizer == "fused" else make_reference_optimizer(aligner)
     stepper = td.AlignerTrainStep(aligner, opt, fused_loss=args.loss_path == "fused", pipelined=pipelined)
 
-    host = [td.synthetic_lvlm_batch(seqs, max_len, din, D, seed=1234 + rank + 1000 * j) for j in range(num_batches)]
+    with numa_local(local) as numa:
+        host = [td.synthetic_lvlm_batch(seqs, max_len, din, D, seed=1234 + rank + 1000 * j) for j in range(num_batches)]
+    numa_cpus = numa.cpus
     resident = [(b.flat.to(dev), b.src_row_start.to(dev), b.lens.to(dev), b.total_rows, b.l_max, b.extras["flat_target"].to(dev)) for b in host]
     tokens_per_step = [b.total_rows for b in host]
 
@@ -500,7 +517,8 @@ def main():
     if not args.no_e2e:
         # what the collater ships: only the kept rows of every sample (FlatCollater(truncate_on_host=True), the reference
         # collater's [:split_point] done in the DataLoader worker) -- the device pack then re-packs contiguous rows
-        host_t = [td.synthetic_lvlm_batch(seqs, max_len, din, D, seed=1234 + rank + 1000 * j, truncated=True) for j in range(num_batches)]
+        with numa_local(local):
+            host_t = [td.synthetic_lvlm_batch(seqs, max_len, din, D, seed=1234 + rank + 1000 * j, truncated=True) for j in range(num_batches)]
         for i in range(3):
             float(stepper.step_host(host_t[i % num_batches], dev))
         sync_all()
@@ -567,7 +585,7 @@ def main():
     # ---- per-kernel device times (separate pass of the same steps; CUDA events around every launch) --
     psteps = min(steps, 20)
     prof_stepper, profile_pass = stepper, "same pipelined step (kernels of different streams overlap: per-launch times are upper bounds)"
-    if world == 1 and pipelined:
+    if world == 1 and pipelined and dp_mode is None:
         # one stream, no overlap between the AdamW side stream and the GEMMs: clean per-kernel times for the roofline
         stepper.flush()
         aligner._bwd_order, aligner._record_phase_events = "linear2_first", False
@@ -650,7 +668,7 @@ def main():
                 json.dump({"kernels": kernels, "kernel_ms_per_step": total_ms, "ms_per_step": ms / steps, "peaks": peaks}, f, indent=1)
         emit(line)
         ok = dp_parity is None or dp_parity["ok"]
-    if world > 1:
+    if dist.is_initialized():
         dist.destroy_process_group()
     if not ok:
         print("bench.py: dp_parity FAILED", dp_parity, file=sys.stderr)

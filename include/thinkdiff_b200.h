@@ -183,7 +183,9 @@ int32_t td_peer_open(const uint8_t* handle /*[host]*/, void** ptr /*[host] out*/
 int32_t td_peer_close(void* ptr);
 /* flag_arrays[i][slot] = value at every rank i (release, system scope), ordered after all earlier work on `stream`. */
 int32_t td_peer_signal(void* const* flag_arrays /*[host]*/, int32_t n, int32_t slot, int32_t value, td_stream_t stream);
-/* Blocks `stream` until flags[0..n) >= value (local int32 flags written by the peers). Traps after timeout_s (<= 0: 30 s). */
+/* Blocks `stream` until flags[0..n) >= value (local int32 flags written by the peers). Implemented with stream memory operations
+ * (cuStreamWaitValue32: no kernel occupies an SM while waiting; a peer that never signals blocks the stream, as a lost NCCL rank
+ * would); with TD_PEER_WAIT=kernel a polling kernel is used instead, which traps after timeout_s (<= 0: 600 s). */
 int32_t td_peer_wait(const int32_t* flags, int32_t n, int32_t value, float timeout_s, td_stream_t stream);
 /* dst[i][0..numel) = src[0..numel) for every rank i (the three small gradient vectors: every rank gets every rank's copy). */
 int32_t td_peer_post(const float* src, void* const* dst /*[host]*/, int32_t n, int64_t numel, td_stream_t stream);

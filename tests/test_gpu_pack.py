@@ -67,6 +67,37 @@ def test_pack_matches_reference_collater_golden():
     np.testing.assert_array_equal(mask.cpu().numpy(), g["out_mask"])
 
 
+def test_reference_dict_reproduces_the_reference_collater_output_for_both_streams():
+    """FlatCollater.reference_dict == the dict the reference collater returns (golden), both embed streams of one call padded on
+    the device, int64 masks, pass-through lists."""
+    import random
+
+    import thinkdiff_mlre_b200 as td
+    from oracle.golden import load_golden
+
+    g = load_golden("collater_input_embed.npz")
+    bi = {k[3:]: int(v) for k, v in g.items() if k.startswith("bi_")}
+    full = [int(v) for v in g["full_lens"]]
+    off = np.concatenate([[0], np.cumsum(full)])
+    samples = []
+    for i in range(len(full)):
+        e = torch.from_numpy(g["src_bits"][off[i] : off[i + 1]].view(np.int16).copy()).view(torch.bfloat16)
+        ids = [int(v) for v in g["src_ids_flat"][off[i] : off[i + 1]]]
+        samples.append({"json": {"generated_text": f"t{i}", "output_token_ids": ids, "gpt": f"g{i}"},
+                        "model.norm.input_embed.pth": e, "model.norm.output_embed.pth": e})
+    random.seed(int(g["seed"]))
+    out = td.FlatCollater.reference_dict(td.FlatCollater(bi)(samples), "cuda")
+    assert set(out) == {"generated_texts", "output_token_ids", "llava_gpts", "model.norm.input_embed", "input_embed_mask",
+                        "model.norm.output_embed", "output_embed_mask"}
+    np.testing.assert_array_equal(_u16(out["model.norm.output_embed"]), g["out_embed_bits"])
+    np.testing.assert_array_equal(out["output_embed_mask"].cpu().numpy(), g["out_mask"])
+    np.testing.assert_array_equal(_u16(out["model.norm.input_embed"]), g["in_embed_bits"])
+    np.testing.assert_array_equal(out["input_embed_mask"].cpu().numpy(), g["in_mask"])
+    assert out["output_embed_mask"].dtype == torch.int64 and out["llava_gpts"] == [f"g{i}" for i in range(len(full))]
+    ids = [list(map(int, g["ids_flat"][g["ids_off"][i] : g["ids_off"][i + 1]])) for i in range(len(full))]
+    assert [list(map(int, t)) for t in out["output_token_ids"]] == ids
+
+
 def test_pack_fp32_rows_and_int_payloads():
     import thinkdiff_mlre_b200 as td
 

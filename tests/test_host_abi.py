@@ -155,6 +155,34 @@ def test_flat_collater_input_branch_and_errors():
         td.kept_lengths([1], dict(random_split_output_embed=1, output_embed_max_split_len=4))
 
 
+def test_flat_collater_dual_stream_and_pass_through_keys():
+    """use_input_embed and use_output_embed both set: the reference returns both padded tensors from one call, and passes the
+    `gpt` / `revised_generated_text` lists through when the samples carry them (...mllama_embed_2.py:38-46, :64-99, :172-181)."""
+    g = load_golden("collater_input_embed.npz")
+    bi = {k[3:]: int(v) for k, v in g.items() if k.startswith("bi_")}
+    assert bi["use_input_embed"] and bi["use_output_embed"]
+    samples = _samples_from_golden(g)
+    for i, s_ in enumerate(samples):
+        s_["json"]["gpt"] = f"answer {i}"
+        s_["json"]["revised_generated_text"] = f"revised {i}"
+    random.seed(int(g["seed"]))
+    fb = td.FlatCollater(bi, pin_memory=False)(samples)
+    fin = fb.extras["input_batch"]
+    for batch, embed_bits, mask, key in ((fb, g["out_embed_bits"], g["out_mask"], "model.norm.output_embed"),
+                                         (fin, g["in_embed_bits"], g["in_mask"], "model.norm.input_embed")):
+        bits = batch.flat.view(torch.int16).numpy().view(np.uint16)
+        packed, cu = pack_ref.pack_from_flat(bits, batch.src_row_start.tolist(), batch.lens.tolist())
+        padded, m = pack_ref.unpack_padded(packed, cu, batch.l_max)
+        np.testing.assert_array_equal(padded, embed_bits)
+        np.testing.assert_array_equal(m, mask)
+        assert batch.extras["embed_key"] == key
+    assert fb.extras["mask_key"] == "output_embed_mask" and fin.extras["mask_key"] == "input_embed_mask"
+    assert fb.extras["llava_gpts"] == [f"answer {i}" for i in range(len(samples))]
+    assert fb.extras["revised_generated_texts"] == [f"revised {i}" for i in range(len(samples))]
+    plain = td.FlatCollater(bi, pin_memory=False, which="output")(_samples_from_golden(g))
+    assert "llava_gpts" not in plain.extras and "revised_generated_texts" not in plain.extras and "input_batch" not in plain.extras
+
+
 def test_synthetic_batch_shape_contract():
     b = td.synthetic_lvlm_batch(64, 256, 128, 64, seed=1234, pin=False)
     assert b.flat.shape[1] == 128 and b.extras["flat_target"].shape == (b.flat.shape[0], 64)

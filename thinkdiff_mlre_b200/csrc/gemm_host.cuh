@@ -65,7 +65,10 @@ struct DeviceState {
   int cc_major = -1;
   int* sk_flags = nullptr;  // pool of zeroed stream-K flag blocks, one block per launch, re-armed by the kernels
   std::atomic<unsigned> sk_seq{0};
+  int* sched = nullptr;     // pool of {next unit, finished workers} counter pairs for the dynamic tile scheduler
+  std::atomic<unsigned> sched_seq{0};
 };
+constexpr unsigned kSchedPairs = 1024;                       // a pair is re-armed (zeroed) by the kernel that used it
 constexpr unsigned kSkFlagSlots = 256;                       // far more launches than can be in flight at once
 constexpr int kSkFlagsPerSlot = 148 * kEpiWarps;             // [workers][CTAS][8] with workers * CTAS <= 148
 
@@ -112,6 +115,22 @@ inline int* next_sk_flags() {
     }
   }
   return s->sk_flags + (size_t)(s->sk_seq.fetch_add(1) % kSkFlagSlots) * kSkFlagsPerSlot;
+}
+
+// Every launch takes the next counter pair; no per-launch memset is needed.
+inline int* next_sched_counter() {
+  DeviceState* s = device_state();
+  if (!s) return nullptr;
+  if (!s->sched) {
+    std::lock_guard<std::mutex> lock(s->mu);
+    if (!s->sched) {
+      int* p = nullptr;
+      if (cudaMalloc(&p, sizeof(int) * 2 * kSchedPairs) != cudaSuccess) return nullptr;
+      if (cudaMemset(p, 0, sizeof(int) * 2 * kSchedPairs) != cudaSuccess) return nullptr;
+      s->sched = p;
+    }
+  }
+  return s->sched + 2 * (s->sched_seq.fetch_add(1) % kSchedPairs);
 }
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -221,7 +240,8 @@ int launch_gemm(GemmOperand a, GemmOperand b, GemmParams p, void* ws, cudaStream
   if (p.N % 32) TD_FAIL(TD_ERR_UNSUPPORTED, "GEMM N=%d must be a multiple of 32", p.N);
   if (p.K <= 0) TD_FAIL(TD_ERR_ARG, "GEMM K=%d must be positive (caller zero-fills empty contractions)", p.K);
   CUtensorMap ma, mb, mo0, mo1, maux;
-  memset(&mo0, 0, sizeof(mo0)); memset(&mo1, 0, sizeof(mo1)); memset(&maux, 0, sizeof(maux));
+  ScatterMaps smaps;
+  memset(&mo0, 0, sizeof(mo0)); memset(&mo1, 0, sizeof(mo1)); memset(&maux, 0, sizeof(maux)); memset(&smaps, 0, sizeof(smaps));
   int rc = make_operand_map(&ma, a.ptr, p.M, p.K, a.ld, A_MN, kBlockM);
   if (rc) return rc;
   rc = make_operand_map(&mb, b.ptr, p.N, p.K, b.ld, B_MN, kBlockN / CTAS);
@@ -234,6 +254,14 @@ int launch_gemm(GemmOperand a, GemmOperand b, GemmParams p, void* ws, cudaStream
     rc = make_epilogue_map(&mo1, p.out1, p.M, p.N, p.ld_out, false);
     if (rc) return rc;
   }
+  if (EPI == EPI_F32_SCATTER) {
+    if (p.scatter_rows <= 0 || p.scatter_rows % 32 || p.M % p.scatter_rows || p.M / p.scatter_rows > kMaxPeers)
+      TD_FAIL(TD_ERR_ARG, "row-scattered GEMM: %d rows per owner must be a multiple of 32 and divide M=%d into at most %d blocks", p.scatter_rows, p.M, kMaxPeers);
+    for (int o = 0; o < p.M / p.scatter_rows; ++o) {
+      rc = make_epilogue_map(&smaps.m[o], p.scatter_dst[o], p.scatter_rows, p.N, p.ld_out, true);
+      if (rc) return rc;
+    }
+  }
   if (EPI == EPI_DGELU) {
     rc = make_epilogue_map(&maux, p.aux0, p.M, p.N, p.ld_out, false);
     if (rc) return rc;
@@ -243,6 +271,8 @@ int launch_gemm(GemmOperand a, GemmOperand b, GemmParams p, void* ws, cudaStream
   p.num_k_blocks = (p.K + kBlockK - 1) / kBlockK;
   plan_schedule(p, device_sm_count() / CTAS, ws != nullptr);
   p.sk_partials = static_cast<float*>(ws);
+  p.sched_counter = next_sched_counter();
+  if (!p.sched_counter) TD_FAIL(TD_ERR_DRIVER, "cannot allocate the tile-scheduler counters");
   p.sk_flags = nullptr;
   if (p.tail_workers > 0) {
     p.sk_flags = next_sk_flags();
@@ -271,7 +301,7 @@ int launch_gemm(GemmOperand a, GemmOperand b, GemmParams p, void* ws, cudaStream
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfScope prof(tag, 2.0 * double(p.M) * double(p.N) * double(p.K), stream);
-  TD_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo0, mo1, maux, p));
+  TD_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo0, mo1, maux, smaps, p));
   return TD_OK;
 }
 

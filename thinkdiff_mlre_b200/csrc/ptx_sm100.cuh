@@ -115,17 +115,25 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// Wait until another CTA of this grid has stored a non-zero value (release) to *p. Same 4 s trap as the mbarrier waits.
+// Wait until another CTA of this grid has stored a non-zero value (release) to *p: relaxed polls, one acquire fence at the end
+// (an acquire load per iteration would invalidate L1 every time). Same 4 s trap as the mbarrier waits.
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void spin_until_set(const int* p) {
-  if (ld_acquire_gpu(p) != 0) return;
-  const uint64_t t0 = global_timer_ns();
-  while (ld_acquire_gpu(p) == 0) {
-    __nanosleep(64);
-    if (global_timer_ns() - t0 > TD_MBAR_TIMEOUT_NS) {
-      printf("td: stream-K flag timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
-      __trap();
+  if (ld_relaxed_gpu(p) == 0) {
+    const uint64_t t0 = global_timer_ns();
+    while (ld_relaxed_gpu(p) == 0) {
+      __nanosleep(64);
+      if (global_timer_ns() - t0 > TD_MBAR_TIMEOUT_NS) {
+        printf("td: stream-K flag timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
     }
   }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
 // ---------------------------------------------------------------- cluster

@@ -35,6 +35,23 @@ __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
   __stcs(p, v);
 #endif
 }
+// 256-bit streaming accesses (sm_100: LDG/STG .256) that are dropped from L2 first: for data touched once per step (optimizer
+// state, gradients) next to GEMM operands that should stay resident.
+__device__ __forceinline__ void ld256_evict_first(const float* p, float (&r)[8]) {
+  uint32_t u[8];
+  asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "l"(p));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void st256_evict_first(float* p, const float (&r)[8]) {
+  asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p),
+               "r"(__float_as_uint(r[0])), "r"(__float_as_uint(r[1])), "r"(__float_as_uint(r[2])), "r"(__float_as_uint(r[3])),
+               "r"(__float_as_uint(r[4])), "r"(__float_as_uint(r[5])), "r"(__float_as_uint(r[6])), "r"(__float_as_uint(r[7]))
+               : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -409,6 +426,45 @@ adamw_kernel(const AdamParams a) {
   }
 }
 
+// The same update on 8 parameters per thread and iteration with 256-bit accesses (all sizes and addresses multiples of 32 bytes):
+// half the memory instructions, and p / g / m / v are marked evict-first in L2 -- they are not needed again before the next
+// optimizer step, while the bf16 copy written last is read by the very next forward GEMM and keeps the default policy.
+__global__ void __launch_bounds__(256)
+adamw256_kernel(const AdamParams a) {
+  const AdamSegment s = a.seg[blockIdx.y];
+  const long long n8 = s.n >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float bias_c1 = a.bias_c1, sqrt_bias_c2 = a.sqrt_bias_c2, grad_scale = a.grad_scale;
+  if (a.ctl != nullptr) {
+    if (a.ctl->skip) return;
+    bias_c1 = a.ctl->bias_c1; sqrt_bias_c2 = a.ctl->sqrt_bias_c2; grad_scale *= a.ctl->grad_mult;
+  }
+  const float decay = 1.0f - a.lr * s.weight_decay;
+  const float step_size = a.lr / bias_c1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    float pp[8], gg[8], mm[8], vv[8];
+    ld256_evict_first(s.p + 8 * i, pp);
+    ld256_evict_first(s.g + 8 * i, gg);
+    ld256_evict_first(s.m + 8 * i, mm);
+    ld256_evict_first(s.v + 8 * i, vv);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float g = gg[q] * grad_scale;
+      pp[q] *= decay;
+      mm[q] = a.beta1 * mm[q] + (1.0f - a.beta1) * g;
+      vv[q] = a.beta2 * vv[q] + (1.0f - a.beta2) * g * g;
+      const float denom = sqrtf(vv[q]) / sqrt_bias_c2 + a.eps;
+      pp[q] -= step_size * (mm[q] / denom);
+    }
+    st256_evict_first(s.p + 8 * i, pp);
+    st256_evict_first(s.m + 8 * i, mm);
+    st256_evict_first(s.v + 8 * i, vv);
+    if (s.p_bf16 != nullptr)
+      reinterpret_cast<uint4*>(s.p_bf16)[i] = make_uint4(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]), pack_bf16x2(pp[4], pp[5]),
+                                                        pack_bf16x2(pp[6], pp[7]));
+  }
+}
+
 // One thread: fold this step's gradient statistics into the control block.
 //   stats[0] = number of non-finite gradient values seen (summed over ranks), stats[1] = sum of squares of the SCALED gradients
 //   (only when clipping). use_scaler = 0: scale stays 1 and nothing is ever skipped (but a clip still applies).
@@ -507,6 +563,7 @@ norm_mse_bwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restric
   constexpr int PF = T_BF16 ? 2 : 1;  // iterations of loads in flight beyond the one being computed
   constexpr int NB = PF + 1;
   constexpr int NW = kNormBwdThreads / 32;
+  static_assert(NW == 16, "the partial-sum butterfly assumes 16 warps");
   __shared__ float red[2][R][NW];
   __shared__ float lred[NW];
   __shared__ float rs_sm[kNormMseMaxRows];
@@ -603,9 +660,10 @@ norm_mse_bwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restric
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const int row = rr + r;
-            float tot = 0.f;
+            // the 16 warp partials: one shared-memory read per lane, then a 4-step butterfly (same tree in every warp)
+            float tot = red[par][r][lane & (NW - 1)];
 #pragma unroll
-            for (int i = 0; i < NW; ++i) tot += red[par][r][i];  // broadcast reads, same order in every thread
+            for (int o = NW / 2; o >= 1; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
             if (row < b1 && col_ok) {
               const float rstd = rs[r];
               const float c = tot * inv_d * rstd * rstd * rstd;

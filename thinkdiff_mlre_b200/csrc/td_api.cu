@@ -694,12 +694,15 @@ int32_t td_adamw_step(int32_t num_tensors, float* const* params, const float* co
   AdamParams a;
   memset(&a, 0, sizeof(a));
   long long max_n = 0;
+  bool wide = true;  // every tensor a multiple of 8 elements at 32-byte aligned addresses: 256-bit kernel
   for (int i = 0; i < num_tensors; ++i) {
     if (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i] || numel[i] < 0) TD_FAIL(TD_ERR_ARG, "td_adamw_step: null pointer");
     if (numel[i] % 4) TD_FAIL(TD_ERR_UNSUPPORTED, "td_adamw_step: tensor sizes must be multiples of 4 (got %lld)", (long long)numel[i]);
     const uintptr_t bits = reinterpret_cast<uintptr_t>(params[i]) | reinterpret_cast<uintptr_t>(grads[i]) |
                            reinterpret_cast<uintptr_t>(exp_avg[i]) | reinterpret_cast<uintptr_t>(exp_avg_sq[i]);
     if (bits & 15) TD_FAIL(TD_ERR_ARG, "td_adamw_step: buffers must be 16-byte aligned");
+    const uintptr_t b16 = reinterpret_cast<uintptr_t>(params_bf16 ? params_bf16[i] : nullptr);
+    wide = wide && !(bits & 31) && !(b16 & 15) && numel[i] % 8 == 0;
     a.seg[i] = AdamSegment{params[i], grads[i], exp_avg[i], exp_avg_sq[i],
                            static_cast<__nv_bfloat16*>(params_bf16 ? params_bf16[i] : nullptr), numel[i], weight_decay[i]};
     if (numel[i] > max_n) max_n = numel[i];
@@ -711,9 +714,9 @@ int32_t td_adamw_step(int32_t num_tensors, float* const* params, const float* co
   double total = 0;
   for (int i = 0; i < num_tensors; ++i) total += double(numel[i]);
   cudaStream_t st = (cudaStream_t)stream;
-  const int gx = grid_for_rows(max_n / 4, 256, 8);
   ProfScope prof("adamw_bf16", 30.0 * total, st);
-  adamw_kernel<<<dim3(gx, num_tensors), 256, 0, st>>>(a);
+  if (wide) adamw256_kernel<<<dim3(grid_for_rows(max_n / 8, 256, 8), num_tensors), 256, 0, st>>>(a);
+  else adamw_kernel<<<dim3(grid_for_rows(max_n / 4, 256, 8), num_tensors), 256, 0, st>>>(a);
   TD_CUDA(cudaGetLastError());
   return TD_OK;
 }
@@ -815,10 +818,37 @@ int32_t td_peer_signal(void* const* flag_arrays, int32_t n, int32_t slot, int32_
   return TD_OK;
 }
 
+namespace {
+// Stream memory operations (driver API, resolved at run time): the stream itself waits until a 32-bit word in device memory
+// reaches a value -- no kernel, no SM, nothing that could keep a CTA pair of a persistent GEMM from becoming resident.
+typedef CUresult (*PFN_streamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+inline PFN_streamWaitValue32 stream_wait_fn() {
+  static PFN_streamWaitValue32 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* mode = getenv("TD_PEER_WAIT");
+    if (mode && !strcmp(mode, "kernel")) return;  // developer override: the spinning wait kernel
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_streamWaitValue32>(p);
+  });
+  return fn;
+}
+}  // namespace
+
 int32_t td_peer_wait(const int32_t* flags, int32_t n, int32_t value, float timeout_s, td_stream_t stream) {
   TD_DEVICE_OR_RETURN();
   if (!flags || n < 1 || n > 32) TD_FAIL(TD_ERR_ARG, "td_peer_wait: 1..32 flags");
-  if (!(timeout_s > 0.f)) timeout_s = 30.f;
+  if (PFN_streamWaitValue32 wait = stream_wait_fn()) {
+    // flags only ever grow (step numbers): "*addr - value >= 0" is the condition CU_STREAM_WAIT_VALUE_GEQ tests
+    for (int i = 0; i < n; ++i) {
+      CUresult r = wait((CUstream)stream, (CUdeviceptr)(uintptr_t)(flags + i), (cuuint32_t)value, CU_STREAM_WAIT_VALUE_GEQ);
+      if (r != CUDA_SUCCESS) TD_FAIL(TD_ERR_DRIVER, "cuStreamWaitValue32 failed with CUresult %d", int(r));
+    }
+    return TD_OK;
+  }
+  if (!(timeout_s > 0.f)) timeout_s = 600.f;
   peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, n, value, (unsigned long long)(double(timeout_s) * 1e9));
   TD_CUDA(cudaGetLastError());
   return TD_OK;

@@ -41,13 +41,15 @@ class FusedAdamW(torch.optim.Optimizer):
         if a._grad_flats is None or a._grad_flats.get(name) is None:
             return {k: named[k].grad for k in keys if named[k].grad is not None}
         views = dict(zip(keys, a.bucket_grads(name)))
-        if dp is not None and dp.world > 1:
-            for k, v in views.items():
-                g = named[k].grad
-                if g is not None and g.data_ptr() != v.data_ptr():
+        for k, v in views.items():
+            g = named[k].grad
+            if g is not None and g.data_ptr() != v.data_ptr():
+                # autograd accumulated into (or cloned) .grad: the flat buckets of the LAST backward are not the gradient
+                if dp is not None and dp.world > 1:
                     raise RuntimeError(
-                        f"{k}.grad does not alias the all-reduced gradient bucket: autograd accumulated or cloned it (two "
-                        "backward passes per step?) -- use AlignerTrainStep(accum_grad_iters=...) for gradient accumulation")
+                        f"{k}.grad does not alias the all-reduced gradient bucket: data-parallel FusedAdamW supports exactly one "
+                        "autograd backward per optimizer step -- use AlignerTrainStep(accum_grad_iters=...) for gradient accumulation")
+                return {k: named[k].grad for k in keys if named[k].grad is not None}
         return views
 
     def _named(self):

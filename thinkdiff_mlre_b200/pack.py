@@ -70,24 +70,32 @@ def kept_lengths(full_lens, build_info: dict, key: str = "output", rng=random):
 class FlatCollater:
     """Drop-in for the reference collater's role in the DataLoader (``collate_fn``), emitting a ``FlatBatch``.
 
-    ``samples`` are the reference's webdataset dicts: ``sample["json"]`` with ``generated_text`` / ``output_token_ids``
-    and the ``*output_embed*`` / ``*input_embed*`` tensors ``[L_i, C]``. The returned ``extras`` carry the same non-tensor
-    keys the reference returns (``generated_texts``, ``output_token_ids`` sliced exactly as at :120 / :147-149)."""
+    ``samples`` are the reference's webdataset dicts: ``sample["json"]`` with ``generated_text`` / ``output_token_ids`` (and
+    optionally ``gpt`` / ``revised_generated_text``) and the ``*output_embed*`` / ``*input_embed*`` tensors ``[L_i, C]``. The
+    returned ``extras`` carry the same non-tensor keys the reference returns (``generated_texts``, ``output_token_ids`` sliced
+    exactly as at :120 / :147-149, ``llava_gpts`` and ``revised_generated_texts`` when the samples have them, :38-46, :172-175).
 
-    def __init__(self, build_info: dict, pin_memory: bool = True, which: str = "output", truncate_on_host: bool = False):
+    ``which``: "output" / "input" collates that embed stream; ``None`` (default) follows ``build_info`` like the reference
+    (:50-53): the output stream when ``use_output_embed``, else the input stream, and when BOTH flags are set the output
+    stream is the returned batch and the input stream rides along as ``extras["input_batch"]`` (a second ``FlatBatch``).
+    ``reference_dict(batch, device)`` turns either into the exact dict of the reference collater (:169-183)."""
+
+    def __init__(self, build_info: dict, pin_memory: bool = True, which: str | None = None, truncate_on_host: bool = False):
         if not (build_info.get("use_output_embed") or build_info.get("use_input_embed")):
             raise ValueError("No input or output embeds are used.")  # reference message (:52-53)
+        if which not in (None, "output", "input"):
+            raise ValueError("which must be None, 'output' or 'input'")
         self.build_info, self.pin_memory, self.which = build_info, pin_memory, which
         # truncate_on_host: copy only the kept rows of every sample into the flat buffer (what the reference collater's
         # ``[:split_point]`` does) -- the H2D then moves M rows instead of sum(L_i); the device pack degenerates to a copy
         self.truncate_on_host = truncate_on_host
 
-    def __call__(self, samples) -> FlatBatch:
-        key = [k for k in samples[0].keys() if f"{self.which}_embed" in k][0]
+    def _stream(self, samples, which: str) -> FlatBatch:
+        key = [k for k in samples[0].keys() if f"{which}_embed" in k][0]
         embeds = [s[key] for s in samples]
         ids = [s["json"]["output_token_ids"] for s in samples]
         full_lens = [int(e.shape[0]) for e in embeds]
-        lens, l_max = kept_lengths(full_lens, self.build_info, self.which)
+        lens, l_max = kept_lengths(full_lens, self.build_info, which)
         src_lens = lens if self.truncate_on_host else full_lens
         flat = torch.cat([e[:n] for e, n in zip(embeds, lens)] if self.truncate_on_host else embeds, dim=0)
         if self.pin_memory and torch.cuda.is_available():
@@ -95,15 +103,48 @@ class FlatCollater:
         start = torch.zeros(len(embeds), dtype=torch.int64)
         if len(embeds) > 1:
             start[1:] = torch.cumsum(torch.tensor(src_lens[:-1], dtype=torch.int64), 0)
-        if self.which == "output" and self.build_info.get("random_split_output_embed"):
+        if which == "output" and self.build_info.get("random_split_output_embed"):
             out_ids = [t[n:] for t, n in zip(ids, lens)]
-        elif self.which == "output":
+        elif which == "output":
             out_ids = [t[:l_max] if L > l_max else t for t, L in zip(ids, full_lens)]
         else:
             out_ids = ids
+        js0 = samples[0]["json"]
         extras = {"generated_texts": [s["json"]["generated_text"] for s in samples], "output_token_ids": out_ids,
-                  "embed_key": key.replace(".pth", "")}
+                  "embed_key": key.replace(".pth", ""), "mask_key": f"{which}_embed_mask"}
+        if "gpt" in js0:  # pass-through keys, present only when the first sample has them (reference :38-46)
+            extras["llava_gpts"] = [s["json"]["gpt"] for s in samples]
+        if "revised_generated_text" in js0:
+            extras["revised_generated_texts"] = [s["json"]["revised_generated_text"] for s in samples]
         return FlatBatch(flat, start, torch.tensor(lens, dtype=torch.int32), l_max, extras)
+
+    def __call__(self, samples) -> FlatBatch:
+        bi = self.build_info
+        if self.which is not None:
+            return self._stream(samples, self.which)
+        if bi.get("use_output_embed"):
+            batch = self._stream(samples, "output")
+            if bi.get("use_input_embed"):
+                batch.extras["input_batch"] = self._stream(samples, "input")
+            return batch
+        return self._stream(samples, "input")
+
+    @staticmethod
+    def reference_dict(batch: FlatBatch, device="cuda") -> dict:
+        """The reference collater's return value (:169-183) from a ``FlatBatch``: H2D of the flat source, device-side zero
+        padding + int64 mask (``td_pack_padded``), and the pass-through lists. With a dual-stream batch both tensor pairs are
+        present, as in the reference when ``use_input_embed`` and ``use_output_embed`` are both set."""
+        ex = batch.extras
+        out = {"generated_texts": ex["generated_texts"], "output_token_ids": ex["output_token_ids"]}
+        for k in ("llava_gpts", "revised_generated_texts"):
+            if k in ex:
+                out[k] = ex[k]
+        streams = [batch] + ([ex["input_batch"]] if "input_batch" in ex else [])
+        for fb in streams:
+            padded, mask = pack_batch(fb, device).to_padded()
+            out[fb.extras["embed_key"]] = padded
+            out[fb.extras["mask_key"]] = mask
+        return out
 
 
 def pack_batch(batch: FlatBatch, device="cuda", non_blocking: bool = True) -> PackedBatch:

@@ -18,6 +18,7 @@ One exchange buffer per rank (``td_peer_alloc``: cudaMalloc + CUDA IPC handle; h
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 from . import _lib as L
@@ -130,8 +131,14 @@ class PeerExchange:
         self.timeout_s = float(timeout_s)
         lay = self.layout
         ptr, handle = C.c_void_p(), C.create_string_buffer(64)
-        with torch.cuda.device(self.device):
-            L.check(L.lib().td_peer_alloc(lay.total_bytes, C.byref(ptr), handle), "td_peer_alloc")
+        self._torch_backing = None
+        if self.world == 1 and os.environ.get("TD_PEER_NO_IPC") == "1":
+            # developer A/B: the same layout in ordinary caching-allocator memory (single rank only: nothing to export)
+            self._torch_backing = torch.zeros((lay.total_bytes,), dtype=torch.uint8, device=self.device)
+            ptr = C.c_void_p(self._torch_backing.data_ptr())
+        else:
+            with torch.cuda.device(self.device):
+                L.check(L.lib().td_peer_alloc(lay.total_bytes, C.byref(ptr), handle), "td_peer_alloc")
         self._local = int(ptr.value)
         self._opened = []
         self.base = [0] * self.world  # base[o] = address of rank o's buffer in THIS process
@@ -226,7 +233,8 @@ class PeerExchange:
     def __del__(self):
         try:
             if getattr(self, "_local", 0):
-                L.lib().td_peer_free(C.c_void_p(self._local))
+                if getattr(self, "_torch_backing", None) is None:
+                    L.lib().td_peer_free(C.c_void_p(self._local))
                 self._local = 0
         except Exception:
             pass
