@@ -215,6 +215,7 @@ def workload_config(name, n):
             "cfg4": "ThinkDiff-CLIP two-image + text composition, inference (BASELINE config 4 per GPU: 32 samples; N=8 = batch 256)"}[name]
     cfg = {"workload": what, "name": name, "seqs_per_gpu": seqs, "global_batch": seqs * n, "max_len": max_len, "ragged": f"len ~ U{{1..{max_len}}}",
            "din": din, "d": D, "parallelism": f"dp{n}",
+           "sharding": "one global batch of global_batch sequences per step; " + ("length-balanced assignment to ranks (equal sequence counts, even token counts)" if n > 1 else "single rank"),
            "l2_policy": f"{nb} distinct input batches cycled; the per-step working set exceeds the 126 MB L2"}
     if name != "cfg4":
         cfg.update(loss="masked_mse", optimizer="AdamW wd=0.05")
@@ -304,44 +305,65 @@ def eager_bar(dev, din, seqs, max_len, nb, steps, warmup, rank_seed):
 # ----------------------------------------------------------------------------------------------- multi-GPU parity
 def dp_parity_check(td, dist, dev, world, rank, mode):
     """Numerical check of the multi-GPU path bench.py times, on small dims, outside the timed region:
-    (a) the sharded / peer pipelined run == the plain all-reduce + replicated FusedAdamW run after K steps (<= 1e-6),
+    (a) the sharded / peer pipelined run == a REPLICATED FusedAdamW run whose gradient is the mean of the per-rank gradients summed
+        in rank order (the order the peer path's owners use). Expected: bit-identical parameters after K steps for `peer`; for the
+        NCCL `sharded` mode the summation order is NCCL's, and since bf16 training amplifies a 1e-7 difference of an fp32 master
+        into 1e-3 of the next gradient, that mode is held to a relative Frobenius distance of 2e-4 instead.
     (b) the exchanged gradient of one step == the mean over ranks of the per-rank gradients of an eager fp32-master / bf16-autocast
         PyTorch aligner on each rank's own shard (DDP's mean of per-rank means, runner_base.py:90-92; <= 2e-2),
     (c) every replica holds bit-identical parameters."""
     import torch
     from torch import nn
 
-    din, d, seqs, max_len, steps = 192, 512, 4, 50, 4
+    din, d, seqs, max_len, steps = 192, 512, 4, 50, 3
     torch.manual_seed(11)
-    ref_sd = None
+    ref_sd = {k: v.clone() for k, v in td.ThinkDiffAligner(din, d).to(dev).state_dict().items()}
 
-    def run(kind):
-        nonlocal ref_sd
-        torch.manual_seed(11)
-        m = td.ThinkDiffAligner(din, d).to(dev)
-        if ref_sd is None:
-            ref_sd = {k: v.clone() for k, v in m.state_dict().items()}
-        m.load_state_dict(ref_sd)
-        if kind == "plain":
-            m.enable_data_parallel(defer_wait=True)
-        else:
-            m.enable_data_parallel(defer_wait=True, sharded=True, peer=kind == "peer")
-        step = td.AlignerTrainStep(m, td.FusedAdamW(m, lr=1e-3), pipelined=True)
-        for j in range(steps):
-            b = td.synthetic_lvlm_batch(seqs, max_len, din, d, seed=100 * j + rank, pin=False)
-            step.step_device(b.flat.to(dev), b.src_row_start.to(dev), b.lens.to(dev), b.total_rows, b.l_max, b.extras["flat_target"].to(dev))
-        step.flush()
-        torch.cuda.synchronize()
-        params = [p.detach().clone() for p in m.parameters()]
-        if m._peer is not None:
-            m._peer.close()  # (collective: nobody still stores into a buffer that is about to be unmapped)
-        return params, m
+    def inputs(j):
+        b = td.synthetic_lvlm_batch(seqs, max_len, din, d, seed=100 + j, pin=False, world=world, rank=rank)
+        cu = td.ops.cu_seqlens(b.lens.to(dev))
+        x, idx = td.ops.pack_varlen(b.flat.to(dev), b.src_row_start.to(dev), cu, b.total_rows, want_index=True)
+        return b, x, idx, b.extras["flat_target"].to(dev)
 
-    plain, _ = run("plain")
-    tested, _ = run(mode)
-    max_rel = 0.0
-    for a, b in zip(plain, tested):
-        max_rel = max(max_rel, float((a - b).abs().max() / (a.abs().max() + 1e-30)))
+    # the path under test
+    m = td.ThinkDiffAligner(din, d).to(dev)
+    m.load_state_dict(ref_sd)
+    m.enable_data_parallel(defer_wait=True, sharded=True, peer=mode == "peer")
+    step = td.AlignerTrainStep(m, td.FusedAdamW(m, lr=1e-3), pipelined=True)
+    for j in range(steps):
+        b, _, _, tgt = inputs(j)
+        step.step_device(b.flat.to(dev), b.src_row_start.to(dev), b.lens.to(dev), b.total_rows, b.l_max, tgt)
+    step.flush()
+    torch.cuda.synchronize()
+    tested = [p.detach().clone() for p in m.parameters()]
+    if m._peer is not None:
+        m._peer.close()  # (collective: nobody still stores into a buffer that is about to be unmapped)
+
+    # (a) replicated AdamW on the rank-ordered mean gradient
+    m2 = td.ThinkDiffAligner(din, d).to(dev)
+    m2.load_state_dict(ref_sd)
+    opt2 = td.FusedAdamW(m2, lr=1e-3)
+    inv_world = torch.full((1,), 1.0 / world, dtype=torch.float32, device=dev)
+    for j in range(steps):
+        _, x, idx, tgt = inputs(j)
+        m2.mse_loss_backward_packed(x, tgt, idx, upstream=inv_world)  # this rank's gradient, already divided by the world size
+        for name in ("linear1", "linear2"):
+            flat = m2._grad_flats[name]
+            parts = [torch.empty_like(flat) for _ in range(world)]
+            dist.all_gather(parts, flat)
+            acc = parts[0].clone()
+            for r in range(1, world):
+                acc += parts[r]
+            flat.copy_(acc)
+        opt2.step()
+        opt2.zero_grad()
+    torch.cuda.synchronize()
+    max_rel, num, den = 0.0, 0.0, 0.0
+    for a, t in zip(m2.parameters(), tested):
+        max_rel = max(max_rel, float((a.detach() - t).abs().max() / (a.detach().abs().max() + 1e-30)))
+        num += float((a.detach() - t).float().pow(2).sum())
+        den += float(a.detach().float().pow(2).sum())
+    frob = (num / (den + 1e-30)) ** 0.5
     # (c) replicas identical
     replicas_equal = True
     for p in tested:
@@ -352,17 +374,14 @@ def dp_parity_check(td, dist, dev, world, rank, mode):
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     replicas_equal = bool(flag.item() == 1.0)
     # (b) one step's exchanged gradient vs the eager PyTorch reference module, mean over ranks
-    m = td.ThinkDiffAligner(din, d).to(dev)
-    m.load_state_dict(ref_sd)
-    m.enable_data_parallel()
-    b = td.synthetic_lvlm_batch(seqs, max_len, din, d, seed=7 + rank, pin=False)
-    cu = td.ops.cu_seqlens(b.lens.to(dev))
-    x, idx = td.ops.pack_varlen(b.flat.to(dev), b.src_row_start.to(dev), cu, b.total_rows, want_index=True)
-    tgt = b.extras["flat_target"].to(dev)
-    m.mse_loss_backward_packed(x, tgt, idx)
+    m3 = td.ThinkDiffAligner(din, d).to(dev)
+    m3.load_state_dict(ref_sd)
+    m3.enable_data_parallel()
+    _, x, idx, tgt = inputs(7)
+    m3.mse_loss_backward_packed(x, tgt, idx)
     torch.cuda.synchronize()
-    ours = [p.grad.detach().float().clone() for p in m.parameters()]
-    eager = nn.Sequential(nn.Linear(din, d), nn.GELU(), nn.Linear(d, d), type(m[3])(d, 1e-6)).to(dev)
+    ours = [p.grad.detach().float().clone() for p in m3.parameters()]
+    eager = nn.Sequential(nn.Linear(din, d), nn.GELU(), nn.Linear(d, d), type(m3[3])(d, 1e-6)).to(dev)
     eager.load_state_dict(ref_sd)
     with torch.autocast("cuda", dtype=torch.bfloat16):
         y = eager(x)
@@ -373,10 +392,74 @@ def dp_parity_check(td, dist, dev, world, rank, mode):
         dist.all_reduce(r)
         r /= world
         grad_rel = max(grad_rel, float((g - r).norm() / (r.norm() + 1e-30)))
-    res = {"ok": bool(max_rel <= 1e-6 and grad_rel <= 2e-2 and replicas_equal), "mode": mode, "max_rel_vs_allreduce_adamw": max_rel,
+    same = max_rel == 0.0 if mode == "peer" else frob <= 2e-4
+    res = {"ok": bool(same and grad_rel <= 2e-2 and replicas_equal), "mode": mode,
+           "max_rel_vs_replicated_adamw_on_rank_ordered_mean": max_rel, "frobenius_rel": frob,
+           "criterion": "bit-identical" if mode == "peer" else "frobenius_rel <= 2e-4 (NCCL's summation order differs; bf16 training amplifies 1e-7)",
            "grad_rel_vs_eager_mean_of_ranks": grad_rel, "replicas_equal": replicas_equal, "steps": steps, "dims": [din, d]}
-    del m, eager
+    del m, m2, m3, eager
     return res
+
+
+# ----------------------------------------------------------------------------------------------- shard-fed e2e (f-2)
+def e2e_from_shards(td, stepper, host_t, seqs, din, dev, steps, sync_all, max_over_ranks, sum_over_ranks, rank):
+    """The host-fed step with its batches coming from disk: the synthetic samples are written once as two flat shards (features
+    [*, din] and T5-space targets [*, D]; the on-disk format of thinkdiff_mlre_b200/shards.py that replaces the reference's
+    pickled tensors in tar shards, thinkdiff/tasks/image_text_process_data.py:94-118), then every step reads its batch with
+    EmbedShardReader (one slab copy page cache -> pinned ring buffer), ships it and trains on it. The reader runs on this
+    process's main thread, so this number is bounded by one core's memcpy -- it is here to exercise the loader on the GPU path."""
+    import tempfile
+
+    import torch
+
+    tmp = tempfile.mkdtemp(prefix=f"td_shards_r{rank}_")
+    paths = (os.path.join(tmp, "feat.tdemb"), os.path.join(tmp, "tgt.tdemb"))
+    with td.EmbedShardWriter(paths[0], din) as wf, td.EmbedShardWriter(paths[1], D) as wt:
+        for b in host_t:
+            for s0, n in zip(b.src_row_start.tolist(), b.lens.tolist()):
+                wf.add(b.flat[s0 : s0 + n], [0] * n)
+                wt.add(b.extras["flat_target"][s0 : s0 + n], [0] * n)
+    rf, rt = td.EmbedShardReader(paths[0]), td.EmbedShardReader(paths[1])
+    bi = dict(use_output_embed=1, use_input_embed=0, random_split_output_embed=0, output_embed_max_len=1 << 30, input_embed_max_len=1 << 30)
+    nb = len(host_t)
+
+    def load(j):
+        fb = rf.batch(j * seqs, (j + 1) * seqs, bi)
+        tb = rt.batch(j * seqs, (j + 1) * seqs, bi)
+        cbs = [x.extras.get("_h2d_enqueued") for x in (fb, tb)]
+        fb.extras["flat_target"] = tb.flat
+        fb.extras["_h2d_enqueued"] = lambda evs: [cb(evs) for cb in cbs if cb is not None]
+        return fb
+
+    for j in range(2):
+        float(stepper.step_prefetched(stepper.prefetch(load(j % nb), dev)))
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    load_s = 0.0
+    nxt = stepper.prefetch(load(0), dev)
+    for i in range(steps):
+        cur = nxt
+        if i + 1 < steps:
+            tl = time.perf_counter()
+            b = load((i + 1) % nb)
+            load_s += time.perf_counter() - tl
+            nxt = stepper.prefetch(b, dev)
+        float(stepper.step_prefetched(cur))
+    stepper.flush(sync_masters=False)
+    e1.record()
+    sync_all()
+    stepper.flush()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    tokens = sum_over_ranks(float(sum(host_t[i % nb].total_rows for i in range(steps))))
+    rf.close(), rt.close()
+    for p_ in paths:
+        os.remove(p_)
+    os.rmdir(tmp)
+    return {"value": tokens / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "loader_ms_per_batch": load_s / max(steps - 1, 1) * 1e3,
+            "wall_ms_per_step": (time.perf_counter() - t0) / steps * 1e3,
+            "note": "batches read from flat on-disk shards by EmbedShardReader on the main thread (one slab memcpy per tensor into a pinned ring, recycled on CUDA events)"}
 
 
 # ----------------------------------------------------------------------------------------------- B200 arm
@@ -390,6 +473,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-eager-bar", action="store_true")
+    ap.add_argument("--from-shards", action="store_true",
+                    help="also time the host-fed step with its batches read from flat embedding shards on disk (EmbedShardReader, SURVEY 8 f-2)")
     ap.add_argument("--no-dp-parity", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after backward instead of overlapped")
     ap.add_argument("--no-pipeline", action="store_true", help="apply every parameter update inside its own step, on the compute stream")
@@ -397,6 +482,10 @@ def main():
                     help="N > 1 gradient exchange: peer = reduce-scatter fused into the weight-gradient GEMM epilogues over NVLink peer memory "
                          "(no collective kernels on the step); sharded = NCCL reduce-scatter + row-sharded AdamW + all-gather; allreduce = NCCL "
                          "bucketed all-reduce + replicated AdamW. auto = peer")
+    ap.add_argument("--sharding", default="balanced", choices=["balanced", "contiguous"],
+                    help="N > 1: how the global batch of N x seqs_per_gpu sequences is split over the ranks -- balanced = equal sequence counts and "
+                         "even token counts (SURVEY 8e allows it; synchronous data parallel runs at the pace of the rank with the most tokens), "
+                         "contiguous = rank r takes sequences [r * seqs, (r + 1) * seqs)")
     ap.add_argument("--profile-out", default="", help="write the per-kernel table (JSON) here")
     ap.add_argument("--timeline-out", default="", help="write a per-stream device timeline of a few steady-state steps (JSON) here")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
@@ -482,7 +571,8 @@ def main():
     stepper = td.AlignerTrainStep(aligner, opt, fused_loss=args.loss_path == "fused", pipelined=pipelined)
 
     with numa_local(local) as numa:
-        host = [td.synthetic_lvlm_batch(seqs, max_len, din, D, seed=1234 + rank + 1000 * j) for j in range(num_batches)]
+        host = [td.synthetic_lvlm_batch(seqs, max_len, din, D, seed=1234 + 1000 * j, world=world, rank=rank, balanced=args.sharding == "balanced")
+                for j in range(num_batches)]
     numa_cpus = numa.cpus
     resident = [(b.flat.to(dev), b.src_row_start.to(dev), b.lens.to(dev), b.total_rows, b.l_max, b.extras["flat_target"].to(dev)) for b in host]
     tokens_per_step = [b.total_rows for b in host]
@@ -518,7 +608,8 @@ def main():
         # what the collater ships: only the kept rows of every sample (FlatCollater(truncate_on_host=True), the reference
         # collater's [:split_point] done in the DataLoader worker) -- the device pack then re-packs contiguous rows
         with numa_local(local):
-            host_t = [td.synthetic_lvlm_batch(seqs, max_len, din, D, seed=1234 + rank + 1000 * j, truncated=True) for j in range(num_batches)]
+            host_t = [td.synthetic_lvlm_batch(seqs, max_len, din, D, seed=1234 + 1000 * j, truncated=True, world=world, rank=rank,
+                                              balanced=args.sharding == "balanced") for j in range(num_batches)]
         for i in range(3):
             float(stepper.step_host(host_t[i % num_batches], dev))
         sync_all()
@@ -540,6 +631,8 @@ def main():
         e2e = {"value": tokens_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / steps, "h2d_gbs_per_rank": h2d / (ms_e2e / steps * 1e-3) / 1e9, "numa_bound_cpus": numa_cpus,
                "note": "every step: H2D of the kept rows of its bf16 features + T5 targets from pinned memory (row chunks on two copy streams, overlapping the previous step's compute) and loss.item()"}
+        if args.from_shards:
+            e2e["from_shards"] = e2e_from_shards(td, stepper, host_t, seqs, din, dev, min(steps, 12), sync_all, max_over_ranks, sum_over_ranks, rank)
         del host_t
 
     if os.environ.get("TD_HOST_PROFILE") and rank == 0:  # developer aid: where does the host time of a step go?
@@ -644,7 +737,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_eager_bar:
         del resident
         torch.cuda.empty_cache()
-        bar = eager_bar(dev, din, seqs, max_len, num_batches, min(steps, 20), 3, 1234 + rank)
+        bar = eager_bar(dev, din, seqs, max_len, num_batches, min(steps, 20), 3, 1234)
         bar["speedup_of_this_repo"] = value / bar["value"]
 
     ok = True
@@ -654,7 +747,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": dict(workload_config(args.workload, world), loss_path=args.loss_path, optimizer_impl=args.optimizer, pipelined_updates=pipelined,
-                                                 dp_exchange=dp_mode, fp32_master_sync="after the timed region (bf16 compute copies and AdamW are inside it)" if dp_mode in ("peer", "sharded") else None),
+                                                 dp_exchange=dp_mode, sharding_mode=args.sharding if world > 1 else None, fp32_master_sync="after the timed region (bf16 compute copies and AdamW are inside it)" if dp_mode in ("peer", "sharded") else None),
             "clocks": clk, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "eager_bar": bar, "dp_parity": dp_parity,
             "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_peak": step_tflops / tc_peak,

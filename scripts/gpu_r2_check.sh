@@ -3,7 +3,6 @@
 mkdir -p gpurun_out
 echo "=== harness"; timeout 300 ./thinkdiff_mlre_b200/csrc/test_gemm.bin > gpurun_out/r02_harness.log 2>&1; echo "harness rc=$?"; grep -E "FAIL|RESULT|perf|KERNEL|rc=" gpurun_out/r02_harness.log | tail -30
 echo "=== pytest gpu"; timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r02_pytest.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/r02_pytest.log
-echo "=== peer tests"; TD_TEST_PEER=1 timeout 600 python -m pytest tests/test_gpu_peer.py -q -x > gpurun_out/r02_peer.log 2>&1; echo "peer rc=$?"; tail -15 gpurun_out/r02_peer.log
 echo "=== bench"; timeout 600 python bench.py --steps ${1:-20} --warmup 5 --profile-out gpurun_out/r02_bench_profile.json > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err; echo "bench rc=$?"; tail -5 gpurun_out/r02_bench.err
 python - <<'PY'
 import json
@@ -19,3 +18,10 @@ try:
 except Exception as e:
     print("bench parse failed", e)
 PY
+for lib in thinkdiff_mlre_b200/libthinkdiff_b200_*.so; do  # A/B of alternative builds, if any were shipped
+  [ -f "$lib" ] || continue
+  tag=$(basename $lib .so | sed 's/libthinkdiff_b200_//')
+  THINKDIFF_B200_LIB=$PWD/$lib timeout 300 python bench.py --steps ${1:-20} --warmup 5 --no-cpu-baseline --no-e2e --no-eager-bar > gpurun_out/r02_bench_$tag.json 2> gpurun_out/r02_bench_$tag.err
+  python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_$tag.json')); print('variant $tag', 'tok/s %.3fM' % (d['value']/1e6), 'ms/step %.3f' % d['ms_per_step'], {t: round(v['ms_per_launch']*1e3) for t, v in d['kernels'].items()})"
+done

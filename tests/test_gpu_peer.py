@@ -1,7 +1,8 @@
-"""Peer-memory data parallel (EXPERIMENTAL, thinkdiff_mlre_b200/peer.py): opt-in GPU tests, run with TD_TEST_PEER=1.
+"""Peer-memory data parallel (thinkdiff_mlre_b200/peer.py): the gradient exchange fused into the weight-gradient GEMM epilogues.
 
 The kernels take plain pointer arrays, so everything except the CUDA-IPC mapping is exercised on ONE GPU: the "peers" of the
-loop-back tests are separate buffers of the same device. The two-process test needs 2 GPUs (gpurun --gpus 2)."""
+loop-back tests are separate buffers of the same device. The two-process test needs 2 GPUs (gpurun --gpus 2); bench.py repeats
+its check (`dp_parity`) at every N > 1."""
 import ctypes as C
 import os
 import socket
@@ -10,8 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("TD_TEST_PEER") != "1", reason="experimental peer-memory path: set TD_TEST_PEER=1")]
+pytestmark = pytest.mark.gpu
 
 DIN, D = 192, 512
 

@@ -111,6 +111,17 @@ constexpr int kSkSlotFloats = kEpiWarps * kEpiChunks * 32 * 32;  // one CTA's 12
 template <int EPI> struct EpiStage { static constexpr int kBytesPerWarp = 4096; };          // two 2 KB bf16 boxes
 template <> struct EpiStage<EPI_DGELU> { static constexpr int kBytesPerWarp = 6144; };      // + two aux boxes, one out box
 
+// Pipeline depth per epilogue kind. The GEMMs that the optimizer's update kernels run BESIDE (Linear1's update beside the dW2
+// GEMM, Linear2's beside the next forward's first GEMM) keep one stage less than would fit: the 32 KB they leave free -- and their
+// 128 registers per thread -- let one 256-thread CTA of an HBM-bound update kernel be co-resident on every SM, which is the only
+// way such a kernel gets bandwidth while a persistent GEMM holds all 148 SMs.
+template <int EPI> struct StageCap { static constexpr int kMax = TD_MAX_STAGES; };
+#ifndef TD_NO_CORESIDENCY
+template <> struct StageCap<EPI_BIAS_GELU> { static constexpr int kMax = 5; };
+template <> struct StageCap<EPI_F32> { static constexpr int kMax = 5; };
+template <> struct StageCap<EPI_F32_SCATTER> { static constexpr int kMax = 5; };
+#endif
+
 template <int CTAS, int EPI>
 struct GemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;           // 16 KB
@@ -120,7 +131,8 @@ struct GemmSmem {
   static constexpr int kBarrierBytes = 1024;
   static constexpr int kMaxBytes = 227 * 1024;
   static constexpr int kFit = (kMaxBytes - kBarrierBytes - 1024 - kEpiBytes) / kStageBytes;
-  static constexpr int kStages = kFit < TD_MAX_STAGES ? kFit : TD_MAX_STAGES;
+  static constexpr int kCap = (CTAS == 2) ? StageCap<EPI>::kMax : TD_MAX_STAGES;
+  static constexpr int kStages = kFit < kCap ? kFit : kCap;
   static constexpr int kTotal = kStages * kStageBytes + kEpiBytes + kBarrierBytes + 1024;  // +1024 alignment slack
   static_assert(kStages >= 3, "pipeline too shallow");
 };

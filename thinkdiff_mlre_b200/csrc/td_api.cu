@@ -39,6 +39,18 @@ int check_device() {
     if (_rc) return _rc;           \
   } while (0)
 
+// The update kernels are meant to run on SMs that a persistent GEMM has configured for the maximum shared-memory carve-out:
+// ask for the same split (they use no shared memory themselves), so the SM never has to drain to reconfigure.
+template <class K>
+inline void prefer_max_shared(K kernel) {
+  static std::atomic<bool> done[kMaxDevices];
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices || done[dev].load(std::memory_order_acquire)) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaGetLastError();
+  done[dev].store(true, std::memory_order_release);
+}
+
 inline int grid_for_rows(long long rows, int rows_per_block, int blocks_per_sm) {
   const long long want = (rows + rows_per_block - 1) / rows_per_block;
   const long long cap = (long long)device_sm_count() * blocks_per_sm;
@@ -715,7 +727,10 @@ int32_t td_adamw_step(int32_t num_tensors, float* const* params, const float* co
   for (int i = 0; i < num_tensors; ++i) total += double(numel[i]);
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof("adamw_bf16", 30.0 * total, st);
-  if (wide) adamw256_kernel<<<dim3(grid_for_rows(max_n / 8, 256, 8), num_tensors), 256, 0, st>>>(a);
+  // 2 CTAs per SM: a wave of them fits beside a resident GEMM CTA (registers: 320 x 128 + 256 x 64), the second wave takes the
+  // SM over as soon as the GEMM's CTAs retire
+  prefer_max_shared(adamw256_kernel);
+  if (wide) adamw256_kernel<<<dim3(grid_for_rows(max_n / 8, 256, 2), num_tensors), 256, 0, st>>>(a);
   else adamw_kernel<<<dim3(grid_for_rows(max_n / 4, 256, 8), num_tensors), 256, 0, st>>>(a);
   TD_CUDA(cudaGetLastError());
   return TD_OK;
@@ -898,7 +913,8 @@ int32_t td_adamw_slots_step(float* param, const float* grad_slots, int64_t slot_
   if (numel == 0) return TD_OK;
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof("adamw_slots", (28.0 + 4.0 * n_slots + 2.0 * n_dst) * double(numel), st);
-  adamw_slots_kernel<<<grid_for_rows(numel / 4, 256, 8), 256, 0, st>>>(a);
+  prefer_max_shared(adamw_slots_kernel);
+  adamw_slots_kernel<<<grid_for_rows(numel / 4, 256, 2), 256, 0, st>>>(a);
   TD_CUDA(cudaGetLastError());
   return TD_OK;
 }

@@ -152,6 +152,11 @@ def pack_batch(batch: FlatBatch, device="cuda", non_blocking: bool = True) -> Pa
     flat = batch.flat.to(device, non_blocking=non_blocking)
     start = batch.src_row_start.to(device, non_blocking=non_blocking)
     lens = batch.lens.to(device, non_blocking=non_blocking)
+    cb = batch.extras.get("_h2d_enqueued")
+    if cb is not None and flat.is_cuda:
+        ev = torch.cuda.Event()
+        ev.record()
+        cb([ev])  # the producer of the pinned source (EmbedShardReader) may recycle it once this has fired
     return pack_device(flat, start, lens, batch.total_rows, batch.l_max, batch.lens, batch.extras)
 
 

@@ -131,16 +131,31 @@ class EmbedShardReader:
         r0, r1 = int(self.row_start[lo]), int(self.row_start[hi])
         full_lens = self.lens[lo:hi].tolist()
         lens, l_max = kept_lengths(full_lens, build_info, "output")
+        slot_cb = None
         if pin_memory and torch.cuda.is_available():
-            # ring of 3 pinned staging buffers: a batch's buffer is reused only two batches later, after its async H2D
+            # ring of 3 pinned staging buffers. A slot is refilled only after the H2D copies that read it have finished: whoever
+            # enqueues those copies hands their CUDA events back through extras["_h2d_enqueued"] (AlignerTrainStep.prefetch /
+            # step_host do), and the next use of the slot waits for them on the host. Without events (a consumer that never
+            # reports) the slot's previous buffer is dropped instead of being overwritten.
             if self._pinned is None:
-                self._pinned, self._ring = [None, None, None], 0
+                self._pinned, self._slot_events, self._reported, self._ring = [None, None, None], [None, None, None], [True, True, True], 0
             self._ring = (self._ring + 1) % 3
-            buf = self._pinned[self._ring]
+            slot = self._ring
+            if self._slot_events[slot] is not None:
+                for ev in self._slot_events[slot]:
+                    ev.synchronize()
+                self._slot_events[slot] = None
+            elif not self._reported[slot]:
+                self._pinned[slot] = None  # copies of unknown state may still read the old buffer: leave it to its tensor
+            buf = self._pinned[slot]
             if buf is None or buf.shape[0] < r1 - r0:
-                buf = self._pinned[self._ring] = torch.empty((max(r1 - r0, 1), self.width), dtype=torch.bfloat16).pin_memory()
+                buf = self._pinned[slot] = torch.empty((max(r1 - r0, 1), self.width), dtype=torch.bfloat16).pin_memory()
             flat = buf[: r1 - r0]
             flat.view(torch.int16).numpy().view(np.uint16)[:] = self.rows[r0:r1]  # one slab copy, page cache -> pinned
+            self._reported[slot] = False
+
+            def slot_cb(events, _slot=slot):
+                self._slot_events[_slot], self._reported[_slot] = list(events), True
         else:
             flat = torch.from_numpy(np.array(self.rows[r0:r1]).view(np.int16)).view(torch.bfloat16)
         start = torch.from_numpy((self.row_start[lo:hi] - r0).astype(np.int64))
@@ -150,7 +165,9 @@ class EmbedShardReader:
             out_ids = [self.token_ids(i)[:l_max].tolist() if L > l_max else self.token_ids(i).tolist()
                        for i, L in zip(range(lo, hi), full_lens)]
         extras = {"generated_texts": self._meta["generated_text"][lo:hi], "output_token_ids": out_ids,
-                  "embed_key": "model.norm.output_embed"}
+                  "embed_key": "model.norm.output_embed", "mask_key": "output_embed_mask"}
+        if slot_cb is not None:
+            extras["_h2d_enqueued"] = slot_cb
         return FlatBatch(flat, start, torch.tensor(lens, dtype=torch.int32), l_max, extras)
 
     def batches(self, batch_size: int, build_info: dict, drop_last: bool = True, pin_memory: bool = True):

@@ -30,12 +30,18 @@ def make_reference_optimizer(module, lr: float = 1e-4, weight_decay: float = 0.0
 
 
 def synthetic_lvlm_batch(num_seqs: int, max_len: int, din: int, d: int, seed: int, pin: bool = True,
-                         with_target: bool = True, truncated: bool = False) -> FlatBatch:
-    """BASELINE config-2 style ragged batch (``synth.lvlm_batch_tensors``) as a ``FlatBatch`` of (pinned) host tensors.
+                         with_target: bool = True, truncated: bool = False, world: int = 1, rank: int = 0,
+                         balanced: bool = True) -> FlatBatch:
+    """BASELINE config-2 style ragged batch (``synth.py``) as a ``FlatBatch`` of (pinned) host tensors: this rank's ``num_seqs``
+    sequences of the global batch of ``world * num_seqs`` sequences with this seed. ``balanced``: length-balanced assignment of
+    the global batch (``sharding.balanced_assignment``: equal sequence counts, even token counts) instead of a contiguous split.
     ``truncated``: only the kept rows are in the flat source (``FlatCollater(truncate_on_host=True)`` layout)."""
-    from .synth import lvlm_batch_tensors
+    from .sharding import balanced_assignment, contiguous_assignment
+    from .synth import global_lengths, lvlm_sequences
 
-    flat, start, lens, target = lvlm_batch_tensors(num_seqs, max_len, din, d, seed, with_target, truncated)
+    lens_all = global_lengths(num_seqs * world, max_len, seed)
+    groups = balanced_assignment(lens_all.tolist(), world) if (balanced and world > 1) else contiguous_assignment(num_seqs * world, world)
+    flat, start, lens, target = lvlm_sequences(groups[rank], lens_all, din, d, seed, with_target, truncated)
     extras = {}
     if with_target:
         extras["flat_target"] = target
@@ -381,6 +387,9 @@ class AlignerTrainStep:
             ev = torch.cuda.Event()
             ev.record(st)
             events.append(ev)
+        cb = batch.extras.get("_h2d_enqueued")
+        if cb is not None:
+            cb(events)  # the producer of the pinned buffers (EmbedShardReader) may recycle them once these have fired
         return (flat, start, lens, batch.total_rows, batch.l_max, tgt), events
 
     def step_prefetched(self, handle) -> torch.Tensor:
@@ -399,4 +408,9 @@ class AlignerTrainStep:
         tgt = batch.extras["flat_target"].to(device, non_blocking=True)
         start = batch.src_row_start.to(device, non_blocking=True)
         lens = batch.lens.to(device, non_blocking=True)
+        cb = batch.extras.get("_h2d_enqueued")
+        if cb is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            cb([ev])
         return self.step_device(flat, start, lens, batch.total_rows, batch.l_max, tgt)
