@@ -29,8 +29,8 @@ enum { TD_OK_ = 0, TD_ERR_ARG_ = -1, TD_ERR_UNSUPPORTED_ = -2, TD_ERR_DRIVER_ = 
 enum { TD_BWD_PHASE_NORM_W2 = 1, TD_BWD_PHASE_GELU_W1 = 2, TD_BWD_PHASE_ALL = 3,
        /* td_aligner_bwd_dh2 only: the two halves of NORM_W2, so the small vectors' all-reduce can start before the dW2 GEMM */
        TD_BWD_PHASE_SMALL2_ONLY = 4, TD_BWD_PHASE_W2_ONLY = 8,
-       /* the dh0 GEMM + db1 without the dW1 GEMM */
-       TD_BWD_PHASE_GELU_ONLY = 16 };
+       /* the two halves of GELU_W1: the dh0 GEMM + db1 (dh0 stays in the workspace), and the dW1 GEMM from that dh0 */
+       TD_BWD_PHASE_GELU_ONLY = 16, TD_BWD_PHASE_W1_ONLY = 32 };
 /* td_aligner_mse_fwd stages (bit mask) */
 enum { TD_FWD_STAGE_LINEAR1 = 1, TD_FWD_STAGE_REST = 2, TD_FWD_STAGE_ALL = 3,
        /* leave the loss un-finished: td_aligner_bwd_dh2(loss_out = ...) sums the per-CTA partials in its own finisher launch */
@@ -173,7 +173,7 @@ int32_t td_grad_stats(const float* grad, int64_t numel, float* stats, td_stream_
  * the weight-gradient GEMM epilogues: rank o owns rows [o D/world, (o+1) D/world) of W1 and W2; every rank's GEMM stores
  * those rows of its (1/world-scaled) gradient straight into "slot[this rank]" of rank o's exchange buffer; rank o sums the
  * slots in rank order inside its AdamW pass and stores the updated bf16 rows into every rank's compute copy. Ordering is by
- * monotonically increasing step-number flags in the destination's memory (td_peer_signal / td_peer_wait), no collectives.
+ * monotonically increasing counters in the destination's memory (td_peer_signal / td_peer_wait), no collectives.
  * Buffers come from td_peer_alloc (cudaMalloc + CUDA IPC handle, zero-filled); the other processes map them with td_peer_open.
  * All pointer arrays are HOST arrays of `n` / `world` device pointers (<= TD_MAX_PEERS), entry o = the address in rank o. */
 enum { TD_MAX_PEERS = 8, TD_IPC_HANDLE_BYTES = 64 };
@@ -181,8 +181,9 @@ int32_t td_peer_alloc(int64_t bytes, void** ptr /*[host] out*/, uint8_t* handle 
 int32_t td_peer_free(void* ptr);
 int32_t td_peer_open(const uint8_t* handle /*[host]*/, void** ptr /*[host] out*/);
 int32_t td_peer_close(void* ptr);
-/* flag_arrays[i][slot] = value at every rank i (release, system scope), ordered after all earlier work on `stream`. */
-int32_t td_peer_signal(void* const* flag_arrays /*[host]*/, int32_t n, int32_t slot, int32_t value, td_stream_t stream);
+/* flag_arrays[i][slot] += 1 at every rank i (remote atomic add, release at system scope), ordered after all earlier work on
+ * `stream`: a counter reaches t * world when every rank has signalled step t. */
+int32_t td_peer_signal(void* const* flag_arrays /*[host]*/, int32_t n, int32_t slot, td_stream_t stream);
 /* Blocks `stream` until flags[0..n) >= value (local int32 flags written by the peers). Implemented with stream memory operations
  * (cuStreamWaitValue32: no kernel occupies an SM while waiting; a peer that never signals blocks the stream, as a lost NCCL rank
  * would); with TD_PEER_WAIT=kernel a polling kernel is used instead, which traps after timeout_s (<= 0: 600 s). */

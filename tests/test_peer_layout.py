@@ -30,9 +30,9 @@ def test_regions_are_disjoint_aligned_and_tiled(world, din, d):
         assert [lay.weight_rows_offset(which, o) for o in range(world)] == [off_w + 2 * o * numel for o in range(world)]
         assert lay.weight_rows_offset(which, world - 1) + 2 * numel == off_w + 2 * d * cols
     assert lay.small_numel == 3 * d and lay.small_slot_offset(world - 1) + 4 * lay.small_numel <= lay.off_w1
-    # flags: one 128-byte line per row, one int32 per source rank
-    assert lay.flag_offset(ROW_GRAD1, 0) == 0 and lay.flag_offset(ROW_W2, world - 1) == 4 * (ROW_W2 * FLAG_ROW_STRIDE + world - 1)
-    assert lay.flag_offset(ROW_W2, world - 1) < FLAG_BYTES
+    # flags: one monotone int32 counter per row, one 128-byte line per row
+    assert lay.flag_offset(ROW_GRAD1) == 0 and lay.flag_offset(ROW_W2) == 4 * ROW_W2 * FLAG_ROW_STRIDE
+    assert 4 * FLAG_ROW_STRIDE >= 128 and lay.flag_offset(ROW_W2) + 4 <= FLAG_BYTES
 
 
 def test_rejects_unsupported_worlds():

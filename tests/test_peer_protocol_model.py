@@ -9,15 +9,18 @@ model, and asserts the three hazards can never happen:
   * a rank's GEMM reads weight rows while their owner is storing newer ones into them, or reads rows that are a step stale;
   * the small-vector slots are summed while being re-posted.
 
-Every data operation is split into begin / end so that overlapping accesses are visible to the checker. Flags are monotone step
-numbers with release/acquire semantics: a signal is an atomic store that becomes visible only after the signalling stream's
-earlier operations have ENDED (in-order streams), a wait blocks its stream until all ``world`` flags of a row reach the value.
+Every data operation is split into begin / end so that overlapping accesses are visible to the checker. Every flag row is ONE
+monotone counter per destination rank: a signal is a remote atomic add of 1 (release) that becomes visible only after the
+signalling stream's earlier operations have ENDED (in-order streams); a wait for step ``t`` blocks its stream until the counter
+reaches ``t * world``, i.e. until every rank has signalled ``t`` times. Two sync points per step and direction: GRAD1 (the small
+vectors ride along: they are posted before the signal) and GRAD2 towards the owners, W1 (covers the replicated bias / norm
+vectors, updated before the signal) and W2 back.
 """
 import random
 
 import pytest
 
-GRAD1, GRAD2, SMALL, W1, W2 = range(5)
+GRAD1, GRAD2, W1, W2 = range(4)
 
 
 class Violation(AssertionError):
@@ -32,8 +35,7 @@ class Memory:
         self.small = {(dst, src): {"v": 0, "writers": 0, "readers": 0} for dst in range(world) for src in range(world)}
         self.weight = {(w, holder, owner): {"v": 0, "writers": 0, "readers": 0} for w in (1, 2) for holder in range(world) for owner in range(world)}
         self.vecs = {r: {"v": 0, "writers": 0, "readers": 0} for r in range(world)}  # b1 / b2 / g compute copies of rank r
-        self.flags = {(row, dst, src): 0 for row in range(5) for dst in range(world) for src in range(world)}
-        self.events = {}  # (rank, name, step) -> recorded
+        self.flags = {(row, dst): 0 for row in range(4) for dst in range(world)}  # counters: += 1 per signal
 
     @staticmethod
     def begin_read(cell, want, what):
@@ -61,47 +63,34 @@ class Memory:
         cell["v"] = version
 
 
-def compute_stream(rank, world, steps, grouped=False):
-    """Operations of the compute stream of ``rank``: ("wait", row, value) | ("wait_event", name, step) | ("signal", row, value) |
-    ("data", begin_fn, end_fn)."""
+def compute_stream(rank, world, steps):
+    """Operations of the compute stream of ``rank``: ("wait", row, step) | ("signal", row) | data operations."""
     ops = []
     for t in range(1, steps + 1):
         if t > 1:
             ops.append(("wait", W1, t - 1))
-            ops.append(("wait_event", "small", t - 1))
         ops.append(("read_weight", 1, t - 1))        # GEMM1
-        ops.append(("read_vecs", t - 1))             # b1 in GEMM1's epilogue (b2 / g later: same event)
+        ops.append(("read_vecs", t - 1))             # b1 in GEMM1's epilogue
         if t > 1:
             ops.append(("wait", W2, t - 1))
         ops.append(("read_weight", 2, t - 1))        # GEMM2
+        ops.append(("read_vecs", t - 1))             # b2 / g in GEMM2's epilogue and the fused norm kernel
         ops.append(("read_weight", 2, t - 1))        # backward: dh0 = dh2 . W2
-        if grouped:                                  # TD_PEER_GROUPED=1: dW1 + dW2 as one launch, after the small vectors
-            ops.append(("post_small", t))
-            ops.append(("signal", SMALL, t))
-            ops.append(("write_slots", 1, t))
-            ops.append(("write_slots", 2, t))
-            ops.append(("signal", GRAD1, t))
-            ops.append(("signal", GRAD2, t))
-            continue
+        ops.append(("post_small", t))                # [db2 | dg | db1] to every rank, right after the finisher
         ops.append(("write_slots", 1, t))            # dW1 GEMM, scatter epilogue
-        ops.append(("signal", GRAD1, t))
-        ops.append(("post_small", t))
-        ops.append(("signal", SMALL, t))
+        ops.append(("signal", GRAD1))
         ops.append(("write_slots", 2, t))            # dW2 GEMM
-        ops.append(("signal", GRAD2, t))
+        ops.append(("signal", GRAD2))
     return ops
 
 
-def update_stream(rank, world, steps, order=("w1", "small", "w2")):
+def update_stream(rank, world, steps, vecs_before_signal=True):
     ops = []
     for t in range(1, steps + 1):
-        for what in order:
-            if what == "w1":
-                ops += [("wait", GRAD1, t), ("adamw", 1, t), ("signal", W1, t)]
-            elif what == "w2":
-                ops += [("wait", GRAD2, t), ("adamw", 2, t), ("signal", W2, t)]
-            else:
-                ops += [("wait", SMALL, t), ("sum_small", t), ("update_vecs", t), ("record_event", "small", t)]
+        ops += [("wait", GRAD1, t), ("adamw", 1, t)]
+        small = [("sum_small", t), ("update_vecs", t)]
+        ops += (small + [("signal", W1)]) if vecs_before_signal else ([("signal", W1)] + small)
+        ops += [("wait", GRAD2, t), ("adamw", 2, t), ("signal", W2)]
     return ops
 
 
@@ -120,9 +109,7 @@ def runnable(st, mem):
         return False
     op = st.ops[st.pc]
     if op[0] == "wait":
-        return all(mem.flags[(op[1], st.rank, src)] >= op[2] for src in range(mem.world))
-    if op[0] == "wait_event":
-        return mem.events.get((st.rank, op[1], op[2]), False)
+        return mem.flags[(op[1], st.rank)] >= op[2] * mem.world
     return True
 
 
@@ -136,14 +123,11 @@ def advance(st, mem):
         return
     op = st.ops[st.pc]
     kind = op[0]
-    if kind in ("wait", "wait_event"):
+    if kind == "wait":
         st.pc += 1
     elif kind == "signal":
         for dst in range(world):
-            mem.flags[(op[1], dst, r)] = op[2]
-        st.pc += 1
-    elif kind == "record_event":
-        mem.events[(r, op[1], op[2])] = True
+            mem.flags[(op[1], dst)] += 1
         st.pc += 1
     elif kind == "read_weight":
         w, want = op[1], op[2]
@@ -214,19 +198,16 @@ def simulate(world, steps, seed, compute=compute_stream, update=update_stream):
     return mem
 
 
-@pytest.mark.parametrize("grouped", [False, True])
 @pytest.mark.parametrize("world", [1, 2, 3, 4])
-def test_no_hazard_and_no_deadlock_under_random_interleavings(world, grouped):
-    def compute(rank, w, steps):
-        return compute_stream(rank, w, steps, grouped=grouped)
-
+def test_no_hazard_and_no_deadlock_under_random_interleavings(world):
     for seed in range(150):
-        mem = simulate(world, steps=4, seed=seed, compute=compute)
+        mem = simulate(world, steps=4, seed=seed)
         assert all(c["v"] == 4 for c in mem.weight.values())
+        assert all(c["v"] == 4 for c in mem.vecs.values())
 
 
 def test_the_checker_catches_a_missing_wait():
-    """Drop the wait on the W2 flags before GEMM2: some interleaving must read stale or in-flight rows."""
+    """Drop the wait on the W2 counter before GEMM2: some interleaving must read stale or in-flight rows."""
 
     def broken(rank, world, steps):
         return [op for op in compute_stream(rank, world, steps) if op[:2] != ("wait", W2)]
@@ -237,10 +218,11 @@ def test_the_checker_catches_a_missing_wait():
 
 
 def test_the_checker_catches_a_wrong_update_order():
-    """Small vectors updated AFTER the W2 signal: a peer may re-post its small slot while this rank still sums it."""
+    """Bias / norm vectors updated AFTER the W1 signal: the next forward may read them a step stale, or a peer may re-post its
+    small slot while this rank still sums it."""
 
     def late_small(rank, world, steps):
-        return update_stream(rank, world, steps, order=("w1", "w2", "small"))
+        return update_stream(rank, world, steps, vecs_before_signal=False)
 
     with pytest.raises(Violation):
         for seed in range(600):

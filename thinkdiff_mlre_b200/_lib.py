@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("THINKDIFF_B200_LIB", os.path.join(_HERE, "libthinkdiff_b200.so"))  # override: A/B builds
 
 F32, BF16 = 0, 1
-BWD_NORM_W2, BWD_GELU_W1, BWD_ALL, BWD_SMALL2_ONLY, BWD_W2_ONLY, BWD_GELU_ONLY = 1, 2, 3, 4, 8, 16
+BWD_NORM_W2, BWD_GELU_W1, BWD_ALL, BWD_SMALL2_ONLY, BWD_W2_ONLY, BWD_GELU_ONLY, BWD_W1_ONLY = 1, 2, 3, 4, 8, 16, 32
 FWD_LINEAR1, FWD_REST, FWD_ALL, FWD_DEFER_LOSS = 1, 2, 3, 4
 STEP_CTL_SCALE_OFFSET = 20
 
@@ -54,7 +54,7 @@ SIGNATURES = {
     "td_peer_free": (_i32, [_vp]),
     "td_peer_open": (_i32, [C.c_char_p, C.POINTER(_vp)]),
     "td_peer_close": (_i32, [_vp]),
-    "td_peer_signal": (_i32, [_vp, _i32, _i32, _i32, _vp]),
+    "td_peer_signal": (_i32, [_vp, _i32, _i32, _vp]),
     "td_peer_wait": (_i32, [_vp, _i32, _i32, _f32, _vp]),
     "td_peer_post": (_i32, [_vp, _vp, _i32, _i64, _vp]),
     "td_sum_slots": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp]),

@@ -278,23 +278,23 @@ class _AlignerMSEFn(torch.autograd.Function):
 
 
 def _peer_backward(module, bwd, d: int, device):
-    """Backward schedule of the peer-memory data-parallel mode (Linear1 first): each weight-gradient GEMM stores its rows into
-    the owners' exchange buffers and is followed by a flag store; the small vectors are posted to every rank in between.
-    Returns the gradients in parameter order -- None for the two matrices, which never exist as local tensors."""
-    from .peer import ROW_GRAD1, ROW_GRAD2, ROW_SMALL
+    """Backward schedule of the peer-memory data-parallel mode: dh0 GEMM + one finisher for the three small vectors, which are
+    posted to every rank right away; then each weight-gradient GEMM stores its rows into the owners' exchange buffers and is
+    followed by a +1 on the owners' counters (GRAD1 also covers the small vectors). Returns the gradients in parameter order --
+    None for the two matrices, which never exist as local tensors."""
+    from .peer import ROW_GRAD1, ROW_GRAD2
 
     px = module._ensure_peer()
     module._peer_epoch += 1
-    e = module._peer_epoch
     small = torch.empty(3 * d, dtype=torch.float32, device=device)  # [db2 | dg | db1], GradBuckets' small layout
     db2, dg, db1 = small[:d], small[d : 2 * d], small[2 * d :]
     module._grad_flats = {"small": small}
-    bwd.gelu_linear1_small_scatter(px.dw_dst(1), db1, db2, dg, px.world)
-    px.signal(ROW_GRAD1, e)
+    bwd.gelu_and_small(db1, db2, dg)
     px.post_small(small)
-    px.signal(ROW_SMALL, e)
+    bwd.linear1_only_scatter(px.dw_dst(1), px.world)
+    px.signal(ROW_GRAD1)
     bwd.linear2_only_scatter(px.dw_dst(2), px.world)
-    px.signal(ROW_GRAD2, e)
+    px.signal(ROW_GRAD2)
     return None, db1, None, db2, dg
 
 

@@ -2,14 +2,14 @@
 // EPI_F32_SCATTER GEMM epilogue. Every rank owns the rows [r * rows/N, (r + 1) * rows/N) of each weight matrix:
 //
 //   weight-gradient GEMM (rank s)  --stores-->  slot[s] of the owner's gradient buffer     (gemm_sm100.cuh)
-//   peer_signal_kernel             --flag---->  "rank s has written step t"                 (after the GEMM, same stream)
-//   peer_wait_kernel (owner)       spins until all N flags carry step t
+//   peer_signal_kernel             --count--->  +1 on the owner's counter                   (after the GEMM, same stream)
+//   td_peer_wait (owner)           the stream waits until the counter reaches t * N (stream memory op; or peer_wait_kernel)
 //   adamw_slots_kernel (owner)     g = slot[0] + slot[1] + ... (fixed order: bit-reproducible, identical on every rank),
 //                                  AdamW on the owner's fp32 master rows, bf16 rows stored into EVERY rank's compute copy
 //   peer_signal_kernel             "owner o has written the weights of step t"; the next forward waits on those flags
 //
-// Flags are monotonically increasing step numbers in the destination rank's memory: release/acquire at system scope, no
-// resets, no barriers. A wait that sees no progress for `timeout_ns` traps (sticky error) instead of hanging the GPU.
+// Flags are monotonically increasing counters in the destination rank's memory: release/acquire at system scope, no resets, no
+// barriers.
 //
 // Reference being replaced: DDP's bucketed NCCL all-reduce of the aligner gradients + the replicated optimizer step
 // (thinkdiff/runners/runner_base.py:88-92, :98-127; thinkdiff/tasks/base_task.py:247-258).
@@ -32,13 +32,15 @@ __device__ __forceinline__ void* select_peer(const PeerPtrs& a, int i) {
   return r;
 }
 
-// Thread i < n stores `value` into element `slot` of the int32 flag array flags.p[i] lives in rank i's memory.
-__global__ void peer_signal_kernel(const PeerPtrs flags, int n, int slot, int value) {
+// Thread i < n adds 1 to counter `slot` of the int32 flag array that lives in rank i's memory (release at system scope: everything
+// this stream did before -- the GEMM's stores into that rank's slots, the AdamW's stores into its weight copy -- is visible to
+// whoever observes the new count). A row's counter reaches t * world when every rank has signalled step t.
+__global__ void peer_signal_kernel(const PeerPtrs flags, int n, int slot) {
   const int i = threadIdx.x;
   if (i < n) {
     int* f = static_cast<int*>(select_peer(flags, i)) + slot;
     __threadfence_system();
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(value) : "memory");
+    asm volatile("red.release.sys.global.add.s32 [%0], 1;" ::"l"(f) : "memory");
   }
 }
 

@@ -497,8 +497,8 @@ int bwd_from_dh2(const __nv_bfloat16* dh2, const void* x, const void* h0, const 
       TD_CUDA(cudaGetLastError());
     }
   }
-  if (phases & TD_BWD_PHASE_GELU_W1) {
-    // dW1[D, Din] = scale * dh0^T . x   (dh0 already carries the upstream scalar)
+  if (phases & (TD_BWD_PHASE_GELU_W1 | TD_BWD_PHASE_W1_ONLY)) {
+    // dW1[D, Din] = scale * dh0^T . x   (dh0 already carries the upstream scalar; W1_ONLY: dh0 is in the workspace from a GELU_ONLY call)
     memset(&p, 0, sizeof(p));
     p.M = D; p.N = Din; p.K = int(M); p.ld_out = Din; p.alpha = scale; p.out0 = dW1; p.stats = ex.stats; p.accumulate = ex.accumulate;
     int rc = launch_dw_gemm({w.dh0, D, true}, {x, Din, true}, p, sc ? sc->dW1 : nullptr, world, w.sk, st,
@@ -650,6 +650,7 @@ int bwd_dh2_impl(const void* dh2, const void* x, const void* h0, const void* h1,
   }
   if ((phases & TD_BWD_PHASE_GELU_W1) && (!x || !h0 || !W2 || !dW1 || !db1)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (phase 2)");
   if ((phases & TD_BWD_PHASE_GELU_ONLY) && (!dh2 || !h0 || !W2 || !db1)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (dh0 / db1)");
+  if ((phases & TD_BWD_PHASE_W1_ONLY) && (!x || !dW1)) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2: null pointer (dW1)");
   return bwd_from_dh2(static_cast<const __nv_bfloat16*>(dh2), x, h0, h1, W2, M, Din, D, grad_scale, grad_scale_ptr, dW1, db1,
                       dW2, db2, dg, w, phases, st, sc, ex);
 }
@@ -674,7 +675,7 @@ int32_t td_aligner_bwd_dh2_scatter(const void* dh2, const void* x, const void* h
     TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2_scatter: world=%d must be 1..%d and divide D=%d", world, kMaxPeers, D);
   ScatterDst sc;
   sc.world = world;
-  const bool need1 = (phases & TD_BWD_PHASE_GELU_W1) != 0;
+  const bool need1 = (phases & (TD_BWD_PHASE_GELU_W1 | TD_BWD_PHASE_W1_ONLY)) != 0;
   const bool need2 = (phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_W2_ONLY)) != 0;
   for (int o = 0; o < world; ++o) {
     if ((need1 && (!dW1_dst || !dW1_dst[o])) || (need2 && (!dW2_dst || !dW2_dst[o])))
@@ -822,13 +823,14 @@ int fill_peers(PeerPtrs& pp, void* const* arr, int n, const char* what) {
 }
 }  // namespace
 
-int32_t td_peer_signal(void* const* flag_arrays, int32_t n, int32_t slot, int32_t value, td_stream_t stream) {
+int32_t td_peer_signal(void* const* flag_arrays, int32_t n, int32_t slot, td_stream_t stream) {
   TD_DEVICE_OR_RETURN();
   PeerPtrs pp;
   int rc = fill_peers(pp, flag_arrays, n, "td_peer_signal");
   if (rc) return rc;
   if (slot < 0) TD_FAIL(TD_ERR_ARG, "td_peer_signal: negative slot");
-  peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pp, n, slot, value);
+  ProfScope prof("peer_signal", 0.0, (cudaStream_t)stream);
+  peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pp, n, slot);
   TD_CUDA(cudaGetLastError());
   return TD_OK;
 }
@@ -855,8 +857,9 @@ inline PFN_streamWaitValue32 stream_wait_fn() {
 int32_t td_peer_wait(const int32_t* flags, int32_t n, int32_t value, float timeout_s, td_stream_t stream) {
   TD_DEVICE_OR_RETURN();
   if (!flags || n < 1 || n > 32) TD_FAIL(TD_ERR_ARG, "td_peer_wait: 1..32 flags");
+  ProfScope prof("peer_wait", 0.0, (cudaStream_t)stream);  // (events around the wait: its span in the timeline is time spent blocked)
   if (PFN_streamWaitValue32 wait = stream_wait_fn()) {
-    // flags only ever grow (step numbers): "*addr - value >= 0" is the condition CU_STREAM_WAIT_VALUE_GEQ tests
+    // flags only ever grow (counters): "*addr - value >= 0" is the condition CU_STREAM_WAIT_VALUE_GEQ tests
     for (int i = 0; i < n; ++i) {
       CUresult r = wait((CUstream)stream, (CUdeviceptr)(uintptr_t)(flags + i), (cuuint32_t)value, CU_STREAM_WAIT_VALUE_GEQ);
       if (r != CUDA_SUCCESS) TD_FAIL(TD_ERR_DRIVER, "cuStreamWaitValue32 failed with CUresult %d", int(r));
@@ -876,6 +879,7 @@ int32_t td_peer_post(const float* src, void* const* dst, int32_t n, int64_t nume
   if (rc) return rc;
   if (!src || numel < 0 || numel % 4) TD_FAIL(TD_ERR_ARG, "td_peer_post: numel must be a non-negative multiple of 4");
   if (numel == 0) return TD_OK;
+  ProfScope prof("peer_post", 4.0 * double(numel) * n, (cudaStream_t)stream);
   peer_post_kernel<<<grid_for_rows(numel / 4, 256, 2), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src), pp, n, numel / 4);
   TD_CUDA(cudaGetLastError());
   return TD_OK;

@@ -210,7 +210,7 @@ class AlignerBackwardFromDh2:
             n += 2  # dh0 GEMM + finisher
         elif phase & (L.BWD_NORM_W2 | L.BWD_SMALL2_ONLY):
             n += 1  # finisher
-        if phase & L.BWD_GELU_W1:
+        if phase & (L.BWD_GELU_W1 | L.BWD_W1_ONLY):
             n += 1
         if phase & (L.BWD_NORM_W2 | L.BWD_W2_ONLY):
             n += 1
@@ -238,6 +238,10 @@ class AlignerBackwardFromDh2:
         """dh0 GEMM, one finisher for all three small vectors (+ the deferred loss), dW1 GEMM."""
         self._call(L.BWD_GELU_W1 | L.BWD_SMALL2_ONLY, dW1, db1, None, db2, dg)
 
+    def gelu_and_small(self, db1, db2, dg):
+        """dh0 GEMM (dh0 stays in the workspace) and ONE finisher for all three small vectors (+ the deferred loss)."""
+        self._call(L.BWD_GELU_ONLY | L.BWD_SMALL2_ONLY, None, db1, None, db2, dg)
+
     def norm_small(self, db2, dg):
         self._call(L.BWD_SMALL2_ONLY, None, None, None, db2, dg)
 
@@ -260,6 +264,10 @@ class AlignerBackwardFromDh2:
         """As ``gelu_linear1_and_small`` with dW1's rows stored to their owner ranks (``dW1_dst``: host array of ``world``
         device pointers)."""
         self._call_scatter(L.BWD_GELU_W1 | L.BWD_SMALL2_ONLY, dW1_dst, db1, None, db2, dg, world)
+
+    def linear1_only_scatter(self, dW1_dst, world: int):
+        """dW1 GEMM from the dh0 a ``gelu_and_small`` call left in the workspace, rows stored to their owner ranks."""
+        self._call_scatter(L.BWD_W1_ONLY, dW1_dst, None, None, None, None, world)
 
     def linear2_only_scatter(self, dW2_dst, world: int):
         self._call_scatter(L.BWD_W2_ONLY, None, None, dW2_dst, None, None, world)

@@ -159,7 +159,9 @@ class FusedAdamW(torch.optim.Optimizer):
     def launch_peer_update(self, name: str, t: int, epoch: int):
         """Peer data parallel (current stream = the caller's update stream): wait until every rank has stored its slot of this
         weight's gradient rows into this rank's exchange buffer, run AdamW on the summed slots (bf16 rows go straight into every
-        rank's compute copy) and raise this rank's "weights written" flag everywhere."""
+        rank's compute copy) and add 1 to the "weights written" counter everywhere. The Linear1 update also carries the three
+        replicated vectors: their slots arrived under the same GRAD1 counter, and they are updated BEFORE the W1 signal, so the
+        next forward's single wait on W1 covers b1 / b2 / g as well."""
         from .peer import ROW_GRAD1, ROW_GRAD2, ROW_W1, ROW_W2
 
         a = self.aligner
@@ -177,26 +179,16 @@ class FusedAdamW(torch.optim.Optimizer):
         px.wait(ROW_GRAD1 if which == 1 else ROW_GRAD2, epoch)
         px.adamw_rows(which, W.data[lo:hi], st["exp_avg"], st["exp_avg_sq"], g["weight_decay"], g["lr"], g["betas"], g["eps"], t,
                       self.grad_scale)
-        px.signal(ROW_W1 if which == 1 else ROW_W2, epoch)
-
-    @torch.no_grad()
-    def launch_peer_small_update(self, t: int, epoch: int):
-        """Peer data parallel: sum every rank's posted [db2 | dg | db1] (rank order, in place of the local values) and update the
-        three replicated vectors."""
-        from .peer import ROW_SMALL
-
-        a = self.aligner
-        px = a._ensure_peer()
-        small, d = a._grad_flats["small"], a.hidden_size
-        px.wait(ROW_SMALL, epoch)
-        px.sum_small(small)
-        grads = {"2.bias": small[:d], "3.weight": small[d : 2 * d], "0.bias": small[2 * d :]}
-        keys = ["2.bias", "3.weight", "0.bias"]
-        self._update_tensors(keys, t, grads)
-        named = self._named()
-        for k in keys:
-            named[k].grad = None
-        a._grad_flats["small"] = None
+        if which == 1:
+            small, d = a._grad_flats["small"], a.hidden_size
+            px.sum_small(small)  # every rank's posted [db2 | dg | db1], summed in rank order in place of the local values
+            keys = ["2.bias", "3.weight", "0.bias"]
+            self._update_tensors(keys, t, {"2.bias": small[:d], "3.weight": small[d : 2 * d], "0.bias": small[2 * d :]})
+            named = self._named()
+            for k in keys:
+                named[k].grad = None
+            a._grad_flats["small"] = None
+        px.signal(ROW_W1 if which == 1 else ROW_W2)
 
     @torch.no_grad()
     def launch_small_update(self, t: int):

@@ -10,7 +10,10 @@ step at all:
   * rank ``o`` sums the N slots in rank order inside its AdamW pass (``td_adamw_slots_step``: bit-reproducible, and every
     replica is identical by construction) and stores the updated bf16 rows into every rank's compute copy of the weight;
   * the three small vectors are posted to every rank (``td_peer_post``) and summed there in the same order;
-  * ordering is by step-number flags in the destination's memory (``td_peer_signal`` / ``td_peer_wait``).
+  * ordering is by counters in the destination's memory: ``td_peer_signal`` adds 1 to a row's counter at every rank (remote
+    atomic, release), ``td_peer_wait`` lets a stream wait -- as a stream memory operation, no kernel -- until the counter shows
+    that all ranks have signalled the step. Two sync points per step in each direction (GRAD1 / GRAD2 towards the owners,
+    W1 / W2 back); the protocol is model-checked in tests/test_peer_protocol_model.py.
 
 One exchange buffer per rank (``td_peer_alloc``: cudaMalloc + CUDA IPC handle; handles travel through
 ``torch.distributed.all_gather_object``, which is plumbing). ``ExchangeLayout`` is pure arithmetic and identical on all ranks.
@@ -25,8 +28,11 @@ from . import _lib as L
 
 MAX_PEERS = 8
 FLAG_BYTES = 4096
-# flag array (int32) rows: each row holds one flag per source rank
-ROW_GRAD1, ROW_GRAD2, ROW_SMALL, ROW_W1, ROW_W2 = 0, 1, 2, 3, 4
+# flag array (int32): one monotone counter per row, 128 bytes apart. Every rank adds 1 per step to the row's counter at every
+# destination, so "all ranks have signalled step t" is the single comparison counter >= t * world.
+#   GRAD1: dW1's rows AND the small vectors [db2 | dg | db1] of step t have been stored at their destinations
+#   GRAD2: dW2's rows;  W1: the owner's rows of W1 (and, locally, b1 / b2 / g) are updated;  W2: the owner's rows of W2
+ROW_GRAD1, ROW_GRAD2, ROW_W1, ROW_W2 = 0, 1, 2, 3
 FLAG_ROW_STRIDE = 32  # int32 elements between rows (128 bytes: one line per row)
 
 
@@ -90,8 +96,8 @@ class ExchangeLayout:
     def total_bytes(self) -> int:
         return _align(self.off_w2 + 2 * self.d * self.d)
 
-    def flag_offset(self, row: int, src: int = 0) -> int:
-        return 4 * (row * FLAG_ROW_STRIDE + src)
+    def flag_offset(self, row: int) -> int:
+        return 4 * row * FLAG_ROW_STRIDE
 
     def grad_slot_offset(self, which: int, src: int) -> int:
         """Byte offset of slot ``src`` of weight ``which`` (1 or 2) inside the owner's buffer."""
@@ -182,14 +188,14 @@ class PeerExchange:
         return self._local + self.layout.grad_slot_offset(which, 0)
 
     # -- device operations (all asynchronous on torch's current stream)
-    def signal(self, row: int, value: int):
+    def signal(self, row: int):
+        """+1 on counter ``row`` at every rank, after everything enqueued so far on the current stream."""
         L.launch_count += 1
-        L.check(L.lib().td_peer_signal(self._flag_arrays, self.world, row * FLAG_ROW_STRIDE + self.rank, int(value), L.stream_ptr()),
-                "td_peer_signal")
+        L.check(L.lib().td_peer_signal(self._flag_arrays, self.world, row * FLAG_ROW_STRIDE, L.stream_ptr()), "td_peer_signal")
 
-    def wait(self, row: int, value: int):
-        L.launch_count += 1
-        L.check(L.lib().td_peer_wait(C.c_void_p(self._local + self.layout.flag_offset(row)), self.world, int(value), self.timeout_s,
+    def wait(self, row: int, step: int):
+        """The current stream waits until every rank has signalled ``row`` ``step`` times."""
+        L.check(L.lib().td_peer_wait(C.c_void_p(self._local + self.layout.flag_offset(row)), 1, int(step) * self.world, self.timeout_s,
                                      L.stream_ptr()), "td_peer_wait")
 
     def post_small(self, small):

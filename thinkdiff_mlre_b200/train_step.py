@@ -243,7 +243,7 @@ class AlignerTrainStep:
 
     def _step_pipelined_peer(self, packed, target) -> torch.Tensor:
         """The sharded pipeline with no collectives (peer.py): gradients reach their owner from the GEMM epilogues, updated bf16
-        rows come back from the owners' AdamW kernels, and the compute stream only ever waits on step-number flags."""
+        rows come back from the owners' AdamW kernels, and the compute stream only ever waits on two counters per step."""
         from .peer import ROW_W1, ROW_W2
 
         a, opt = self.aligner, self.optimizer
@@ -251,16 +251,15 @@ class AlignerTrainStep:
         opt.grad_scale = 1.0 / self.loss_scale
         if self._pending_t is not None:
             prev = a._peer_epoch
-            px.wait(ROW_W1, prev)             # every owner has stored its rows of W1 for the previous step
-            self._wait_update("linear1")      # small vectors (b1 for GEMM1's epilogue; b2 / g for stage 2)
+            px.wait(ROW_W1, prev)             # every owner has stored its rows of W1 (and this rank its b1 / b2 / g) for the previous step
 
             def before_gemm2():
                 px.wait(ROW_W2, prev)
 
             a._between_fwd_stages = before_gemm2
             a._bf16_managed = True
-        # (the previous step's gradient buckets stay alive in self._grads_hold until the end of this step: by then the compute
-        #  stream is ordered after both of that step's updates, which read them on the update stream)
+        # (the previous step's small-vector bucket stays alive in self._grads_hold until the end of this step: by then the compute
+        #  stream is ordered after that step's updates, which read it on the update stream)
         try:
             loss = self._fwd_bwd(packed, target)
         finally:
@@ -270,16 +269,11 @@ class AlignerTrainStep:
         e = a._peer_epoch
         if not hasattr(self, "_update_stream"):
             self._update_stream = torch.cuda.Stream()
-        if not hasattr(self, "_small_done"):
-            self._small_done = torch.cuda.Event()
         grads = list(a._grad_flats.values())
         with torch.cuda.stream(self._update_stream):
-            # no event from the compute stream is needed: each update waits on flags, and this rank's own flag is stored by
-            # the compute stream right after the GEMM that produced the data
-            opt.launch_peer_update("linear1", t, e)
-            opt.launch_peer_small_update(t, e)
-            self._small_done.record(self._update_stream)
-            self._upd_done["linear1"] = self._small_done
+            # no event from the compute stream is needed: each update waits on a counter, and this rank's own +1 is issued by the
+            # compute stream right after the GEMM that produced the data
+            opt.launch_peer_update("linear1", t, e)   # (+ the three small vectors)
             opt.launch_peer_update("linear2", t, e)
         self._grads_hold = grads
         return loss
@@ -330,7 +324,6 @@ class AlignerTrainStep:
                 px, e = self.aligner._ensure_peer(), self.aligner._peer_epoch
                 px.wait(ROW_W1, e)
                 px.wait(ROW_W2, e)
-                self._wait_update("linear1")
                 self._grads_hold = None
                 self._masters_stale = True
             elif self._sharded:
