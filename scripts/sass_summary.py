@@ -11,7 +11,7 @@ import subprocess
 import sys
 
 LIB = sys.argv[1] if len(sys.argv) > 1 else "thinkdiff_mlre_b200/libthinkdiff_b200.so"
-COLS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "UTMALDG.2CTA", "UTCBAR", "UTCATOMSWS", "SYNCS", "UCGABAR", "REDG",
+COLS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "UTMALDG.2CTA", "UTMASTG", "UTMAREDG", "UTCBAR", "UTCATOMSWS", "SYNCS", "UCGABAR", "REDG",
         "ATOMG", "LDG", "STG", "LDS", "STS", "SHFL", "MUFU", "BAR"]
 
 

@@ -23,7 +23,9 @@ def short(name):
 
 
 def launches():
-    path = os.path.join(ROOT, "gpurun_out", "launches.csv")
+    path = os.path.join(ROOT, "gpurun_out", f"{TAG}_launches.csv")
+    if not os.path.isfile(path):
+        path = os.path.join(ROOT, "gpurun_out", "launches.csv")
     if not os.path.isfile(path):
         return
     rows = [r for r in csv.reader(open(path)) if len(r) > 10]
@@ -84,8 +86,12 @@ def full():
                     tag = EPI_TAG[args[3]]
                 elif args[3] == "4":
                     tag = "gemm_dW2" if "gemm_dW2" not in traffic else "gemm_dW1"
-            elif "pack_rows_kernel<0>" in name:
+            elif "pack_rows_kernel" in name:
                 tag = "pack_varlen"
+            elif "norm_mse_bwd" in name:
+                tag = "norm_mse_bwd_fused"
+            elif "adamw" in name:
+                tag = "adamw_bf16"
             elif "rmsnorm_fwd" in name:
                 tag = "rmsnorm_fwd"
             elif "rmsnorm_bwd" in name:

@@ -45,13 +45,16 @@ def test_flags_post_sum_and_adamw_slots_loopback():
 
     world, n = 4, 4096
     flags = [torch.zeros(64, dtype=torch.int32, device="cuda") for _ in range(world)]
-    # signal: element `slot` of every flag array; wait: all of one local array
-    for src in range(world):
-        L.check(L.lib().td_peer_signal(_arr(flags), world, 32 + src, 7, L.stream_ptr()), "td_peer_signal")
-    L.check(L.lib().td_peer_wait(C.c_void_p(flags[2].data_ptr() + 4 * 32), world, 7, 5.0, L.stream_ptr()), "td_peer_wait")
+    # signal: +1 on counter `slot` of every flag array (one call per "rank" and step); wait: the local counter has reached
+    # steps * world, i.e. every rank has signalled every step
+    steps = 3
+    for _ in range(steps):
+        for _src in range(world):
+            L.check(L.lib().td_peer_signal(_arr(flags), world, 32, L.stream_ptr()), "td_peer_signal")
+    L.check(L.lib().td_peer_wait(C.c_void_p(flags[2].data_ptr() + 4 * 32), 1, steps * world, 5.0, L.stream_ptr()), "td_peer_wait")
     torch.cuda.synchronize()
     for f in flags:
-        assert f[32 : 32 + world].tolist() == [7] * world and int(f.sum()) == 7 * world
+        assert int(f[32]) == steps * world and int(f.sum()) == steps * world
     # post + sum (fixed order)
     g = torch.Generator(device="cuda").manual_seed(1)
     srcs = [torch.randn(n, generator=g, device="cuda") for _ in range(world)]
