@@ -65,6 +65,28 @@ def load_synth():
 
 
 # ----------------------------------------------------------------------------------------------- clocks
+def nvml_handle(pynvml, cuda_index: int):
+    """NVML handle of CUDA device `cuda_index` of this process. NVML enumerates every GPU of the box while CUDA enumerates
+    CUDA_VISIBLE_DEVICES, so the two indices differ on a shared box: match by UUID (then PCI bus id), index only as a last resort."""
+    try:
+        import torch
+
+        props = torch.cuda.get_device_properties(cuda_index)
+        uuid = getattr(props, "uuid", None)
+        if uuid is not None:
+            try:
+                return pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                pass
+        bus = getattr(props, "pci_bus_id", None)
+        if bus is not None:
+            dom, dev = getattr(props, "pci_domain_id", 0), getattr(props, "pci_device_id", 0)
+            return pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev:02x}.0".encode())
+    except Exception:
+        pass
+    return pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+
+
 class ClockSampler:
     """Samples SM clock and throttle reasons through NVML while a timed region runs."""
 
@@ -78,7 +100,7 @@ class ClockSampler:
 
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.h = nvml_handle(pynvml, index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception as e:  # NVML missing: report that instead of guessing
             self.nv, self.err = None, repr(e)
@@ -128,7 +150,7 @@ class numa_local:
             import pynvml
 
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            h = nvml_handle(pynvml, self.index)
             words = (os.cpu_count() + 63) // 64
             mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
             cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}

@@ -134,6 +134,10 @@ int64_t td_gemm_workspace_bytes(void);
 /* Plain bf16 linear  out[M, N] = x[M, K] . W[N, K]^T (+ bias)  -- nn.Linear under autocast (F.linear). */
 int32_t td_linear_bf16(const void* x, int64_t M, int32_t K, const void* W, int32_t N, const void* bias, void* out,
                        void* workspace, int64_t workspace_bytes, td_stream_t stream);
+/* Input gradient of td_linear_bf16 for a FROZEN weight:  dx[M, K] (bf16) = dy[M, N] (bf16) . W[N, K]  -- W is contracted over
+ * its row index and read where it lies (MN-major operand), no transposed copy. Needs N % 8 == 0, K % 64 == 0. */
+int32_t td_linear_bf16_dx(const void* dy, int64_t M, int32_t N, const void* W, int32_t K, void* dx, void* workspace,
+                          int64_t workspace_bytes, td_stream_t stream);
 /* Generic entry to the tcgen05 GEMM for tests: D[M,N] (fp32) (+)= alpha * A.B^T with either operand K-major
  * ([rows, K]) or MN-major ([K, rows]); cta_pair selects cta_group::2; accumulate != 0 adds into D. */
 int32_t td_gemm_bf16_f32out(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb,
@@ -225,6 +229,25 @@ int32_t td_masked_ce_fwd_bwd(const void* logits, int32_t logits_dtype, const int
                              int64_t R, int32_t V, float grad_scale, float* loss,
                              void* dlogits /* logits_dtype, may be NULL */, void* workspace, int64_t workspace_bytes,
                              td_stream_t stream);
+
+
+/* ---- SURVEY section 8 f-1, first slice: the frozen T5 decoder's output head with its loss --------------------------
+ * Replaces `lm_logits = self.lm_head(sequence_output)` + `CrossEntropyLoss(ignore_index=-100)(lm_logits.view(-1, V),
+ * labels.view(-1))` of T5ForDecoder.forward (thinkdiff/models/mllama_vllm_t5_embed_decoder_2.py:236-246) under the bf16
+ * autocast of tasks/base_task.py:237, and the backward of both down to the decoder output:
+ *   logits[R, V]  = bf16(seq[R, K] . W_lm[V, K]^T)                     tcgen05 GEMM (lm_head has no bias, T5Config)
+ *   loss          = mean over rows with label != -100 of logsumexp(logits) - logits[label]   (fp32; row staged in smem, one read)
+ *   dlogits[R, V] = bf16((softmax - onehot) * grad_scale / n_valid)   same pass; may alias `logits` (in place) to save R*V*2 bytes
+ *   dseq[R, K]    = bf16(dlogits . W_lm)                               tcgen05 GEMM, W_lm read in place (frozen: no dW)
+ * `dlogits` and `dseq` may both be NULL (evaluation: loss only). `tie_word_embeddings` checkpoints scale seq by K^-0.5 first
+ * (:231-234); google/flan-t5-xxl -- the checkpoint every shipped config names -- is untied, so no scale is applied here.
+ * Needs K % 64 == 0, V % 32 == 0. */
+int64_t td_lm_head_ce_workspace_bytes(int64_t R);
+int32_t td_lm_head_ce_fwd_bwd(const void* seq, int64_t R, int32_t K, const void* W_lm, int32_t V, const int64_t* labels,
+                              float grad_scale, float* loss, void* logits /* [R, V] bf16 */,
+                              void* dlogits /* [R, V] bf16, may be == logits, may be NULL */,
+                              void* dseq /* [R, K] bf16, may be NULL */, void* workspace, int64_t workspace_bytes,
+                              td_stream_t stream);
 
 #ifdef __cplusplus
 }

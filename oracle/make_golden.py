@@ -9,6 +9,7 @@ the reference functions exec'd from source by ``oracle.ref_loader``:
   aligner_cfg1_fp32.npz           BASELINE config 1 (4 x 32 x 768 -> 4096, fp32): y rows, loss, sampled grad entries
   collater_{random_split,fixed_max,input_embed}.npz   the reference collater's three branches on ragged batches
   ce_small.npz                    CrossEntropyLoss(ignore_index=-100) expression of ...embed_decoder_2.py:243-246
+  lm_head_ce_small.npz            lm_head (bias-free Linear, frozen) + that loss under CPU bf16 autocast, ...embed_decoder_2.py:239-246
   lr_schedule.npz                 the two LR scheduler classes of thinkdiff/common/optims.py at fixed (epoch, step) points
                                   (``python -m oracle.make_golden lr`` regenerates only this one)
 The bf16 fixtures run the reference module under ``torch.autocast('cpu', dtype=bfloat16)`` -- the CPU analogue of the
@@ -148,6 +149,32 @@ def make_ce(name, R, V, seed):
     print(f"{name}: loss={float(loss):.6f}")
 
 
+def make_lm_head_ce(name, R, K, V, seed):
+    # the reference expressions, thinkdiff/models/mllama_vllm_t5_embed_decoder_2.py:239 and :243-246, under bf16 autocast
+    # (tasks/base_task.py:237) with the head frozen (:715-717)
+    from torch.nn import CrossEntropyLoss
+
+    rng = np.random.RandomState(seed)
+    lm_head = torch.nn.Linear(K, V, bias=False)
+    with torch.no_grad():
+        lm_head.weight.copy_(torch.from_numpy((rng.standard_normal((V, K)) * 0.5).astype(np.float32)))
+    lm_head.weight.requires_grad_(False)
+    seq = torch.from_numpy(rng.standard_normal((R, K)).astype(np.float32)).to(torch.bfloat16).requires_grad_(True)
+    labels = torch.from_numpy(rng.randint(0, V, size=R).astype(np.int64))
+    labels[rng.rand(R) < 0.3] = -100
+    labels[1] = -100
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        lm_logits = lm_head(seq)
+        loss_fct = CrossEntropyLoss(ignore_index=-100)
+        loss = loss_fct(lm_logits.view(-1, lm_logits.size(-1)), labels.view(-1))
+    loss.backward()
+    assert lm_logits.dtype == torch.bfloat16 and loss.dtype == torch.float32 and seq.grad.dtype == torch.bfloat16
+    np.savez_compressed(os.path.join(GOLDEN, name), seq=seq.detach().float().numpy(), weight=lm_head.weight.detach().numpy(),
+                        labels=labels.numpy(), logits=lm_logits.detach().float().numpy(), loss=loss.detach().numpy(),
+                        dseq=seq.grad.float().numpy())
+    print(f"{name}: loss={float(loss):.6f}")
+
+
 LR_CASES = {
     # the schedule every shipped config uses (configs/*.yaml: lr_sched / init_lr / min_lr / warmup_lr / warmup_steps / ...)
     "cosine_shipped": ("linear_warmup_cosine_lr", dict(max_epoch=40, iters_per_epoch=5000, min_lr=8e-5, init_lr=1e-4,
@@ -197,6 +224,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "lr":  # only the (later-added) schedule fixture; the others stay as committed
         os.makedirs(GOLDEN, exist_ok=True)
         return make_lr_schedule()
+    if len(sys.argv) > 1 and sys.argv[1] == "lm_head":  # only the (later-added) output-head fixture
+        os.makedirs(GOLDEN, exist_ok=True)
+        return make_lm_head_ce("lm_head_ce_small.npz", 40, 128, 992, 11)
     os.makedirs(GOLDEN, exist_ok=True)
     torch.manual_seed(0)
     make_aligner("aligner_small_fp32.npz", 64, 128, (3, 7, 64), 11, autocast=False, full=True)
@@ -220,6 +250,7 @@ def main():
                   dict(use_input_embed=1, use_output_embed=1, random_split_output_embed=1, output_embed_max_split_len=128,
                        output_embed_max_len=64, input_embed_max_len=10), lens, 16, 104)
     make_ce("ce_small.npz", 24, 512, 7)
+    make_lm_head_ce("lm_head_ce_small.npz", 40, 128, 992, 11)
     make_lr_schedule()
 
 

@@ -178,3 +178,23 @@ def test_masked_mse_matches_torch():
     np.testing.assert_allclose(loss, ref.item(), rtol=1e-6)
     np.testing.assert_allclose(dy, yt.grad.numpy(), rtol=1e-6, atol=1e-9)
     assert n == 6
+
+
+def test_lm_head_ce_restatement_matches_reference_expression_golden():
+    """oracle/t5_head_ref.py (frozen lm_head + CE + backward to the decoder output, section 8 f-1) vs the reference's expression
+    executed by torch under CPU bf16 autocast (tests/golden/lm_head_ce_small.npz, written by oracle/make_golden.py)."""
+    from oracle import t5_head_ref
+    from oracle.golden import load_golden
+
+    g = load_golden("lm_head_ce_small.npz")
+    loss, dseq, logits = t5_head_ref.lm_head_ce_fwd_bwd(g["seq"], g["weight"], g["labels"])
+    np.testing.assert_allclose(loss, g["loss"], rtol=1e-5)
+    # bf16 outputs: identical except where a different fp32 summation order flips the last bf16 bit
+    assert np.abs(logits - g["logits"]).max() <= 2.0 ** -7 * np.abs(g["logits"]).max()
+    assert (logits != g["logits"]).mean() < 5e-3
+    assert np.linalg.norm(dseq - g["dseq"]) / np.linalg.norm(g["dseq"]) < 1e-3
+    ignored = g["labels"] == -100
+    assert ignored.any() and not dseq[ignored].any() and not g["dseq"][ignored].any()
+    # the K / V projection shape: a frozen bias-free Linear and its input gradient
+    y = t5_head_ref.frozen_linear_fwd(g["seq"], g["weight"])
+    assert np.array_equal(y, logits)

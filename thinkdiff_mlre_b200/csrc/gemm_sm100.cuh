@@ -340,19 +340,25 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
       const uint32_t b = st.aux_use & 1;
       mbar_wait(&aux_bar[b], (st.aux_use >> 1) & 1);
       st.aux_use++;
+      // Rows past M need no predicate: their A rows and their aux box are zero-filled by the TMA, so t = 0 and the output is
+      // 0 * gelu'(0) = 0. Rounding to bf16 goes through the packed conversion (two values per ALU-pipe instruction).
       float colsum[32];
       uint4 outp[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float x[8], h[8];
+        float x[8];
+        uint32_t w[4];
         unpack8(*reinterpret_cast<const uint4*>(aux_box + b * 2048 + box64_off(lane, q)), x);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float t = bf16_round(alpha * __uint_as_float(v[q * 8 + j]));
-          h[j] = row_ok ? bf16_round(t * gelu_grad_fast(x[j])) : 0.f;
-          colsum[q * 8 + j] = h[j];
+        for (int j = 0; j < 8; j += 2) {
+          float t0 = alpha * __uint_as_float(v[q * 8 + j]), t1 = alpha * __uint_as_float(v[q * 8 + j + 1]);
+          bf16_round2(t0, t1);
+          float h0 = t0 * gelu_grad_fast(x[j]), h1 = t1 * gelu_grad_fast(x[j + 1]);
+          w[j >> 1] = bf16_round2(h0, h1);
+          colsum[q * 8 + j] = h0;
+          colsum[q * 8 + j + 1] = h1;
         }
-        outp[q] = pack8(h);
+        outp[q] = make_uint4(w[0], w[1], w[2], w[3]);
       }
       stage_acquire(lane, true);  // (also orders every lane's aux reads before the next request overwrites that box)
 #pragma unroll
@@ -377,6 +383,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float b[8], h[8];
+        uint32_t w0[4], w1[4];
         if (p.bias != nullptr) {
           unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias + col0) + q), b);
         } else {
@@ -384,13 +391,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
           for (int j = 0; j < 8; ++j) b[j] = 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) h[j] = bf16_round(__uint_as_float(v[q * 8 + j]) + b[j]);
-        o0[q] = pack8(h);
+        for (int j = 0; j < 8; j += 2) {  // bf16 rounding through the packed conversion (ALU pipe), two values at a time
+          h[j] = __uint_as_float(v[q * 8 + j]) + b[j];
+          h[j + 1] = __uint_as_float(v[q * 8 + j + 1]) + b[j + 1];
+          w0[j >> 1] = bf16_round2(h[j], h[j + 1]);
+        }
+        o0[q] = make_uint4(w0[0], w0[1], w0[2], w0[3]);
         if constexpr (EPI == EPI_BIAS_GELU) {
-          float g[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = gelu_fast(h[j]);
-          o1[q] = pack8(g);
+          for (int j = 0; j < 8; j += 2) w1[j >> 1] = pack_bf16x2(gelu_fast(h[j]), gelu_fast(h[j + 1]));
+          o1[q] = make_uint4(w1[0], w1[1], w1[2], w1[3]);
         }
         if constexpr (EPI == EPI_BIAS_SSQ) {
 #pragma unroll

@@ -294,18 +294,38 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
+// Round two fp32 values to bf16 (round-to-nearest-even) with ONE packed conversion on the ALU pipe and get them back as fp32:
+// the scalar form (F2F.BF16.F32) is an XU-pipe instruction -- quarter rate, the pipe the GELU's MUFU ops need.
+__device__ __forceinline__ uint32_t bf16_round2(float& a, float& b) {
+  const uint32_t p = pack_bf16x2(a, b);
+  a = bf16lo(p);
+  b = bf16hi(p);
+  return p;
+}
+// MUFU ops without the denormal-range scaling the libm-style wrappers add (3-4 extra instructions each): the arguments here
+// are never in those ranges (ex2: x <= 0, flushing a denormal result to zero is exact enough; rcp: the argument is >= 1).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Fast GELU(erf) for the GEMM epilogues. Phi(-|x|) = 0.5 erfc(|x| / sqrt 2) by Abramowitz-Stegun 7.1.26
 // (|abs error| <= 7.5e-8 on Phi), sharing ONE exponential e^{-x^2/2} between the cdf and the pdf:
-// 2 MUFU (ex2, rcp) + ~14 FMA-pipe ops per element instead of erff's ~45. Outputs are rounded to bf16 afterwards.
+// 2 MUFU (ex2, rcp) + 12 FMA-pipe ops per element instead of erff's ~45. Outputs are rounded to bf16 afterwards.
 __device__ __forceinline__ float normal_cdf_pdf(float x, float& pdf) {
-  const float ax = fabsf(x);
-  const float e = exp2f(-0.72134752044448170368f * x * x);                   // e^{-x^2/2}
-  const float t = __fdividef(1.0f, fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  const float q = 0.5f * t * poly * e;                                       // Phi(-|x|)
+  const float e = ex2_approx((-0.72134752044448170368f * x) * x);            // e^{-x^2/2}
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);           // (the 0.5 of Phi is folded into the coefficients)
+  poly = fmaf(t, poly, 0.5f * 1.421413741f);
+  poly = fmaf(t, poly, 0.5f * -0.284496736f);
+  poly = fmaf(t, poly, 0.5f * 0.254829592f);
+  const float q = (t * poly) * e;                                            // Phi(-|x|)
   pdf = 0.39894228040143267794f * e;
   return x >= 0.f ? 1.0f - q : q;
 }

@@ -302,6 +302,18 @@ int32_t td_linear_bf16(const void* x, int64_t M, int32_t K, const void* W, int32
   return launch_gemm<2, false, false, EPI_BF16>({x, K, false}, {W, K, false}, p, sk_ws_or_null(ws, ws_bytes), (cudaStream_t)stream, "gemm_linear");
 }
 
+int32_t td_linear_bf16_dx(const void* dy, int64_t M, int32_t N, const void* W, int32_t K, void* dx, void* ws, int64_t ws_bytes,
+                          td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (M < 0 || K <= 0 || N <= 0 || N % 8 || K % 64) TD_FAIL(TD_ERR_UNSUPPORTED, "td_linear_bf16_dx: need N %% 8 == 0, K %% 64 == 0");
+  if (M == 0) return TD_OK;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = int(M); p.N = K; p.K = N;  // output [M, K]; the contraction runs over the N rows of W
+  p.out0 = dx; p.ld_out = K; p.alpha = 1.f;
+  return launch_gemm<2, false, true, EPI_BF16>({dy, N, false}, {W, K, true}, p, sk_ws_or_null(ws, ws_bytes), (cudaStream_t)stream, "gemm_linear_dx");
+}
+
 int32_t td_gemm_bf16_f32out(const void* A, int64_t lda, int32_t a_mn, const void* B, int64_t ldb, int32_t b_mn, int64_t M,
                             int32_t N, int64_t K, float alpha, float* out, int32_t cta_pair, int32_t accumulate, void* ws,
                             int64_t ws_bytes, td_stream_t stream) {
@@ -1008,6 +1020,28 @@ int32_t td_masked_ce_fwd_bwd(const void* logits, int32_t dtype, const int64_t* l
   loss_finish_kernel<<<1, 256, 0, st>>>(row_loss, int(R), meta, 1.0f, loss);
   TD_CUDA(cudaGetLastError());
   return TD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ lm_head + CE (8 f-1)
+int64_t td_lm_head_ce_workspace_bytes(int64_t R) { return td_loss_workspace_bytes(R) + 256 + td_gemm_workspace_bytes(); }
+
+int32_t td_lm_head_ce_fwd_bwd(const void* seq, int64_t R, int32_t K, const void* W_lm, int32_t V, const int64_t* labels,
+                              float grad_scale, float* loss, void* logits, void* dlogits, void* dseq, void* ws, int64_t ws_bytes,
+                              td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (R < 0 || K <= 0 || V <= 0 || K % 64 || V % 32) TD_FAIL(TD_ERR_UNSUPPORTED, "td_lm_head_ce_fwd_bwd: need K %% 64 == 0 and V %% 32 == 0 (K=%d V=%d)", K, V);
+  if (!loss || (R > 0 && (!seq || !W_lm || !labels || !logits))) TD_FAIL(TD_ERR_ARG, "td_lm_head_ce_fwd_bwd: null pointer");
+  if (dseq && !dlogits) TD_FAIL(TD_ERR_ARG, "td_lm_head_ce_fwd_bwd: dseq needs a dlogits buffer (it may alias logits)");
+  if (!ws || ws_bytes < td_lm_head_ce_workspace_bytes(R)) TD_FAIL(TD_ERR_ARG, "td_lm_head_ce_fwd_bwd: workspace too small");
+  const int64_t loss_bytes = (td_loss_workspace_bytes(R) + 255) / 256 * 256;
+  char* sk = static_cast<char*>(ws) + loss_bytes;
+  const int64_t sk_bytes = ws_bytes - loss_bytes;
+  int rc = td_linear_bf16(seq, R, K, W_lm, V, nullptr, logits, sk, sk_bytes, stream);
+  if (rc) return rc;
+  rc = td_masked_ce_fwd_bwd(logits, TD_DTYPE_BF16, labels, R, V, grad_scale, loss, dlogits, ws, loss_bytes, stream);
+  if (rc) return rc;
+  if (dseq) rc = td_linear_bf16_dx(dlogits, R, V, W_lm, K, dseq, sk, sk_bytes, stream);
+  return rc;
 }
 
 }  // extern "C"

@@ -55,3 +55,57 @@ class _MaskedCE(torch.autograd.Function):
 def masked_cross_entropy(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
     """``CrossEntropyLoss(ignore_index=-100)`` over ``logits[..., V]`` / ``labels[...]`` (int64)."""
     return _MaskedCE.apply(logits, labels)
+
+
+class _LMHeadCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, seq, weight, labels):
+        s2 = seq.reshape(-1, seq.shape[-1]).to(torch.bfloat16).contiguous()
+        w = weight.detach()
+        w = w if w.dtype == torch.bfloat16 else w.to(torch.bfloat16)  # autocast's cast of the frozen fp32 weight
+        loss, dseq, _ = ops.lm_head_ce(s2, w.contiguous(), labels.reshape(-1).contiguous(), 1.0, want_grad=ctx.needs_input_grad[0])
+        ctx.dseq, ctx.shape, ctx.dtype = dseq, seq.shape, seq.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        dseq = ctx.dseq
+        ctx.dseq = None
+        return (dseq.mul_(g.to(dseq.dtype))).view(ctx.shape).to(ctx.dtype), None, None
+
+
+def lm_head_cross_entropy(sequence_output: torch.Tensor, lm_head_weight: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """``CrossEntropyLoss(ignore_index=-100)(lm_head(sequence_output).view(-1, V), labels.view(-1))`` of the frozen T5 decoder
+    (thinkdiff/models/mllama_vllm_t5_embed_decoder_2.py:236-246) as one call: tcgen05 GEMM -> single-read CE (the logits' gradient
+    overwrites them in place) -> tcgen05 GEMM back to ``sequence_output``. The head is frozen (the whole T5 is,
+    ...embed_decoder_2.py:715-717, `freeze_language`), so no weight gradient is formed. SURVEY.md section 8 f-1, first slice."""
+    if lm_head_weight.requires_grad:
+        raise NotImplementedError("lm_head_cross_entropy: the T5 head is frozen in ThinkDiff; a trainable head has no kernel path")
+    return _LMHeadCE.apply(sequence_output, lm_head_weight, labels)
+
+
+class _FrozenLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight):
+        x2 = x.reshape(-1, x.shape[-1]).to(torch.bfloat16).contiguous()
+        w = weight.detach()
+        w = (w if w.dtype == torch.bfloat16 else w.to(torch.bfloat16)).contiguous()
+        ctx.w, ctx.shape, ctx.dtype = w, x.shape, x.dtype
+        return ops.linear_bf16(x2, w).view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx = ops.linear_bf16_dx(dy.reshape(-1, dy.shape[-1]).to(torch.bfloat16).contiguous(), ctx.w)
+        return dx.view(ctx.shape).to(ctx.dtype), None
+
+
+def frozen_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """Bias-free ``nn.Linear`` with a frozen weight under bf16 autocast, forward and input gradient on the tcgen05 GEMM -- the
+    shape of every projection of the frozen T5 decoder. First use: the cross-attention K / V projections of the aligner output
+    (``T5Attention.k`` / ``.v`` applied to ``encoder_hidden_states``, transformers T5 as pinned by requirements.txt:14, called from
+    ...embed_decoder_2.py:211-224), which can take the PACKED rows ``[M, 4096]`` straight from ``forward_packed``: with
+    ``weight = cat([Wk, Wv])`` one GEMM yields ``[M, 2 * inner]`` and one GEMM returns the gradient to the aligner output."""
+    if weight.requires_grad:
+        raise NotImplementedError("frozen_linear: the weight must not require grad (the T5 decoder is frozen in ThinkDiff)")
+    return _FrozenLinear.apply(x, weight)
+

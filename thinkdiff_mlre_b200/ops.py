@@ -318,6 +318,22 @@ def linear_bf16(x, W, bias=None, stream_k: bool = True):
     return out
 
 
+def linear_bf16_dx(dy, W, stream_k: bool = True):
+    """Input gradient of ``linear_bf16`` for a frozen weight: dy [M, N] bf16, W [N, K] bf16 (nn.Linear layout) -> dx [M, K] bf16.
+    W is contracted over its row index and read in place (MN-major tensor-core operand)."""
+    _need_cuda(dy, W)
+    M, N = dy.shape
+    if W.shape[0] != N or dy.dtype != torch.bfloat16 or W.dtype != torch.bfloat16:
+        raise TypeError("linear_bf16_dx: dy [M, N] and W [N, K] must be bfloat16")
+    K = W.shape[1]
+    dx = torch.empty((M, K), dtype=torch.bfloat16, device=dy.device)
+    ws, ws_bytes = gemm_workspace(dy.device, stream_k)
+    L.launch_count += 1
+    L.check(L.lib().td_linear_bf16_dx(L.ptr(_contig(dy, "dy")), M, N, L.ptr(_contig(W, "W")), K, L.ptr(dx), L.ptr(ws), ws_bytes,
+                                      L.stream_ptr()), "td_linear_bf16_dx")
+    return dx
+
+
 def gemm_f32out(A, B, a_mn_major: bool, b_mn_major: bool, alpha: float = 1.0, cta_pair: bool = True, stream_k: bool = True,
                 out=None):
     """Test entry: D[M, N] fp32 = alpha * A.B^T; K-major operand = [rows, K], MN-major operand = [K, rows].
@@ -374,3 +390,32 @@ def masked_ce_fwd_bwd(logits, labels, grad_scale: float = 1.0, want_grad: bool =
                                          R, V, grad_scale, L.ptr(loss), L.ptr(dz), L.ptr(ws), ws_bytes, L.stream_ptr()),
             "td_masked_ce_fwd_bwd")
     return loss, dz
+
+
+def lm_head_ce(seq, W_lm, labels, grad_scale: float = 1.0, want_grad: bool = True, keep_logits: bool = False):
+    """Frozen T5 output head + loss (thinkdiff/models/mllama_vllm_t5_embed_decoder_2.py:236-246 under bf16 autocast) and their
+    backward down to the decoder output: seq [R, K] bf16, W_lm [V, K] bf16, labels int64 [R] (-100 = ignore).
+    Returns (loss fp32 scalar, dseq [R, K] bf16 or None, logits [R, V] bf16 or None). Unless ``keep_logits``, the gradient of the
+    logits overwrites them in place (one [R, V] buffer instead of two)."""
+    _need_cuda(seq, W_lm, labels)
+    R, K = seq.shape
+    V = W_lm.shape[0]
+    if seq.dtype != torch.bfloat16 or W_lm.dtype != torch.bfloat16 or W_lm.shape[1] != K:
+        raise TypeError("lm_head_ce: seq [R, K] and W_lm [V, K] must be bfloat16")
+    if labels.dtype != torch.int64 or labels.numel() != R:
+        raise TypeError("labels must be int64 [R]")
+    dev = seq.device
+    logits = torch.empty((R, V), dtype=torch.bfloat16, device=dev)
+    dlogits = None
+    if want_grad:
+        dlogits = torch.empty_like(logits) if keep_logits else logits
+    dseq = torch.empty((R, K), dtype=torch.bfloat16, device=dev) if want_grad else None
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    ws_bytes = L.lib().td_lm_head_ce_workspace_bytes(R)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    L.launch_count += 5 if want_grad else 4
+    L.check(L.lib().td_lm_head_ce_fwd_bwd(L.ptr(_contig(seq, "seq")), R, K, L.ptr(_contig(W_lm, "W_lm")), V, L.ptr(_contig(labels, "labels")),
+                                          grad_scale, L.ptr(loss), L.ptr(logits), L.ptr(dlogits), L.ptr(dseq), L.ptr(ws), ws_bytes,
+                                          L.stream_ptr()), "td_lm_head_ce_fwd_bwd")
+    return loss, dseq, (logits if keep_logits or not want_grad else None)
+
