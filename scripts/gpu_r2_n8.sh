@@ -27,15 +27,14 @@ timeout 200 python bench.py --steps $STEPS --warmup 5 --no-cpu-baseline --no-eag
 run n${N}_cfg2 $N --timeline-out gpurun_out/r02s_n${N}_timeline_%r.json
 run n${N}_cfg5 $N --workload cfg5 --no-e2e
 run n${N}_cfg4 $N --workload cfg4
-timeout 200 python bench.py --steps $STEPS --warmup 5 --no-cpu-baseline --no-eager-bar --no-e2e --workload cfg5 > gpurun_out/r02s_n1_cfg5.json 2> gpurun_out/r02s_n1_cfg5.err; summ n1_cfg5 gpurun_out/r02s_n1_cfg5.json
 python - $N <<'PY'
 import json, sys
 n = int(sys.argv[1])
 try:
     a, b = json.load(open("gpurun_out/r02s_n1.json")), json.load(open(f"gpurun_out/r02s_n{n}_cfg2.json"))
     print(f"cfg2 efficiency N={n}: {b['value'] / (n * a['value']):.3f}   e2e efficiency {b['e2e']['value'] / (n * a['e2e']['value']):.3f}")
-    a, b = json.load(open("gpurun_out/r02s_n1_cfg5.json")), json.load(open(f"gpurun_out/r02s_n{n}_cfg5.json"))
-    print(f"cfg5 efficiency N={n}: {b['value'] / (n * a['value']):.3f}")
+    b = json.load(open(f"gpurun_out/r02s_n{n}_cfg5.json"))
+    print(f"cfg5 N={n}: {b['value'] / 1e6:.2f} M tok/s, step TFLOP/s/GPU {b['step_tflops_per_gpu']:.0f}, frac burst {b['step_frac_of_bf16_burst']:.3f}")
 except Exception as e:
     print("efficiency table failed", e)
 PY
