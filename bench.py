@@ -582,13 +582,26 @@ def main():
     aligner = td.ThinkDiffAligner(din, D).to(dev)
     fused = args.optimizer == "fused" and args.loss_path == "fused"
     pipelined = fused and not args.no_pipeline
-    dp_mode = None
+    dp_mode, dp_fallback = None, None
     if world > 1 or args.dp in ("peer", "sharded"):
         dp_mode = "peer" if args.dp == "auto" else args.dp
         if not (pipelined and D % world == 0) and dp_mode in ("peer", "sharded"):
             dp_mode = "allreduce"
         aligner.enable_data_parallel(overlap=not args.no_overlap, defer_wait=args.optimizer == "fused", sharded=dp_mode in ("sharded", "peer"),
                                      peer=dp_mode == "peer")
+        if dp_mode == "peer":
+            # map the exchange buffers now (collective). `--dp auto`: a box without peer access / CUDA IPC falls back to the NCCL
+            # row-sharded exchange on every rank (the set-up fails on all ranks or on none) and the line says so.
+            from thinkdiff_mlre_b200.peer import PeerSetupError
+
+            try:
+                aligner._ensure_peer()
+            except PeerSetupError as e:
+                if args.dp != "auto":
+                    raise
+                dp_fallback = str(e)[:300]
+                dp_mode = "sharded"
+                aligner.enable_data_parallel(overlap=not args.no_overlap, defer_wait=True, sharded=True, peer=False)
     opt = td.FusedAdamW(aligner, lr=1e-4, weight_decay=0.05) if args.optimizer == "fused" else make_reference_optimizer(aligner)
     stepper = td.AlignerTrainStep(aligner, opt, fused_loss=args.loss_path == "fused", pipelined=pipelined)
 
@@ -769,7 +782,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": dict(workload_config(args.workload, world), loss_path=args.loss_path, optimizer_impl=args.optimizer, pipelined_updates=pipelined,
-                                                 dp_exchange=dp_mode, sharding_mode=args.sharding if world > 1 else None, fp32_master_sync="after the timed region (bf16 compute copies and AdamW are inside it)" if dp_mode in ("peer", "sharded") else None),
+                                                 dp_exchange=dp_mode, dp_exchange_fallback=dp_fallback, sharding_mode=args.sharding if world > 1 else None, fp32_master_sync="after the timed region (bf16 compute copies and AdamW are inside it)" if dp_mode in ("peer", "sharded") else None),
             "clocks": clk, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "eager_bar": bar, "dp_parity": dp_parity,
             "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_peak": step_tflops / tc_peak,

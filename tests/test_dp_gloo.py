@@ -92,3 +92,37 @@ def test_bucket_views_alias_flat_storage():
     assert gb.linear2.numel() == D * D + 2 * D and gb.linear1.numel() == D * DIN + D
     assert float(gb.linear2.sum()) == D * D + 2 * D + 3 * D and float(gb.linear1.sum()) == 4 * D * DIN + 5 * D
     assert [t.shape for t in gb.in_parameter_order()] == [(D, DIN), (D,), (D, D), (D,), (D,)]
+
+
+def _peer_setup_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from thinkdiff_mlre_b200.peer import PeerExchange, PeerSetupError
+
+        try:
+            PeerExchange(192, 512, None, torch.device("cuda", 0))
+            ret.put((rank, "no error"))
+        except PeerSetupError as e:
+            ret.put((rank, str(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_setup_fails_on_every_rank_with_one_message():
+    """No GPU here, so allocating the exchange buffer fails on both ranks: the set-up is collective and must raise the SAME
+    PeerSetupError everywhere (bench.py's `--dp auto` then falls back to the NCCL exchange on all ranks) instead of leaving a rank
+    blocked in the handle exchange."""
+    if torch.cuda.is_available():
+        pytest.skip("exercises the failure path of a box without CUDA")
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_setup_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(ret.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0] == got[1] and got[0].startswith("peer data parallel set-up failed") and "rank 0" in got[0] and "rank 1" in got[0]

@@ -121,6 +121,11 @@ class _DeviceBytes:
         self._owner = owner  # keeps the allocation alive as long as any tensor aliases it
 
 
+class PeerSetupError(RuntimeError):
+    """Raised on EVERY rank when the exchange buffers cannot be allocated or mapped on some rank (no peer access, CUDA IPC not
+    permitted in this container, out of memory): nothing is left mapped, the NCCL exchange modes remain usable."""
+
+
 class PeerExchange:
     """This rank's exchange buffer + the mapped buffers of the other ranks, and the five tiny device operations on them."""
 
@@ -138,28 +143,48 @@ class PeerExchange:
         lay = self.layout
         ptr, handle = C.c_void_p(), C.create_string_buffer(64)
         self._torch_backing = None
-        if self.world == 1 and os.environ.get("TD_PEER_NO_IPC") == "1":
-            # developer A/B: the same layout in ordinary caching-allocator memory (single rank only: nothing to export)
-            self._torch_backing = torch.zeros((lay.total_bytes,), dtype=torch.uint8, device=self.device)
-            ptr = C.c_void_p(self._torch_backing.data_ptr())
-        else:
-            with torch.cuda.device(self.device):
-                L.check(L.lib().td_peer_alloc(lay.total_bytes, C.byref(ptr), handle), "td_peer_alloc")
-        self._local = int(ptr.value)
-        self._opened = []
+        self._local, self._opened = 0, []
+        # Set-up is COLLECTIVE and must fail on all ranks or on none: a rank whose allocation / mapping fails still takes part in
+        # the exchanges below, then every rank raises the same PeerSetupError (callers may fall back to the NCCL exchange).
+        err = None
+        try:
+            if self.world == 1 and os.environ.get("TD_PEER_NO_IPC") == "1":
+                # developer A/B: the same layout in ordinary caching-allocator memory (single rank only: nothing to export)
+                self._torch_backing = torch.zeros((lay.total_bytes,), dtype=torch.uint8, device=self.device)
+                ptr = C.c_void_p(self._torch_backing.data_ptr())
+            else:
+                with torch.cuda.device(self.device):
+                    L.check(L.lib().td_peer_alloc(lay.total_bytes, C.byref(ptr), handle), "td_peer_alloc")
+            self._local = int(ptr.value)
+        except Exception as e:  # noqa: BLE001  (reported collectively below)
+            err = f"rank {self.rank}: {e}"
         self.base = [0] * self.world  # base[o] = address of rank o's buffer in THIS process
         self.base[self.rank] = self._local
         if self.world > 1:
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle.raw), group=group)
-            with torch.cuda.device(self.device):
-                for o, h in enumerate(handles):
-                    if o == self.rank:
-                        continue
-                    q = C.c_void_p()
-                    L.check(L.lib().td_peer_open(h, C.byref(q)), f"td_peer_open(rank {o})")
-                    self.base[o] = int(q.value)
-                    self._opened.append(int(q.value))
+            dist.all_gather_object(handles, None if err else bytes(handle.raw), group=group)
+            if err is None and all(h is not None for h in handles):
+                try:
+                    with torch.cuda.device(self.device):
+                        for o, h in enumerate(handles):
+                            if o == self.rank:
+                                continue
+                            q = C.c_void_p()
+                            L.check(L.lib().td_peer_open(h, C.byref(q)), f"td_peer_open(rank {o})")
+                            self.base[o] = int(q.value)
+                            self._opened.append(int(q.value))
+                except Exception as e:  # noqa: BLE001
+                    err = f"rank {self.rank}: {e}"
+            elif err is None:
+                err = ""  # another rank failed to allocate; its message arrives below
+            errs = [None] * self.world
+            dist.all_gather_object(errs, err, group=group)
+            errs = [e for e in errs if e]
+            if errs or err is not None:
+                self._release()
+                raise PeerSetupError("peer data parallel set-up failed: " + "; ".join(errs))
+        elif err is not None:
+            raise PeerSetupError("peer data parallel set-up failed: " + err)
         self._bytes = torch.as_tensor(_DeviceBytes(self._local, lay.total_bytes, self), device=self.device)
         # local views
         self.flags = self._view(0, FLAG_BYTES, torch.int32)
@@ -222,6 +247,15 @@ class PeerExchange:
         L.check(L.lib().td_adamw_slots_step(L.ptr(param_rows), C.c_void_p(self.grad_slots_ptr(which)), n, self.world, L.ptr(exp_avg),
                                             L.ptr(exp_avg_sq), self._w_dst[which], self.world, n, weight_decay, lr, betas[0], betas[1],
                                             eps, int(step), grad_scale, None, L.stream_ptr()), "td_adamw_slots_step")
+
+    def _release(self):
+        """Undo a partial set-up (no collectives, no synchronisation)."""
+        for q in self._opened:
+            L.lib().td_peer_close(C.c_void_p(q))
+        self._opened = []
+        if self._local and self._torch_backing is None:
+            L.lib().td_peer_free(C.c_void_p(self._local))
+        self._local = 0
 
     def close(self):
         torch = self.torch
