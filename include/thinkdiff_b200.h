@@ -203,17 +203,33 @@ int32_t td_adamw_slots_step(float* param, const float* grad_slots, int64_t slot_
                             float grad_scale, const void* step_ctl, td_stream_t stream);
 /* td_aligner_bwd_dh2 with the two weight gradients row-scattered: dW?_dst[o] = [D / world, cols] fp32 block for the rows
  * rank o owns. Every output element is stored exactly once (bit-reproducible) with coalesced 128-byte stores. */
+/* Optional extras of td_aligner_bwd_dh2_scatter: the exchange protocol's tiny launches folded into the kernels of the call.
+ *   signal_flags / signal_slot : the LAST weight-gradient GEMM of the call, once ALL of its stores have completed, adds 1 to int32
+ *                                element `signal_slot` of every rank's flag array (what td_peer_signal after the call would do);
+ *   small_dst / small_base / small_numel : the finisher launch stores every output that lies in [small_base, small_base +
+ *                                small_numel) -- this rank's [db2 | dg | db1] bucket -- at the same offset into small_dst[o], this
+ *                                rank's slot at every rank (what td_peer_post after the call would do). */
+typedef struct td_peer_fold {
+  void* const* signal_flags; /* [host] world device pointers, or NULL */
+  int32_t signal_slot;
+  void* const* small_dst;    /* [host] world device pointers, or NULL */
+  const float* small_base;
+  int64_t small_numel;
+} td_peer_fold;
 int32_t td_aligner_bwd_dh2_scatter(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
                                    const void* norm_partials, int64_t M, int32_t Din, int32_t D, float grad_scale,
                                    const float* grad_scale_ptr, float* const* dW1_dst /*[host]*/, float* db1,
                                    float* const* dW2_dst /*[host]*/, float* db2, float* dg, float* loss_out, float* stats,
-                                   int32_t world, void* workspace, int64_t workspace_bytes, int32_t phases,
-                                   td_stream_t stream);
+                                   int32_t world, int32_t rank /* of the caller; < 0: no traffic shaping */,
+                                   const td_peer_fold* fold /*[host] or NULL*/, void* workspace, int64_t workspace_bytes,
+                                   int32_t phases, td_stream_t stream);
 /* Test entry for the scatter epilogue: out[M, N] = alpha * A^T.B with A [K, M], B [K, N] (both MN-major, the weight-gradient
- * shape), rows [o M/world, (o+1) M/world) written to dst[o] ([M / world, N] fp32). */
+ * shape), rows [o M/world, (o+1) M/world) written to dst[o] ([M / world, N] fp32). `rank` >= 0 (and an owner's rows being whole
+ * 256-row tiles) selects the owner-grouped tile order rotated by rank that the data-parallel step uses, so that the N ranks'
+ * GEMMs store to N different owners at any moment; rank < 0 keeps the tile order -- and the bits -- of the local-output GEMM. */
 int32_t td_gemm_tn_scatter(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int32_t N, int64_t K,
-                           float alpha, float* const* dst /*[host]*/, int32_t world, void* workspace, int64_t workspace_bytes,
-                           td_stream_t stream);
+                           float alpha, float* const* dst /*[host]*/, int32_t world, int32_t rank, void* workspace,
+                           int64_t workspace_bytes, td_stream_t stream);
 
 /* ---- (3) masked losses, forward + gradient in one pass -----------------------------------------------------
  * Cross entropy replaces `CrossEntropyLoss(ignore_index=-100)(lm_logits.view(-1, V), labels.view(-1))`

@@ -2,26 +2,19 @@
 equal DDP's semantics -- the mean over ranks of each rank's own mean-loss gradients (runner_base.py:88-92) -- computed
 here by the oracle in one process. The CUDA kernels are not involved (no GPU here); gradients come from the oracle."""
 import os
-import socket
 
 import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
-import torch.multiprocessing as mp
 
+from _mp import spawn_ranks
 from oracle import aligner_ref
 from thinkdiff_mlre_b200.aligner import DataParallelState, GradBuckets
 from thinkdiff_mlre_b200.sharding import shard_bounds
 
 DIN, D, SEQS = 64, 128, 5
 NAMES = ("dW1", "db1", "dW2", "db2", "dg")
-
-
-def _free_port():
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
 
 
 def _global_batch():
@@ -40,9 +33,8 @@ def _shard_grads(xs, ts, params):
     return [out[n] for n in NAMES]
 
 
-def _worker(rank, world, port, overlap, ret):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+def _worker(rank, world, init, overlap, ret):
+    dist.init_process_group("gloo", init_method=init, rank=rank, world_size=world)
     try:
         params = aligner_ref.init_params_numpy(DIN, D, seed=3)
         xs, ts = _global_batch()
@@ -64,16 +56,7 @@ def _worker(rank, world, port, overlap, ret):
 @pytest.mark.parametrize("overlap", [True, False])
 def test_two_rank_gradient_mean_matches_oracle(overlap):
     world = 2
-    ctx = mp.get_context("spawn")
-    ret = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, overlap, ret)) for r in range(world)]
-    for p in procs:
-        p.start()
-    got = ret.get(timeout=120)
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    got = spawn_ranks(_worker, world, (overlap,), results=1)[0]
     params = aligner_ref.init_params_numpy(DIN, D, seed=3)
     xs, ts = _global_batch()
     per_rank = [_shard_grads(xs[slice(*shard_bounds(SEQS, world, r))], ts[slice(*shard_bounds(SEQS, world, r))], params) for r in range(world)]
@@ -94,9 +77,8 @@ def test_bucket_views_alias_flat_storage():
     assert [t.shape for t in gb.in_parameter_order()] == [(D, DIN), (D,), (D, D), (D,), (D,)]
 
 
-def _peer_setup_worker(rank, world, port, ret):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+def _peer_setup_worker(rank, world, init, ret):
+    dist.init_process_group("gloo", init_method=init, rank=rank, world_size=world)
     try:
         from thinkdiff_mlre_b200.peer import PeerExchange, PeerSetupError
 
@@ -115,14 +97,5 @@ def test_peer_setup_fails_on_every_rank_with_one_message():
     blocked in the handle exchange."""
     if torch.cuda.is_available():
         pytest.skip("exercises the failure path of a box without CUDA")
-    ctx = mp.get_context("spawn")
-    ret = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_peer_setup_worker, args=(r, 2, port, ret)) for r in range(2)]
-    for p in procs:
-        p.start()
-    got = dict(ret.get(timeout=120) for _ in range(2))
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    got = dict(spawn_ranks(_peer_setup_worker, 2))
     assert got[0] == got[1] and got[0].startswith("peer data parallel set-up failed") and "rank 0" in got[0] and "rank 1" in got[0]

@@ -1,23 +1,18 @@
 """Multi-GPU (NCCL) data-parallel parity: world-size-2 run of the real kernels with the built-in bucketed all-reduce
 (overlapped and not) must equal the mean of the per-shard oracle gradients (DDP semantics). Skipped with < 2 GPUs."""
 import os
-import socket
 
 import numpy as np
 import pytest
 import torch
+
+from _mp import spawn_ranks
 
 pytestmark = pytest.mark.gpu
 
 DIN, D, SEQS = 192, 512, 6
 NAMES = ("dW1", "db1", "dW2", "db2", "dg")
 KEYS = ("0.weight", "0.bias", "2.weight", "2.bias", "3.weight")
-
-
-def _free_port():
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
 
 
 def _batch():
@@ -28,16 +23,15 @@ def _batch():
     return xs, ts
 
 
-def _worker(rank, world, port, overlap, ret):
+def _worker(rank, world, init, overlap, ret):
     import torch.distributed as dist
 
     import thinkdiff_mlre_b200 as td
     from oracle import aligner_ref
     from thinkdiff_mlre_b200.sharding import shard_bounds
 
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dist.init_process_group("nccl", init_method=init, rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         m = td.ThinkDiffAligner(DIN, D).cuda()
         m.load_state_dict(aligner_ref.init_params_numpy(DIN, D, seed=3))
@@ -60,22 +54,11 @@ def _worker(rank, world, port, overlap, ret):
 def test_two_gpu_bucketed_allreduce_equals_oracle_mean(overlap):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
-    import torch.multiprocessing as mp
-
     from oracle import aligner_ref
     from thinkdiff_mlre_b200.sharding import shard_bounds
 
     world = 2
-    ctx = mp.get_context("spawn")
-    ret = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, overlap, ret)) for r in range(world)]
-    for p in procs:
-        p.start()
-    got = ret.get(timeout=90)
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    got = spawn_ranks(_worker, world, (overlap,), results=1)[0]
     params = aligner_ref.init_params_numpy(DIN, D, seed=3)
     xs, ts = _batch()
     want = None
@@ -91,15 +74,14 @@ def test_two_gpu_bucketed_allreduce_equals_oracle_mean(overlap):
         assert err < 2e-2, (n, err)
 
 
-def _train_worker(rank, world, port, pipelined, ret, sharded=False):
+def _train_worker(rank, world, init, pipelined, sharded, ret):
     import torch.distributed as dist
 
     import thinkdiff_mlre_b200 as td
     from oracle import aligner_ref
 
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dist.init_process_group("nccl", init_method=init, rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         m = td.ThinkDiffAligner(DIN, D).cuda()
         m.load_state_dict(aligner_ref.init_params_numpy(DIN, D, seed=3))
@@ -120,20 +102,9 @@ def _train_worker(rank, world, port, pipelined, ret, sharded=False):
 def test_two_gpu_pipelined_training_equals_sequential_and_keeps_replicas_in_sync():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
-    import torch.multiprocessing as mp
-
     out = {}
     for pipelined in (False, True, "sharded"):
-        ctx = mp.get_context("spawn")
-        ret = ctx.Queue()
-        port = _free_port()
-        procs = [ctx.Process(target=_train_worker, args=(r, 2, port, bool(pipelined), ret, pipelined == "sharded")) for r in range(2)]
-        for p in procs:
-            p.start()
-        res = [ret.get(timeout=90) for _ in range(2)]
-        for p in procs:
-            p.join(timeout=120)
-            assert p.exitcode == 0
+        res = spawn_ranks(_train_worker, 2, (bool(pipelined), pipelined == "sharded"))
         out[pipelined] = {r: (params, losses) for r, params, losses in res}
     for pipelined in (False, True, "sharded"):  # replicas stay identical (same averaged gradients on every rank)
         for a, b in zip(out[pipelined][0][0], out[pipelined][1][0]):

@@ -5,11 +5,12 @@ loop-back tests are separate buffers of the same device. The two-process test ne
 its check (`dp_parity`) at every N > 1."""
 import ctypes as C
 import os
-import socket
 
 import numpy as np
 import pytest
 import torch
+
+from _mp import spawn_ranks
 
 pytestmark = pytest.mark.gpu
 
@@ -34,10 +35,22 @@ def test_scatter_gemm_matches_local_gemm_bit_exactly(world, shape, stream_k):
     want = ops.gemm_f32out(A, B, True, True, alpha=0.5, cta_pair=True, stream_k=stream_k)
     parts = [torch.full((M // world, N), float("nan"), device="cuda") for _ in range(world)]
     ws, ws_bytes = ops.gemm_workspace(A.device, stream_k)
-    L.check(L.lib().td_gemm_tn_scatter(L.ptr(A), M, L.ptr(B), N, M, N, K, 0.5, _arr(parts), world, L.ptr(ws), ws_bytes, L.stream_ptr()),
+    L.check(L.lib().td_gemm_tn_scatter(L.ptr(A), M, L.ptr(B), N, M, N, K, 0.5, _arr(parts), world, -1, L.ptr(ws), ws_bytes, L.stream_ptr()),
             "td_gemm_tn_scatter")
     torch.cuda.synchronize()
     assert torch.equal(torch.cat(parts), want)  # same schedule, same accumulation order: same bits as the local-output GEMM
+    # the data-parallel step's tile order (grouped by owner, rotated by rank): every output element is still stored exactly once;
+    # which tiles the stream-K tail cuts along K changes, so bits may differ in the last place -- never more
+    for rank in sorted({0, world // 2, world - 1}):
+        parts = [torch.full((M // world, N), float("nan"), device="cuda") for _ in range(world)]
+        L.check(L.lib().td_gemm_tn_scatter(L.ptr(A), M, L.ptr(B), N, M, N, K, 0.5, _arr(parts), world, rank, L.ptr(ws), ws_bytes,
+                                           L.stream_ptr()), "td_gemm_tn_scatter")
+        torch.cuda.synchronize()
+        got = torch.cat(parts)
+        assert torch.isfinite(got).all()
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5 * float(want.abs().max()))
+        if not stream_k:
+            assert torch.equal(got, want)  # whole tiles only: the order of the tiles does not change any bit
 
 
 def test_flags_post_sum_and_adamw_slots_loopback():
@@ -85,21 +98,60 @@ def test_flags_post_sum_and_adamw_slots_loopback():
         assert torch.equal(t, ref_bf16)
 
 
-def _free_port():
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
+def test_folded_signal_and_small_post_loopback():
+    """td_peer_fold: the finisher stores the small vectors into every "rank"'s slot as it writes them, and each scattered
+    weight-gradient GEMM bumps its counter at every "rank" exactly once, after all of its stores (here: buffers of one device)."""
+    import thinkdiff_mlre_b200 as td
+    from thinkdiff_mlre_b200 import _lib as L
+    from thinkdiff_mlre_b200 import ops
+
+    world, M = 4, 300
+    torch.manual_seed(0)
+    m = td.ThinkDiffAligner(DIN, D).cuda()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((M, DIN), generator=gen, device="cuda").to(torch.bfloat16)
+    tgt = torch.randn((M, D), generator=gen, device="cuda").to(torch.bfloat16)
+    W1b, b1b, W2b, b2b = m._bf16_params()
+    g = m[3].weight.detach()
+    _, saved = ops.aligner_mse_fwd(x, W1b, b1b, W2b, b2b, g, m.eps, tgt, defer_loss=True)
+    # reference: the same backward with local outputs
+    ref = ops.AlignerBackwardFromDh2(x, saved, W2b, None, grad_scale=1.0 / world)
+    rsmall = torch.zeros(3 * D, device="cuda")
+    rdW1, rdW2 = torch.empty((D, DIN), device="cuda"), torch.empty((D, D), device="cuda")
+    ref.gelu_and_small(rsmall[2 * D :], rsmall[:D], rsmall[D : 2 * D])
+    ref.gelu_linear1_and_small(rdW1, rsmall[2 * D :], rsmall[:D], rsmall[D : 2 * D])
+    ref.linear2_only(rdW2)
+    # folded: four launches, no separate post / signal kernels
+    flags = [torch.zeros(64, dtype=torch.int32, device="cuda") for _ in range(world)]
+    slots = [torch.full((3 * D,), float("nan"), device="cuda") for _ in range(world)]
+    p1 = [torch.full((D // world, DIN), float("nan"), device="cuda") for _ in range(world)]
+    p2 = [torch.full((D // world, D), float("nan"), device="cuda") for _ in range(world)]
+    small = torch.zeros(3 * D, device="cuda")
+    flag_arr, slot_arr = _arr(flags), _arr(slots)
+    bwd = ops.AlignerBackwardFromDh2(x, saved, W2b, None, grad_scale=1.0 / world)
+    bwd.gelu_and_small_scatter(small[2 * D :], small[:D], small[D : 2 * D], world,
+                               L.PeerFold(None, -1, C.cast(slot_arr, C.c_void_p), C.c_void_p(small.data_ptr()), small.numel()))
+    bwd.linear1_only_scatter(_arr(p1), world, 1, L.PeerFold(C.cast(flag_arr, C.c_void_p), 0, None, None, 0))
+    bwd.linear2_only_scatter(_arr(p2), world, 1, L.PeerFold(C.cast(flag_arr, C.c_void_p), 32, None, None, 0))
+    bwd.linear2_only_scatter(_arr(p2), world, 2, L.PeerFold(C.cast(flag_arr, C.c_void_p), 32, None, None, 0))  # a second GEMM: +1 again
+    torch.cuda.synchronize()
+    for f in flags:
+        assert int(f[0]) == 1 and int(f[32]) == 2 and int(f.sum()) == 3
+    assert torch.equal(small, rsmall)
+    for sl in slots:
+        assert torch.equal(sl, small)
+    torch.testing.assert_close(torch.cat(p1), rdW1, rtol=1e-5, atol=1e-5 * float(rdW1.abs().max()))
+    torch.testing.assert_close(torch.cat(p2), rdW2, rtol=1e-5, atol=1e-5 * float(rdW2.abs().max()))
 
 
-def _train(rank, world, port, mode, ret):
+def _train(rank, world, init, mode, ret):
     import torch.distributed as dist
 
     import thinkdiff_mlre_b200 as td
     from oracle import aligner_ref
 
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dist.init_process_group("nccl", init_method=init, rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         m = td.ThinkDiffAligner(DIN, D).cuda()
         m.load_state_dict(aligner_ref.init_params_numpy(DIN, D, seed=3))
@@ -118,18 +170,7 @@ def _train(rank, world, port, mode, ret):
 
 
 def _run(world, mode):
-    import torch.multiprocessing as mp
-
-    ctx = mp.get_context("spawn")
-    ret = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_train, args=(r, world, port, mode, ret)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = [ret.get(timeout=90) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    res = spawn_ranks(_train, world, (mode,))
     return {r: (params, losses) for r, params, losses in res}
 
 

@@ -62,12 +62,19 @@ SIGNATURES = {
     "td_peer_post": (_i32, [_vp, _vp, _i32, _i64, _vp]),
     "td_sum_slots": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp]),
     "td_adamw_slots_step": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _f32, _vp, _vp]),
-    "td_aligner_bwd_dh2_scatter": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _vp]),
-    "td_gemm_tn_scatter": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _i64, _f32, _vp, _i32, _vp, _i64, _vp]),
+    "td_aligner_bwd_dh2_scatter": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i32, _vp]),
+    "td_gemm_tn_scatter": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _i64, _f32, _vp, _i32, _i32, _vp, _i64, _vp]),
     "td_loss_workspace_bytes": (_i64, [_i64]),
     "td_masked_mse_fwd_bwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _i64, _vp]),
     "td_masked_ce_fwd_bwd": (_i32, [_vp, _i32, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _i64, _vp]),
 }
+
+
+class PeerFold(C.Structure):
+    """``td_peer_fold`` of include/thinkdiff_b200.h: the exchange protocol's tiny launches folded into a backward call."""
+
+    _fields_ = [("signal_flags", C.c_void_p), ("signal_slot", C.c_int32), ("small_dst", C.c_void_p), ("small_base", C.c_void_p),
+                ("small_numel", C.c_int64)]
 
 
 class LibraryMissing(ImportError):

@@ -286,15 +286,23 @@ def _peer_backward(module, bwd, d: int, device):
 
     px = module._ensure_peer()
     module._peer_epoch += 1
+    rot_rank = -1 if os.environ.get("TD_PEER_NO_ROTATE") == "1" else px.rank  # developer A/B: one common tile order on all ranks
     small = torch.empty(3 * d, dtype=torch.float32, device=device)  # [db2 | dg | db1], GradBuckets' small layout
     db2, dg, db1 = small[:d], small[d : 2 * d], small[2 * d :]
     module._grad_flats = {"small": small}
-    bwd.gelu_and_small(db1, db2, dg)
-    px.post_small(small)
-    bwd.linear1_only_scatter(px.dw_dst(1), px.world)
-    px.signal(ROW_GRAD1)
-    bwd.linear2_only_scatter(px.dw_dst(2), px.world)
-    px.signal(ROW_GRAD2)
+    if os.environ.get("TD_PEER_UNFOLDED") == "1":  # developer A/B: the protocol's tiny launches as separate kernels
+        bwd.gelu_and_small(db1, db2, dg)
+        px.post_small(small)
+        bwd.linear1_only_scatter(px.dw_dst(1), px.world, rot_rank)
+        px.signal(ROW_GRAD1)
+        bwd.linear2_only_scatter(px.dw_dst(2), px.world, rot_rank)
+        px.signal(ROW_GRAD2)
+        return None, db1, None, db2, dg
+    # 4 launches: dh0 GEMM, finisher (stores the small vectors into this rank's slot at every rank as it writes them), dW1 GEMM
+    # (+1 on GRAD1 everywhere once all of its stores have landed), dW2 GEMM (+1 on GRAD2)
+    bwd.gelu_and_small_scatter(db1, db2, dg, px.world, px.fold_post_small(small))
+    bwd.linear1_only_scatter(px.dw_dst(1), px.world, rot_rank, px.fold_signal(ROW_GRAD1))
+    bwd.linear2_only_scatter(px.dw_dst(2), px.world, rot_rank, px.fold_signal(ROW_GRAD2))
     return None, db1, None, db2, dg
 
 

@@ -65,7 +65,7 @@ struct DeviceState {
   int cc_major = -1;
   int* sk_flags = nullptr;  // pool of zeroed stream-K flag blocks, one block per launch, re-armed by the kernels
   std::atomic<unsigned> sk_seq{0};
-  int* sched = nullptr;     // pool of {next unit, finished workers} counter pairs for the dynamic tile scheduler
+  int* sched = nullptr;     // pool of {next unit, workers out of units, workers torn down, -} counters for the dynamic tile scheduler
   std::atomic<unsigned> sched_seq{0};
 };
 constexpr unsigned kSchedPairs = 1024;                       // a pair is re-armed (zeroed) by the kernel that used it
@@ -125,12 +125,12 @@ inline int* next_sched_counter() {
     std::lock_guard<std::mutex> lock(s->mu);
     if (!s->sched) {
       int* p = nullptr;
-      if (cudaMalloc(&p, sizeof(int) * 2 * kSchedPairs) != cudaSuccess) return nullptr;
-      if (cudaMemset(p, 0, sizeof(int) * 2 * kSchedPairs) != cudaSuccess) return nullptr;
+      if (cudaMalloc(&p, sizeof(int) * 4 * kSchedPairs) != cudaSuccess) return nullptr;
+      if (cudaMemset(p, 0, sizeof(int) * 4 * kSchedPairs) != cudaSuccess) return nullptr;
       s->sched = p;
     }
   }
-  return s->sched + 2 * (s->sched_seq.fetch_add(1) % kSchedPairs);
+  return s->sched + 4 * (s->sched_seq.fetch_add(1) % kSchedPairs);
 }
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -61,7 +61,7 @@ struct GemmParams {
   int tail_q, tail_r;  // tail worker w gets tail_q (+1 if w < tail_r) consecutive k-block units
   float* sk_partials;  // [tail ranges][CTAS][8 warps][4 chunks][32 cols][32 rows] fp32 (nullptr = tail tiles are whole tiles)
   int* sk_flags;       // [tail ranges][CTAS][8 warps] zero before the launch; re-armed by the consumer
-  int* sched_counter;  // [2] zero-initialised {next unit, finished workers}; re-armed by the kernel itself
+  int* sched_counter;  // [4] zero-initialised {next unit, workers out of units, workers torn down, -}; re-armed by the kernel itself
   void* out0;
   void* out1;
   const void* aux0;
@@ -75,6 +75,17 @@ struct GemmParams {
   // EPI_F32_SCATTER
   float* scatter_dst[kMaxPeers];
   int scatter_rows;  // output rows per owner rank (a multiple of 32: a warp's 32-row slab never straddles two owners)
+  // Raster of the output tiles (0 / 0 = groups of kGroupM m-blocks, no rotation). The scattered GEMMs of N ranks run at the same
+  // time: with one common raster every rank would store to the SAME owner at the same moment (and to half of the owners for half
+  // of the kernel), i.e. N senders into one NVLink port. raster_group_m = m-blocks per owner and a per-rank rotation of the
+  // m-blocks turn that into a permutation: at any moment rank r stores to owner (r + 1 + t) mod N, its own rows come last.
+  int raster_group_m;
+  int raster_rot_m;
+  // EPI_F32_SCATTER, optional: the exchange protocol's "+1 after the GEMM" folded into the GEMM itself. The last CTA pair to
+  // finish (a third self-re-arming counter, sched_counter[2]) adds 1 to post_signal[o] for o < post_signal_n -- one counter in
+  // every rank's memory -- after every pair's bulk stores have completed and been fenced at system scope.
+  int* post_signal[kMaxPeers];
+  int post_signal_n;
 };
 // The owners' output tensor maps of EPI_F32_SCATTER (kernel parameter; unused by the other epilogues).
 struct ScatterMaps {
@@ -110,6 +121,10 @@ constexpr int kSkSlotFloats = kEpiWarps * kEpiChunks * 32 * 32;  // one CTA's 12
 // 64-byte rows with the 64-byte swizzle for bf16, 128-byte rows with the 128-byte swizzle for fp32.
 template <int EPI> struct EpiStage { static constexpr int kBytesPerWarp = 4096; };          // two 2 KB bf16 boxes
 template <> struct EpiStage<EPI_DGELU> { static constexpr int kBytesPerWarp = 6144; };      // + two aux boxes, one out box
+// fp32 output: two 4 KB boxes, so a warp converts chunk c + 1 while the bulk store of chunk c is still reading its box -- over
+// NVLink (scatter) that read is paced by the link, and a single box made the epilogue longer than the next tile's mainloop
+template <> struct EpiStage<EPI_F32> { static constexpr int kBytesPerWarp = 8192; };
+template <> struct EpiStage<EPI_F32_SCATTER> { static constexpr int kBytesPerWarp = 8192; };
 
 // Pipeline depth per epilogue kind. The GEMMs that the optimizer's update kernels run BESIDE (Linear1's update beside the dW2
 // GEMM, Linear2's beside the next forward's first GEMM) keep one stage less than would fit: the 32 KB they leave free -- and their
@@ -187,12 +202,17 @@ __device__ __forceinline__ void for_each_segment(const GemmParams& p, int unit, 
 constexpr int kGroupM = 8;  // rasterise m-blocks in groups so that concurrently running tiles share operands in L2
 __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& m_blk, int& n_blk) {
   const int nnb = p.num_n_blocks;
-  const int group = tile / (kGroupM * nnb);
-  const int first_m = group * kGroupM;
-  const int gsize = min(kGroupM, p.num_m_blocks - first_m);
-  const int in_group = tile - group * kGroupM * nnb;
+  const int G = p.raster_group_m > 0 ? p.raster_group_m : kGroupM;
+  const int group = tile / (G * nnb);
+  const int first_m = group * G;
+  const int gsize = min(G, p.num_m_blocks - first_m);
+  const int in_group = tile - group * G * nnb;
   m_blk = first_m + in_group % gsize;
   n_blk = in_group / gsize;
+  if (p.raster_rot_m > 0) {
+    m_blk += p.raster_rot_m;
+    if (m_blk >= p.num_m_blocks) m_blk -= p.num_m_blocks;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ epilogue helpers
@@ -322,7 +342,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
         map = &smaps.m[owner];
         out_row0 = slab_row0 - owner * p.scatter_rows;
       }
-      stage_acquire(lane, true);
+      uint8_t* box = stage + (st.box & 1) * 4096;
+      stage_acquire(lane, false);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         float o[4];
@@ -331,10 +352,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
           o[j] = alpha * __uint_as_float(v[4 * q + j]);
           bad |= row_ok && !(fabsf(o[j]) <= 3.4028234e38f);
         }
-        *reinterpret_cast<uint4*>(stage + box128_off(lane, q)) =
+        *reinterpret_cast<uint4*>(box + box128_off(lane, q)) =
             make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
       }
-      stage_store(map, stage, col0, out_row0, lane, EPI == EPI_F32 && p.accumulate != 0);
+      stage_store(map, box, col0, out_row0, lane, EPI == EPI_F32 && p.accumulate != 0);
+      st.box++;
     } else if constexpr (EPI == EPI_DGELU) {
       // dh0 = bf16( bf16(dh1) * gelu'(h0) ): dh1 is rounded to bf16 first, as autograd materialises it.
       const uint32_t b = st.aux_use & 1;
@@ -445,8 +467,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const CUtenso
 // -- and, for a pair, to the peer CTA over DSMEM.
 constexpr int kSchedStages = 4;
 
+// Register budget. A warp's registers come from its SM sub-partition's quarter of the register file (16 384 x 32 bit): the ten
+// GEMM warps put three on sub-partitions 0 and 1, so at more than 128 registers per thread (allocated in units of 8) there is no
+// room left there for even two warps of a co-resident 256-thread update kernel at 64 registers -- which then sits in the block
+// scheduler until the GEMM's CTAs exit. TD_GEMM_MAXNREG caps the allocation (3 x 32 x 128 + 2 x 32 x 64 = 16 384 exactly).
+#ifdef TD_GEMM_MAXNREG
+#define TD_GEMM_BOUNDS __maxnreg__(TD_GEMM_MAXNREG)
+#else
+#define TD_GEMM_BOUNDS __launch_bounds__(kGemmThreads, 1)
+#endif
 template <int CTAS, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void TD_GEMM_BOUNDS
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out0, const __grid_constant__ CUtensorMap tmap_out1,
                  const __grid_constant__ CUtensorMap tmap_aux, const __grid_constant__ ScatterMaps smaps, const GemmParams p) {
@@ -674,6 +705,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc<CTAS>(tmem_base, 512);
+  }
+  if constexpr (EPI == EPI_F32_SCATTER) {
+    // Every epilogue warp of this pair has waited for its bulk stores and fenced at system scope before the barrier above. The
+    // worker that finds all others already here publishes the whole GEMM: release at system scope, one counter per rank.
+    if (p.post_signal_n > 0 && leader && warp == kProducerWarp && lane == 0) {
+      __threadfence();
+      if (atomicAdd(p.sched_counter + 2, 1) == num_workers - 1) {
+        p.sched_counter[2] = 0;
+        __threadfence_system();
+#pragma unroll
+        for (int o = 0; o < kMaxPeers; ++o)
+          if (o < p.post_signal_n) asm volatile("red.release.sys.global.add.s32 [%0], 1;" ::"l"(p.post_signal[o]) : "memory");
+      }
+    }
   }
 }
 

@@ -668,15 +668,19 @@ norm_mse_bwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restric
               const float rstd = rs[r];
               const float c = tot * inv_d * rstd * rstd * rstd;
               float o[8];
+              uint32_t ow[4];
+#pragma unroll
+              for (int q = 0; q < 8; q += 2) {  // bf16 rounding through the packed conversion (ALU pipe; the scalar form is an XU-pipe op)
+                o[q] = rstd * gg[q] * dyv[r][q] - hv[r][q] * c;
+                o[q + 1] = rstd * gg[q + 1] * dyv[r][q + 1] - hv[r][q + 1] * c;
+                ow[q >> 1] = bf16_round2(o[q], o[q + 1]);
+              }
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
-                o[q] = bf16_round(rstd * gg[q] * dyv[r][q] - hv[r][q] * c);
                 adb[q] += o[q];
                 adg[q] = fmaf(dyv[r][q] * hv[r][q], rstd, adg[q]);
               }
-              st_stream(reinterpret_cast<uint4*>(dh2 + (long long)row * D) + t,
-                        make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                                   pack_bf16x2(o[6], o[7])));
+              st_stream(reinterpret_cast<uint4*>(dh2 + (long long)row * D) + t, make_uint4(ow[0], ow[1], ow[2], ow[3]));
             }
           }
           ++it;
@@ -717,6 +721,9 @@ struct FinishParams {
   int accumulate;  // 1: out += (gradient accumulation over micro-batches)
   float* stats;    // optional
   const float* loss_part; int loss_P; float* loss_out; float loss_div;
+  // peer data parallel: outputs that lie inside [post_base, post_base + post_numel) -- this rank's small-vector bucket -- are ALSO
+  // stored at the same offset into post[o], o < n_post: this rank's slot at every rank (the separate posting kernel, folded in)
+  float* post[8]; int n_post; const float* post_base; long long post_numel;
 };
 
 __global__ void __launch_bounds__(256)
@@ -761,6 +768,14 @@ finish_kernel(const FinishParams f) {
     if (f.stats != nullptr && !(fabsf(v) <= 3.4028234e38f)) atomicAdd(f.stats, 1.0f);
     if (f.accumulate) v += j.out[col];
     j.out[col] = v;
+    if (f.n_post > 0) {
+      const long long off = (j.out + col) - f.post_base;
+      if (off >= 0 && off < f.post_numel) {
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+          if (o < f.n_post) f.post[o][off] = v;
+      }
+    }
   }
 }
 

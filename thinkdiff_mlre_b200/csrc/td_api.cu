@@ -449,6 +449,14 @@ NormPartials carve_norm_partials(void* buf, int64_t M, int32_t D) {
 // rank o go (a [D / world, cols] fp32 block in rank o's memory, this rank's slot). world == 0: plain local outputs.
 struct ScatterDst {
   int world = 0;
+  int rank = -1;  // this rank (>= 0: owner-grouped raster rotated so that concurrent ranks store to different owners)
+  // td_peer_fold: the protocol's tiny launches folded into this call's kernels
+  int* signal[kMaxPeers] = {};   // counter bumped at every rank by the LAST weight-gradient GEMM of the call, at its end
+  int n_signal = 0;
+  float* post[kMaxPeers] = {};   // this rank's small-vector slot at every rank: the finisher stores db1 / dg / db2 there too
+  int n_post = 0;
+  const float* post_base = nullptr;
+  long long post_numel = 0;
   float* dW1[kMaxPeers] = {};
   float* dW2[kMaxPeers] = {};
 };
@@ -461,11 +469,24 @@ struct BwdExtras {
   float loss_div = 1.f;
 };
 
-int launch_dw_gemm(GemmOperand a, GemmOperand b, GemmParams& p, float* const* dst, int world, void* sk, cudaStream_t st, const char* tag) {
+int launch_dw_gemm(GemmOperand a, GemmOperand b, GemmParams& p, float* const* dst, int world, int rank, void* sk, cudaStream_t st,
+                   const char* tag, const ScatterDst* signal_from = nullptr) {
   if (world <= 0) return launch_gemm<2, true, true, EPI_F32>(a, b, p, sk, st, tag);
+  if (signal_from != nullptr) {
+    for (int o = 0; o < signal_from->n_signal; ++o) p.post_signal[o] = signal_from->signal[o];
+    p.post_signal_n = signal_from->n_signal;
+  }
   if (p.M % world || (p.M / world) % 32) TD_FAIL(TD_ERR_UNSUPPORTED, "row-scattered GEMM: %d rows over %d ranks must give a multiple of 32 rows per rank", p.M, world);
   for (int o = 0; o < world; ++o) p.scatter_dst[o] = dst[o];
   p.scatter_rows = p.M / world;
+  // NVLink traffic shaping (see GemmParams::raster_group_m): tiles are grouped by owner, and rank r starts with the rows of
+  // owner r + 1 and ends with its own (local) rows. Only when an owner's rows are whole pair tiles (256 rows).
+  const int tile_m = 2 * kBlockM;
+  if (rank >= 0 && rank < world && world > 1 && p.scatter_rows % tile_m == 0) {
+    const int per_owner = p.scatter_rows / tile_m;
+    p.raster_group_m = per_owner < kGroupM ? per_owner : kGroupM;
+    p.raster_rot_m = ((rank + 1) % world) * per_owner;
+  }
   return launch_gemm<2, true, true, EPI_F32_SCATTER>(a, b, p, sk, st, tag);
 }
 
@@ -504,6 +525,10 @@ int bwd_from_dh2(const __nv_bfloat16* dh2, const void* x, const void* h0, const 
     if (ex.loss_out != nullptr && ex.np != nullptr) {
       f.loss_part = ex.np->loss_part; f.loss_P = ex.np->grid; f.loss_out = ex.loss_out; f.loss_div = ex.loss_div;
     }
+    if (sc != nullptr && sc->n_post > 0) {
+      for (int o = 0; o < sc->n_post; ++o) f.post[o] = sc->post[o];
+      f.n_post = sc->n_post; f.post_base = sc->post_base; f.post_numel = sc->post_numel;
+    }
     if (f.njobs > 0 || f.loss_out != nullptr) {
       finish_kernel<<<dim3((D + 31) / 32, f.njobs + (f.loss_out ? 1 : 0)), 256, 0, st>>>(f);
       TD_CUDA(cudaGetLastError());
@@ -513,8 +538,9 @@ int bwd_from_dh2(const __nv_bfloat16* dh2, const void* x, const void* h0, const 
     // dW1[D, Din] = scale * dh0^T . x   (dh0 already carries the upstream scalar; W1_ONLY: dh0 is in the workspace from a GELU_ONLY call)
     memset(&p, 0, sizeof(p));
     p.M = D; p.N = Din; p.K = int(M); p.ld_out = Din; p.alpha = scale; p.out0 = dW1; p.stats = ex.stats; p.accumulate = ex.accumulate;
-    int rc = launch_dw_gemm({w.dh0, D, true}, {x, Din, true}, p, sc ? sc->dW1 : nullptr, world, w.sk, st,
-                            world ? "gemm_dW1_scatter" : "gemm_dW1");
+    const bool last = !(phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_W2_ONLY));  // the call's last GEMM carries the signal
+    int rc = launch_dw_gemm({w.dh0, D, true}, {x, Din, true}, p, sc ? sc->dW1 : nullptr, world, sc ? sc->rank : -1, w.sk, st,
+                            world ? "gemm_dW1_scatter" : "gemm_dW1", last ? sc : nullptr);
     if (rc) return rc;
   }
   if (phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_W2_ONLY)) {
@@ -522,8 +548,8 @@ int bwd_from_dh2(const __nv_bfloat16* dh2, const void* x, const void* h0, const 
     memset(&p, 0, sizeof(p));
     p.M = D; p.N = D; p.K = int(M); p.ld_out = D; p.alpha = scale; p.alpha_ptr = scale_ptr; p.out0 = dW2; p.stats = ex.stats;
     p.accumulate = ex.accumulate;
-    int rc = launch_dw_gemm({dh2, D, true}, {h1, D, true}, p, sc ? sc->dW2 : nullptr, world, w.sk, st,
-                            world ? "gemm_dW2_scatter" : "gemm_dW2");
+    int rc = launch_dw_gemm({dh2, D, true}, {h1, D, true}, p, sc ? sc->dW2 : nullptr, world, sc ? sc->rank : -1, w.sk, st,
+                            world ? "gemm_dW2_scatter" : "gemm_dW2", sc);
     if (rc) return rc;
   }
   return TD_OK;
@@ -681,12 +707,14 @@ int32_t td_aligner_bwd_dh2(const void* dh2, const void* x, const void* h0, const
 int32_t td_aligner_bwd_dh2_scatter(const void* dh2, const void* x, const void* h0, const void* h1, const void* W2,
                                    const void* norm_partials, int64_t M, int32_t Din, int32_t D, float grad_scale,
                                    const float* grad_scale_ptr, float* const* dW1_dst, float* db1, float* const* dW2_dst,
-                                   float* db2, float* dg, float* loss_out, float* stats, int32_t world, void* ws,
-                                   int64_t ws_bytes, int32_t phases, td_stream_t stream) {
+                                   float* db2, float* dg, float* loss_out, float* stats, int32_t world, int32_t rank,
+                                   const td_peer_fold* fold, void* ws, int64_t ws_bytes, int32_t phases, td_stream_t stream) {
   if (world < 1 || world > kMaxPeers || D % world)
     TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2_scatter: world=%d must be 1..%d and divide D=%d", world, kMaxPeers, D);
+  if (rank >= world) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2_scatter: rank=%d outside world=%d", rank, world);
   ScatterDst sc;
   sc.world = world;
+  sc.rank = rank;
   const bool need1 = (phases & (TD_BWD_PHASE_GELU_W1 | TD_BWD_PHASE_W1_ONLY)) != 0;
   const bool need2 = (phases & (TD_BWD_PHASE_NORM_W2 | TD_BWD_PHASE_W2_ONLY)) != 0;
   for (int o = 0; o < world; ++o) {
@@ -694,6 +722,24 @@ int32_t td_aligner_bwd_dh2_scatter(const void* dh2, const void* x, const void* h
       TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2_scatter: null destination for rank %d", o);
     if (need1) sc.dW1[o] = dW1_dst[o];
     if (need2) sc.dW2[o] = dW2_dst[o];
+  }
+  if (fold != nullptr) {
+    if (fold->signal_flags != nullptr) {
+      if (!(need1 || need2) || fold->signal_slot < 0) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2_scatter: a folded signal needs a weight-gradient GEMM in this call");
+      for (int o = 0; o < world; ++o) {
+        if (!fold->signal_flags[o]) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2_scatter: null flag array for rank %d", o);
+        sc.signal[o] = static_cast<int*>(fold->signal_flags[o]) + fold->signal_slot;
+      }
+      sc.n_signal = world;
+    }
+    if (fold->small_dst != nullptr) {
+      if (!fold->small_base || fold->small_numel <= 0) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2_scatter: small_dst needs small_base / small_numel");
+      for (int o = 0; o < world; ++o) {
+        if (!fold->small_dst[o]) TD_FAIL(TD_ERR_ARG, "td_aligner_bwd_dh2_scatter: null small-vector slot for rank %d", o);
+        sc.post[o] = static_cast<float*>(fold->small_dst[o]);
+      }
+      sc.n_post = world; sc.post_base = fold->small_base; sc.post_numel = fold->small_numel;
+    }
   }
   // the impl's null checks look at dW1 / dW2: hand it the first destination
   return bwd_dh2_impl(dh2, x, h0, h1, W2, norm_partials, M, Din, D, grad_scale, grad_scale_ptr, need1 ? sc.dW1[0] : nullptr,
@@ -936,8 +982,9 @@ int32_t td_adamw_slots_step(float* param, const float* grad_slots, int64_t slot_
 }
 
 int32_t td_gemm_tn_scatter(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int32_t N, int64_t K, float alpha,
-                           float* const* dst, int32_t world, void* ws, int64_t ws_bytes, td_stream_t stream) {
+                           float* const* dst, int32_t world, int32_t rank, void* ws, int64_t ws_bytes, td_stream_t stream) {
   TD_DEVICE_OR_RETURN();
+  if (rank >= world) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter: rank=%d outside world=%d", rank, world);
   if (world < 1 || world > kMaxPeers || M % world) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter: world=%d must be 1..%d and divide M", world, kMaxPeers);
   if (M <= 0 || M > 0x7fffffffll || K <= 0 || K > 0x7fffffffll) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter: size out of range");
   GemmParams p;
@@ -946,7 +993,7 @@ int32_t td_gemm_tn_scatter(const void* A, int64_t lda, const void* B, int64_t ld
   for (int o = 0; o < world; ++o) {
     if (!dst || !dst[o]) TD_FAIL(TD_ERR_ARG, "td_gemm_tn_scatter: null destination for rank %d", o);
   }
-  return launch_dw_gemm({A, lda, true}, {B, ldb, true}, p, dst, world, sk_ws_or_null(ws, ws_bytes), (cudaStream_t)stream, "gemm_tn_scatter");
+  return launch_dw_gemm({A, lda, true}, {B, ldb, true}, p, dst, world, rank, sk_ws_or_null(ws, ws_bytes), (cudaStream_t)stream, "gemm_tn_scatter");
 }
 
 // ------------------------------------------------------------------------------------------------ losses

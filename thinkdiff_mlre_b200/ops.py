@@ -5,6 +5,8 @@ semantics hold) and launches on ``torch.cuda.current_stream()``.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 from . import _lib as L
@@ -248,29 +250,36 @@ class AlignerBackwardFromDh2:
     def linear2_only(self, dW2):
         self._call(L.BWD_W2_ONLY, None, None, dW2, None, None)
 
-    def _call_scatter(self, phase, dW1_dst, db1, dW2_dst, db2, dg, world):
+    def _call_scatter(self, phase, dW1_dst, db1, dW2_dst, db2, dg, world, rank: int = -1, fold=None):
         self._count(phase)
         loss_out = self._take_loss() if phase & (L.BWD_GELU_W1 | L.BWD_GELU_ONLY | L.BWD_NORM_W2 | L.BWD_SMALL2_ONLY) else None
         L.check(
             L.lib().td_aligner_bwd_dh2_scatter(L.ptr(self.dh2), L.ptr(self.x), L.ptr(self.h0), L.ptr(self.h1), L.ptr(self.W2),
                                                L.ptr(self.partials), self.M, self.Din, self.D, self.grad_scale,
                                                L.ptr(self.upstream), dW1_dst, L.ptr(db1), dW2_dst, L.ptr(db2), L.ptr(dg),
-                                               L.ptr(loss_out), L.ptr(self.stats), world,
+                                               L.ptr(loss_out), L.ptr(self.stats), world, int(rank),
+                                               None if fold is None else C.cast(C.pointer(fold), C.c_void_p),
                                                L.ptr(self.ws), self.ws_bytes, phase, L.stream_ptr()),
             "td_aligner_bwd_dh2_scatter",
         )
 
-    def gelu_linear1_small_scatter(self, dW1_dst, db1, db2, dg, world: int):
+    def gelu_linear1_small_scatter(self, dW1_dst, db1, db2, dg, world: int, rank: int = -1):
         """As ``gelu_linear1_and_small`` with dW1's rows stored to their owner ranks (``dW1_dst``: host array of ``world``
-        device pointers)."""
-        self._call_scatter(L.BWD_GELU_W1 | L.BWD_SMALL2_ONLY, dW1_dst, db1, None, db2, dg, world)
+        device pointers). ``rank`` (of the caller, >= 0) turns on the rank-rotated tile order of the scattered GEMMs."""
+        self._call_scatter(L.BWD_GELU_W1 | L.BWD_SMALL2_ONLY, dW1_dst, db1, None, db2, dg, world, rank)
 
-    def linear1_only_scatter(self, dW1_dst, world: int):
-        """dW1 GEMM from the dh0 a ``gelu_and_small`` call left in the workspace, rows stored to their owner ranks."""
-        self._call_scatter(L.BWD_W1_ONLY, dW1_dst, None, None, None, None, world)
+    def gelu_and_small_scatter(self, db1, db2, dg, world: int, fold):
+        """As ``gelu_and_small`` in the peer data-parallel step: the finisher also stores the three small vectors into this rank's
+        slot at every rank (``fold``: a ``PeerFold`` with ``small_dst``)."""
+        self._call_scatter(L.BWD_GELU_ONLY | L.BWD_SMALL2_ONLY, None, db1, None, db2, dg, world, -1, fold)
 
-    def linear2_only_scatter(self, dW2_dst, world: int):
-        self._call_scatter(L.BWD_W2_ONLY, None, None, dW2_dst, None, None, world)
+    def linear1_only_scatter(self, dW1_dst, world: int, rank: int = -1, fold=None):
+        """dW1 GEMM from the dh0 a ``gelu_and_small`` call left in the workspace, rows stored to their owner ranks. ``fold`` (a
+        ``PeerFold`` with ``signal_flags``): the GEMM bumps that counter at every rank once all of its stores have completed."""
+        self._call_scatter(L.BWD_W1_ONLY, dW1_dst, None, None, None, None, world, rank, fold)
+
+    def linear2_only_scatter(self, dW2_dst, world: int, rank: int = -1, fold=None):
+        self._call_scatter(L.BWD_W2_ONLY, None, None, dW2_dst, None, None, world, rank, fold)
 
 
 def rmsnorm_fwd(x: torch.Tensor, g: torch.Tensor, eps: float = 1e-6, out_bf16: bool = False):

@@ -197,6 +197,7 @@ class PeerExchange:
         self._dw_dst = {w: arr([self.base[o] + lay.grad_slot_offset(w, self.rank) for o in range(self.world)]) for w in (1, 2)}
         self._small_dst = arr([self.base[o] + lay.small_slot_offset(self.rank) for o in range(self.world)])
         self._w_dst = {w: arr([self.base[o] + lay.weight_rows_offset(w, self.rank) for o in range(self.world)]) for w in (1, 2)}
+        self._folds = {}
         if self.world > 1:
             dist.barrier(group=group)  # every buffer is mapped everywhere before anyone stores into a peer
 
@@ -222,6 +223,22 @@ class PeerExchange:
         """The current stream waits until every rank has signalled ``row`` ``step`` times."""
         L.check(L.lib().td_peer_wait(C.c_void_p(self._local + self.layout.flag_offset(row)), 1, int(step) * self.world, self.timeout_s,
                                      L.stream_ptr()), "td_peer_wait")
+
+    def fold_signal(self, row: int):
+        """``PeerFold`` asking the last weight-gradient GEMM of a backward call for the +1 on counter ``row`` at every rank
+        (instead of a ``signal(row)`` launch after it). Cached: the structure must stay alive until the call has returned."""
+        f = self._folds.get(("signal", row))
+        if f is None:
+            f = L.PeerFold(C.cast(self._flag_arrays, C.c_void_p), row * FLAG_ROW_STRIDE, None, None, 0)
+            self._folds[("signal", row)] = f
+        return f
+
+    def fold_post_small(self, small):
+        """``PeerFold`` asking the backward's finisher launch to store ``small`` (fp32 [3 D], this rank's [db2 | dg | db1]) into this
+        rank's slot at every rank as it writes it (instead of a ``post_small`` launch after it)."""
+        if small.numel() != self.layout.small_numel:
+            raise ValueError("small-vector size does not match the layout (3 D must be a multiple of 4)")
+        return L.PeerFold(None, -1, C.cast(self._small_dst, C.c_void_p), C.c_void_p(small.data_ptr()), small.numel())
 
     def post_small(self, small):
         """``small`` fp32 [3 D] -> slot[rank] of every rank's small-vector block."""
