@@ -651,6 +651,7 @@ def main():
                                               balanced=args.sharding == "balanced") for j in range(num_batches)]
         for i in range(3):
             float(stepper.step_host(host_t[i % num_batches], dev))
+        copy_streams = stepper.tune_copy_streams(host_t[0], dev)  # 1 / 2 / 4 copy streams: whichever this host moves a batch fastest with
         sync_all()
         e0.record()
         nxt = stepper.prefetch(host_t[0], dev)  # inside the timed region: every step's H2D is paid for
@@ -668,8 +669,8 @@ def main():
         b0 = host_t[0]
         h2d = b0.flat.nbytes + b0.extras["flat_target"].nbytes + b0.src_row_start.nbytes + b0.lens.nbytes
         e2e = {"value": tokens_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-               "ms_per_step": ms_e2e / steps, "h2d_gbs_per_rank": h2d / (ms_e2e / steps * 1e-3) / 1e9, "numa_bound_cpus": numa_cpus,
-               "note": "every step: H2D of the kept rows of its bf16 features + T5 targets from pinned memory (row chunks on two copy streams, overlapping the previous step's compute) and loss.item()"}
+               "ms_per_step": ms_e2e / steps, "h2d_gbs_per_rank": h2d / (ms_e2e / steps * 1e-3) / 1e9, "numa_bound_cpus": numa_cpus, "copy_streams": copy_streams,
+               "note": "every step: H2D of the kept rows of its bf16 features + T5 targets from pinned memory (row chunks over `copy_streams` copy streams, picked by timing 1 / 2 / 4 on this host before the timed region; overlapping the previous step's compute) and loss.item()"}
         if args.from_shards:
             e2e["from_shards"] = e2e_from_shards(td, stepper, host_t, seqs, din, dev, min(steps, 12), sync_all, max_over_ranks, sum_over_ranks, rank)
         del host_t

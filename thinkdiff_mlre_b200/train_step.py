@@ -385,6 +385,27 @@ class AlignerTrainStep:
             cb(events)  # the producer of the pinned buffers (EmbedShardReader) may recycle them once these have fired
         return (flat, start, lens, batch.total_rows, batch.l_max, tgt), events
 
+    def tune_copy_streams(self, batch: FlatBatch, device="cuda", candidates=(1, 2, 4), reps: int = 2) -> int:
+        """Pick how many copy streams ``prefetch`` spreads a batch over, by timing the H2D of ``batch`` alone for each candidate
+        (hosts differ: on some a single cudaMemcpyAsync stream reaches PCIe line rate, on others several DMA engines are needed,
+        on others more streams only add contention). Synchronises; call it once before the training loop."""
+        import time
+
+        best, best_t = int(getattr(self, "copy_streams", 2)), None
+        for k in candidates:
+            self.copy_streams = int(k)
+            self.prefetch(batch, device)  # creates the streams / warms the allocator
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                self.prefetch(batch, device)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / reps
+            if best_t is None or dt < best_t:
+                best, best_t = int(k), dt
+        self.copy_streams = best
+        return best
+
     def step_prefetched(self, handle) -> torch.Tensor:
         tensors, events = handle
         cur = torch.cuda.current_stream()
