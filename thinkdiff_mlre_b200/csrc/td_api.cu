@@ -789,7 +789,13 @@ int32_t td_adamw_step(int32_t num_tensors, float* const* params, const float* co
   // 2 CTAs per SM: a wave of them fits beside a resident GEMM CTA (registers: 320 x 128 + 256 x 64), the second wave takes the
   // SM over as soon as the GEMM's CTAs retire
   prefer_max_shared(adamw256_kernel);
-  if (wide) adamw256_kernel<<<dim3(grid_for_rows(max_n / 8, 256, 2), num_tensors), 256, 0, st>>>(a);
+  // TD_ADAMW: developer A/B of the launch shape -- "wide2" (default) = 256-bit kernel, 2 CTAs per SM; "wide8" = 256-bit, 8 per SM;
+  // "narrow8" = the 128-bit kernel, 8 per SM
+  static const int mode = [] {
+    const char* e = getenv("TD_ADAMW");
+    return !e ? 0 : !strcmp(e, "wide8") ? 1 : !strcmp(e, "narrow8") ? 2 : 0;
+  }();
+  if (wide && mode != 2) adamw256_kernel<<<dim3(grid_for_rows(max_n / 8, 256, mode == 1 ? 8 : 2), num_tensors), 256, 0, st>>>(a);
   else adamw_kernel<<<dim3(grid_for_rows(max_n / 4, 256, 8), num_tensors), 256, 0, st>>>(a);
   TD_CUDA(cudaGetLastError());
   return TD_OK;
