@@ -1,5 +1,5 @@
 #!/bin/bash
-# Multi-GPU check of a GEMM / peer change, usage: gpu_r2_multi3.sh N. (1) GEMM / peer / aligner / data-parallel parity tests,
+# Multi-GPU check of a GEMM / peer change, usage: gpu_multi.sh N. (1) GEMM / peer / aligner / data-parallel parity tests,
 # (2) N=1 A/B of the default library against every libthinkdiff_b200_<tag>.so (N=1 only: alternative builds may have an older
 # ABI for the multi-GPU entries), (3) the peer step at N with per-rank timelines.
 N=${1:-2}

@@ -199,3 +199,20 @@ def test_shard_bounds():
         assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     with pytest.raises(ValueError):
         shard_bounds(4, 2, 2)
+
+
+def test_peer_fold_struct_matches_the_header_layout():
+    """ctypes mirror of `td_peer_fold` (include/thinkdiff_b200.h): field order, natural alignment, 40 bytes on LP64."""
+    import ctypes as C
+    import re
+
+    from thinkdiff_mlre_b200 import _lib as L
+
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "thinkdiff_b200.h")).read()
+    body = re.search(r"typedef struct td_peer_fold \{(.*?)\} td_peer_fold;", header, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [re.search(r"(\w+)\s*$", decl.strip()).group(1) for decl in body.split(";") if decl.strip()]
+    assert names == [f[0] for f in L.PeerFold._fields_]
+    assert C.sizeof(L.PeerFold) == 40
+    assert L.PeerFold.signal_slot.offset == 8 and L.PeerFold.small_dst.offset == 16 and L.PeerFold.small_numel.offset == 32
+
