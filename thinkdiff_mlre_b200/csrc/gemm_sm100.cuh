@@ -126,10 +126,12 @@ template <> struct EpiStage<EPI_DGELU> { static constexpr int kBytesPerWarp = 61
 template <> struct EpiStage<EPI_F32> { static constexpr int kBytesPerWarp = 8192; };
 template <> struct EpiStage<EPI_F32_SCATTER> { static constexpr int kBytesPerWarp = 8192; };
 
-// Pipeline depth per epilogue kind. The GEMMs that the optimizer's update kernels run BESIDE (Linear1's update beside the dW2
-// GEMM, Linear2's beside the next forward's first GEMM) keep one stage less than would fit: the 32 KB they leave free -- and their
-// 128 registers per thread -- let one 256-thread CTA of an HBM-bound update kernel be co-resident on every SM, which is the only
-// way such a kernel gets bandwidth while a persistent GEMM holds all 148 SMs.
+// Pipeline depth per epilogue kind. The GEMMs that the optimizer's update kernels may run BESIDE (Linear1's update beside the dW2
+// GEMM, Linear2's beside the next forward's first GEMM) keep five stages: with <= 128 registers per thread (see TD_GEMM_BOUNDS)
+// and the shared memory this leaves, one 256-thread CTA of an update kernel can become resident next to the GEMM's CTA instead
+// of queueing until the persistent GEMM retires. Measured: where the update is full size (N = 1) running
+// it beside a GEMM is no faster than running it after it -- the step is power-bound -- but in the data-parallel step it lets every
+// owner finish its AdamW rows while its own dW2 GEMM still runs, so ranks that are ahead never wait for a laggard's rows.
 template <int EPI> struct StageCap { static constexpr int kMax = TD_MAX_STAGES; };
 #ifndef TD_NO_CORESIDENCY
 template <> struct StageCap<EPI_BIAS_GELU> { static constexpr int kMax = 5; };
@@ -469,8 +471,9 @@ constexpr int kSchedStages = 4;
 
 // Register budget. A warp's registers come from its SM sub-partition's quarter of the register file (16 384 x 32 bit): the ten
 // GEMM warps put three on sub-partitions 0 and 1, so at more than 128 registers per thread (allocated in units of 8) there is no
-// room left there for even two warps of a co-resident 256-thread update kernel at 64 registers -- which then sits in the block
-// scheduler until the GEMM's CTAs exit. TD_GEMM_MAXNREG caps the allocation (3 x 32 x 128 + 2 x 32 x 64 = 16 384 exactly).
+// room left there for even two warps of a co-resident 256-thread update kernel at 64 registers (3 x 32 x 128 + 2 x 32 x 64 =
+// 16 384 exactly) -- it then sits in the block scheduler until the GEMM's CTAs exit. The fp32-output epilogues compile to
+// 124-126 registers; TD_GEMM_MAXNREG caps every instantiation (developer A/B: with it the N = 1 step was 2.5 % SLOWER).
 #ifdef TD_GEMM_MAXNREG
 #define TD_GEMM_BOUNDS __maxnreg__(TD_GEMM_MAXNREG)
 #else
