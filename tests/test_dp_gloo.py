@@ -99,3 +99,45 @@ def test_peer_setup_fails_on_every_rank_with_one_message():
         pytest.skip("exercises the failure path of a box without CUDA")
     got = dict(spawn_ranks(_peer_setup_worker, 2))
     assert got[0] == got[1] and got[0].startswith("peer data parallel set-up failed") and "rank 0" in got[0] and "rank 1" in got[0]
+
+
+def _dying_worker(rank, world, init, ret):
+    dist.init_process_group("gloo", init_method=init, rank=rank, world_size=world)
+    if rank == 0:
+        raise SystemExit(3)  # dies before reporting; rank 1 would wait for it forever
+    dist.barrier()
+    ret.put(rank)
+
+
+def test_spawn_ranks_reports_a_dead_rank_at_once_and_reaps_the_others():
+    """The process harness itself: a rank that dies must fail the test within seconds (not after the result timeout) and must
+    not leave its peer running -- a stuck orphan once kept a GPU box busy for 15 minutes after its test had already failed."""
+    import time
+
+    t0 = time.monotonic()
+    with pytest.raises(RuntimeError, match="died before reporting"):
+        spawn_ranks(_dying_worker, 2, timeout=120)
+    assert time.monotonic() - t0 < 60
+
+
+def test_bench_resolves_the_nvml_handle_by_uuid_not_by_index():
+    """bench.py samples clocks / binds NUMA through NVML, which enumerates every GPU of a box while CUDA enumerates
+    CUDA_VISIBLE_DEVICES: the handle must come from the CUDA device's UUID."""
+    import importlib.util
+    import types
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    calls = []
+    fake = types.SimpleNamespace(nvmlDeviceGetHandleByUUID=lambda u: calls.append(("uuid", u)) or "H-uuid",
+                                 nvmlDeviceGetHandleByPciBusId=lambda b: calls.append(("pci", b)) or "H-pci",
+                                 nvmlDeviceGetHandleByIndex=lambda i: calls.append(("index", i)) or "H-index")
+    real = torch.cuda.get_device_properties
+    try:
+        torch.cuda.get_device_properties = lambda i: types.SimpleNamespace(uuid="abc-123", pci_bus_id=7, pci_domain_id=0, pci_device_id=0)
+        assert bench.nvml_handle(fake, 0) == "H-uuid" and calls == [("uuid", b"GPU-abc-123")]
+        torch.cuda.get_device_properties = lambda i: (_ for _ in ()).throw(RuntimeError("no CUDA"))
+        assert bench.nvml_handle(fake, 3) == "H-index"
+    finally:
+        torch.cuda.get_device_properties = real
