@@ -63,6 +63,12 @@ int32_t td_pack_varlen(const void* src, const int64_t* src_row_start /*[B]*/, co
 int32_t td_pack_varlen_indexed(const void* src, const int64_t* src_row_start, const int32_t* cu_seqlens, int32_t B,
                                int64_t total_rows, int64_t row_bytes, void* dst_packed, int64_t* src_row_out,
                                td_stream_t stream);
+/* Gather from TWO sources with one launch: segment i with src_row_start[i] >= 0 reads rows of `src`, with src_row_start[i] =
+ * -(s + 1) rows s.. of `src2`. The ragged `[img1 | img2 | text]` composition of the reference's two-image demo
+ * (scripts/test/test_blip_vision_t5_decoder_flux_text.py:184-208: torch.cat([...], dim=1) per sample) without first concatenating
+ * the aligner output and the text embeddings into one buffer. */
+int32_t td_pack_varlen2(const void* src, const void* src2, const int64_t* src_row_start, const int32_t* cu_seqlens, int32_t B,
+                        int64_t total_rows, int64_t row_bytes, void* dst_packed, td_stream_t stream);
 /* Reference layout: zero-padded [B, L_max, row_bytes] + int64 mask [B, L_max] (mask may be NULL). With
  * src = a packed buffer and src_row_start[i] = cu_seqlens[i] this is the inverse of td_pack_varlen. */
 int32_t td_pack_padded(const void* src, const int64_t* src_row_start, const int32_t* cu_seqlens, int32_t B, int32_t L_max,

@@ -29,6 +29,7 @@ SIGNATURES = {
     "td_cu_seqlens": (_i32, [_vp, _i32, _vp, _vp]),
     "td_pack_varlen": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp]),
     "td_pack_varlen_indexed": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp]),
+    "td_pack_varlen2": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp]),
     "td_pack_padded": (_i32, [_vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]),
     "td_cast_f32_to_bf16": (_i32, [_vp, _vp, _i64, _vp]),
     "td_aligner_fwd_workspace_bytes": (_i64, [_i64, _i32, _i32]),

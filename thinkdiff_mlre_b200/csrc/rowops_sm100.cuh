@@ -105,14 +105,17 @@ __global__ void cu_seqlens_kernel(const int* __restrict__ lens, int B, int* __re
 //   PADDED = false: dst row r of the packed buffer [M, row] <- sample i = upper_bound(cu, r) - 1, row j = r - cu[i]
 //   PADDED = true : dst row r of [B, Lmax, row] <- sample i = r / Lmax, row j = r % Lmax if j < len_i else zeros;
 //                   mask[r] = (j < len_i) as int64 (reference mask dtype, ...embed_2.py:118,128)
-// Source row = src_row_start[i] + j in the flat source (the un-truncated per-sample embeddings back to back).
+// Source row = src_row_start[i] + j in the flat source (the un-truncated per-sample embeddings back to back). With a second
+// source (src2 != nullptr), a NEGATIVE src_row_start[i] = -(s + 1) means "row s + j of src2": segments of two separate tensors
+// are gathered by one launch without concatenating them first (image tokens | text embeddings, BASELINE config 4).
 constexpr int kPackMaxStagedSeqs = 2048;  // cu_seqlens / src_row_start are staged in shared memory up to this batch size
 
 template <bool PADDED>
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const uint4* __restrict__ src, const long long* __restrict__ src_row_start,
                  const int* __restrict__ cu, int B, long long dst_rows, int Lmax, int vec_per_row,
-                 uint4* __restrict__ dst, long long* __restrict__ mask, long long* __restrict__ src_row_out) {
+                 uint4* __restrict__ dst, long long* __restrict__ mask, long long* __restrict__ src_row_out,
+                 const uint4* __restrict__ src2 = nullptr) {
   __shared__ int s_cu[kPackMaxStagedSeqs + 1];
   __shared__ long long s_start[kPackMaxStagedSeqs];
   const bool staged = B <= kPackMaxStagedSeqs;
@@ -145,9 +148,12 @@ pack_rows_kernel(const uint4* __restrict__ src, const long long* __restrict__ sr
     }
     uint4* d = dst + r * vec_per_row;
     if (valid) {
-      const long long src_row = start_t[i] + j;
+      long long src_row = start_t[i];
+      const uint4* base = src;
+      if (src2 != nullptr && src_row < 0) { src_row = -(src_row + 1); base = src2; }
+      src_row += j;
       if (src_row_out != nullptr && lane == 0) src_row_out[r] = src_row;  // lets later kernels read sibling tensors unpacked
-      const uint4* s = src + src_row * vec_per_row;
+      const uint4* s = base + src_row * vec_per_row;
       for (int v0 = 0; v0 < vec_per_row; v0 += 256) {
         uint4 t[8];
 #pragma unroll

@@ -180,6 +180,26 @@ int32_t td_pack_varlen_indexed(const void* src, const int64_t* src_row_start, co
   return TD_OK;
 }
 
+int32_t td_pack_varlen2(const void* src, const void* src2, const int64_t* src_row_start, const int32_t* cu, int32_t B,
+                        int64_t total_rows, int64_t row_bytes, void* dst, td_stream_t stream) {
+  TD_DEVICE_OR_RETURN();
+  if (B < 0 || total_rows < 0 || row_bytes <= 0 || row_bytes % 16)
+    TD_FAIL(TD_ERR_ARG, "td_pack_varlen2: row_bytes=%lld must be a positive multiple of 16", (long long)row_bytes);
+  if (total_rows == 0 || B == 0) return TD_OK;
+  if (!src || !src2 || !src_row_start || !cu || !dst) TD_FAIL(TD_ERR_ARG, "td_pack_varlen2: null pointer");
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(src2) | reinterpret_cast<uintptr_t>(dst)) & 15)
+    TD_FAIL(TD_ERR_ARG, "td_pack_varlen2: buffers must be 16-byte aligned");
+  const int grid = grid_for_rows(total_rows, 8, 8);
+  {
+    ProfScope prof("pack_varlen", 2.0 * double(total_rows) * double(row_bytes), (cudaStream_t)stream);
+    pack_rows_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint4*>(src), reinterpret_cast<const long long*>(src_row_start), cu, B, total_rows, 0,
+        int(row_bytes / 16), static_cast<uint4*>(dst), nullptr, nullptr, static_cast<const uint4*>(src2));
+  }
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
 int32_t td_pack_padded(const void* src, const int64_t* src_row_start, const int32_t* cu, int32_t B, int32_t L_max,
                        int64_t row_bytes, void* dst, int64_t* mask, td_stream_t stream) {
   TD_DEVICE_OR_RETURN();

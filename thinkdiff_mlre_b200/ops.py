@@ -54,6 +54,24 @@ def pack_varlen(flat: torch.Tensor, src_row_start: torch.Tensor, cu: torch.Tenso
     return (out, index) if want_index else out
 
 
+def pack_varlen2(src: torch.Tensor, src2: torch.Tensor, src_row_start: torch.Tensor, cu: torch.Tensor, total_rows: int):
+    """Gather ragged segments of TWO tensors ``[R1, C]`` / ``[R2, C]`` into one packed ``[total_rows, C]`` with a single launch:
+    segment i reads rows ``src_row_start[i]..`` of ``src`` when that is >= 0, rows ``-(src_row_start[i] + 1)..`` of ``src2`` otherwise."""
+    _need_cuda(src, src2, src_row_start, cu)
+    _contig(src, "src")
+    _contig(src2, "src2")
+    if src.shape[1:] != src2.shape[1:] or src.dtype != src2.dtype:
+        raise ValueError("pack_varlen2: the two sources must agree in row shape and dtype")
+    if src_row_start.dtype != torch.int64 or cu.dtype != torch.int32:
+        raise TypeError("src_row_start must be int64 and cu_seqlens int32")
+    out = torch.empty((total_rows, src.shape[1]), dtype=src.dtype, device=src.device)
+    row_bytes = src.shape[1] * src.element_size()
+    L.launch_count += 1
+    L.check(L.lib().td_pack_varlen2(L.ptr(src), L.ptr(src2), L.ptr(src_row_start), L.ptr(cu), cu.numel() - 1, total_rows, row_bytes,
+                                    L.ptr(out), L.stream_ptr()), "td_pack_varlen2")
+    return out
+
+
 def pack_padded(flat: torch.Tensor, src_row_start: torch.Tensor, cu: torch.Tensor, l_max: int, want_mask: bool = True):
     """Reference layout: zero-padded [B, l_max, C] and int64 mask [B, l_max]."""
     _need_cuda(flat, src_row_start, cu)

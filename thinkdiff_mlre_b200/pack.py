@@ -178,16 +178,17 @@ def compose_image_text(image_tokens: torch.Tensor, text_flat: torch.Tensor, text
     if len(text_lens) != B or text_flat.shape[1] != D or text_flat.dtype != image_tokens.dtype:
         raise ValueError("text_flat / text_lens do not match image_tokens")
     dev = image_tokens.device
-    flat = torch.cat([image_tokens.reshape(B * n_img, D), text_flat])  # segments of one source buffer
     text_start = [0] * B
     for i in range(1, B):
         text_start[i] = text_start[i - 1] + text_lens[i - 1]
     starts, lens = [], []
-    for i in range(B):  # two segments per sample: its image rows, then its text rows
-        starts += [i * n_img, B * n_img + text_start[i]]
+    for i in range(B):  # two segments per sample: its image rows (first source), then its text rows (second source: -(row + 1))
+        starts += [i * n_img, -(text_start[i] + 1)]
         lens += [n_img, text_lens[i]]
     start_t = torch.tensor(starts, dtype=torch.int64).to(dev, non_blocking=True)
     lens_t = torch.tensor(lens, dtype=torch.int32).to(dev, non_blocking=True)
-    seg = pack_device(flat, start_t, lens_t, sum(lens), max(n_img + t for t in text_lens))
+    cu = ops.cu_seqlens(lens_t)
+    # one gather launch reading both tensors where they lie (no torch.cat of the aligner output and the text embeddings)
+    x = ops.pack_varlen2(image_tokens.reshape(B * n_img, D).contiguous(), text_flat.contiguous(), start_t, cu, sum(lens))
     sample_lens = torch.tensor([n_img + t for t in text_lens], dtype=torch.int32)
-    return PackedBatch(seg.x, seg.cu_seqlens[::2].contiguous(), sample_lens, int(sample_lens.max()), {"n_img": n_img})
+    return PackedBatch(x, cu[::2].contiguous(), sample_lens, int(sample_lens.max()), {"n_img": n_img})
