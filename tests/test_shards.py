@@ -63,3 +63,42 @@ def test_shard_rejects_garbage(tmp_path):
     w = td.EmbedShardWriter(str(tmp_path / "x.tdemb"), width=8)
     with pytest.raises(ValueError):
         w.add(torch.zeros(3, 8), [1, 2, 3])  # float32, not bf16
+
+
+def test_prefetched_batches_equal_plain_batches_in_order(tmp_path):
+    """batches_prefetched(): the slab copies move to a background thread; batches, order and replayed split points are those of
+    batches(). Also: abandoning the iterator early stops the thread, and a failure inside it surfaces in the consumer."""
+    rng = np.random.RandomState(3)
+    path = str(tmp_path / "p.tdemb")
+    n, width = 23, 64
+    with td.EmbedShardWriter(path, width=width) as w:
+        for i in range(n):
+            L = int(rng.randint(2, 40))
+            e = torch.from_numpy(rng.standard_normal((L, width)).astype(np.float32)).to(torch.bfloat16)
+            w.add(e, list(range(L)), f"t{i}", f"k{i}")
+    bi = dict(use_output_embed=1, use_input_embed=0, random_split_output_embed=1, output_embed_max_split_len=16, output_embed_max_len=64,
+              input_embed_max_len=64)
+    r = td.EmbedShardReader(path)
+    random.seed(11)
+    plain = list(r.batches(4, bi, pin_memory=False))
+    for depth in (1, 2):
+        random.seed(11)
+        pre = list(r.batches_prefetched(4, bi, depth=depth, pin_memory=False))
+        assert len(pre) == len(plain) == n // 4
+        for a, b in zip(plain, pre):
+            assert torch.equal(a.flat.view(torch.int16), b.flat.view(torch.int16))
+            assert a.lens.tolist() == b.lens.tolist() and a.src_row_start.tolist() == b.src_row_start.tolist() and a.l_max == b.l_max
+            assert a.extras["output_token_ids"] == b.extras["output_token_ids"]
+    it = r.batches_prefetched(4, bi, depth=2, pin_memory=False)
+    next(it)
+    it.close()  # consumer walks away: the producer thread must stop instead of blocking on a full queue
+    import threading
+    import time
+
+    t0 = time.monotonic()
+    while any(t.name == "td-shard-prefetch" for t in threading.enumerate()) and time.monotonic() - t0 < 5:
+        time.sleep(0.05)
+    assert not any(t.name == "td-shard-prefetch" for t in threading.enumerate())
+    with pytest.raises(KeyError):  # a broken build_info fails in the thread and is re-raised here
+        list(r.batches_prefetched(4, {"random_split_output_embed": 1}, pin_memory=False))
+    r.close()

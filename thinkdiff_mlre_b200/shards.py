@@ -177,6 +177,50 @@ class EmbedShardReader:
                 return
             yield self.batch(lo, hi, build_info, pin_memory)
 
+    def batches_prefetched(self, batch_size: int, build_info: dict, depth: int = 2, drop_last: bool = True, pin_memory: bool = True):
+        """``batches()`` with the slab copies done by a background thread, ``depth`` (1 or 2) batches ahead of the consumer: the
+        page-cache -> pinned-memory memcpy of batch i+1 (numpy releases the GIL for it) overlaps the H2D and the training step of
+        batch i -- what the reference gets from DataLoader workers + PrefetchLoader (thinkdiff/datasets/datasets/dataloader_utils.py
+        :45-118), without worker processes or pickling. Same batches, same order, same split points as ``batches()`` (the thread is
+        the only caller of ``random`` while it runs). ``depth`` stays below the pinned ring's three slots, so a slot is never
+        refilled while the consumer may still hold the batch that lives in it."""
+        import queue
+        import threading
+
+        depth = max(1, min(int(depth), 2))
+        q: queue.Queue = queue.Queue(maxsize=depth)
+        stop = threading.Event()
+        done = object()
+
+        def produce():
+            try:
+                for b in self.batches(batch_size, build_info, drop_last, pin_memory):
+                    while not stop.is_set():
+                        try:
+                            q.put(b, timeout=0.1)
+                            break
+                        except queue.Full:
+                            continue
+                    if stop.is_set():
+                        return
+                q.put(done)
+            except BaseException as e:  # noqa: BLE001  (re-raised in the consumer)
+                q.put(e)
+
+        th = threading.Thread(target=produce, name="td-shard-prefetch", daemon=True)
+        th.start()
+        try:
+            while True:
+                item = q.get()
+                if item is done:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:
+            stop.set()
+            th.join(timeout=5)
+
     def close(self):
         self.rows = self.lens = self.ids_index = self.ids = None
         try:
