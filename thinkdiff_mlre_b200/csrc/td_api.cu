@@ -1078,12 +1078,15 @@ int32_t td_masked_ce_fwd_bwd(const void* logits, int32_t dtype, const int64_t* l
   if (R > 0) {
     const size_t smem = (size_t)V * (dtype == TD_DTYPE_BF16 ? 2 : 4);  // the row is staged in its input dtype
     ProfScope prof("masked_ce", double(R) * V * (dtype == TD_DTYPE_BF16 ? 2.0 : 4.0) * (dlogits ? 2.0 : 1.0), st);
-    static bool attr_done[2] = {false, false};
+    static std::atomic<bool> attr_done_dev[2][kMaxDevices];  // (function attributes are per device)
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDevices) TD_FAIL(TD_ERR_DRIVER, "no current CUDA device");
+    std::atomic<bool>* attr_done[2] = {&attr_done_dev[0][dev], &attr_done_dev[1][dev]};
     if (dtype == TD_DTYPE_BF16) {
-      if (!attr_done[1]) { TD_CUDA(cudaFuncSetAttribute(masked_ce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done[1] = true; }
+      if (!attr_done[1]->load()) { TD_CUDA(cudaFuncSetAttribute(masked_ce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done[1]->store(true); }
       masked_ce_kernel<true><<<int(R), kCeThreads, smem, st>>>(logits, reinterpret_cast<const long long*>(labels), V, meta, grad_scale, dlogits, row_loss);
     } else {
-      if (!attr_done[0]) { TD_CUDA(cudaFuncSetAttribute(masked_ce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done[0] = true; }
+      if (!attr_done[0]->load()) { TD_CUDA(cudaFuncSetAttribute(masked_ce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done[0]->store(true); }
       masked_ce_kernel<false><<<int(R), kCeThreads, smem, st>>>(logits, reinterpret_cast<const long long*>(labels), V, meta, grad_scale, dlogits, row_loss);
     }
     TD_CUDA(cudaGetLastError());

@@ -77,7 +77,8 @@ class _LMHeadCE(torch.autograd.Function):
 def lm_head_cross_entropy(sequence_output: torch.Tensor, lm_head_weight: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
     """``CrossEntropyLoss(ignore_index=-100)(lm_head(sequence_output).view(-1, V), labels.view(-1))`` of the frozen T5 decoder
     (thinkdiff/models/mllama_vllm_t5_embed_decoder_2.py:236-246) as one call: tcgen05 GEMM -> single-read CE (the logits' gradient
-    overwrites them in place) -> tcgen05 GEMM back to ``sequence_output``. The head is frozen (the whole T5 is,
+    overwrites them in place) -> tcgen05 GEMM back to ``sequence_output``. Pass the weight as bfloat16 (``model.language_model.to(
+    torch.bfloat16)`` for the frozen parts) to skip the per-call cast autocast would otherwise repeat. The head is frozen (the whole T5 is,
     ...embed_decoder_2.py:715-717, `freeze_language`), so no weight gradient is formed. SURVEY.md section 8 f-1, first slice."""
     if lm_head_weight.requires_grad:
         raise NotImplementedError("lm_head_cross_entropy: the T5 head is frozen in ThinkDiff; a trainable head has no kernel path")
