@@ -229,6 +229,12 @@ int32_t td_aligner_bwd_dh2_scatter(const void* dh2, const void* x, const void* h
                                    int32_t world, int32_t rank /* of the caller; < 0: no traffic shaping */,
                                    const td_peer_fold* fold /*[host] or NULL*/, void* workspace, int64_t workspace_bytes,
                                    int32_t phases, td_stream_t stream);
+/* Host arithmetic only (needs no GPU): the rank that owns the rows of output tile number `tile` (256 x 256 tiles, in the order
+ * the kernel claims them) of a row-scattered M x N weight-gradient GEMM run by `rank` of `world`; the tile's block coordinates
+ * go to m_blk / n_blk when those are non-NULL. Documents (and lets a CPU test check) the traffic shaping: for any `tile`, the
+ * owners over rank = 0..world-1 are all different. Returns -1 on arguments the scattered GEMM would reject. */
+int32_t td_scatter_tile_owner(int32_t tile, int32_t M, int32_t N, int32_t world, int32_t rank, int32_t* m_blk /*[host]*/,
+                              int32_t* n_blk /*[host]*/);
 /* Test entry for the scatter epilogue: out[M, N] = alpha * A^T.B with A [K, M], B [K, N] (both MN-major, the weight-gradient
  * shape), rows [o M/world, (o+1) M/world) written to dst[o] ([M / world, N] fp32). `rank` >= 0 (and an owner's rows being whole
  * 256-row tiles) selects the owner-grouped tile order rotated by rank that the data-parallel step uses, so that the N ranks'

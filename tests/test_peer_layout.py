@@ -40,3 +40,50 @@ def test_rejects_unsupported_worlds():
         ExchangeLayout(9, 512, 512)
     with pytest.raises(ValueError):
         ExchangeLayout(3, 512, 512)  # 512 rows do not divide by 3
+
+
+import ctypes as C
+
+import pytest
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("N", [3584, 4096])
+def test_scattered_gemm_tile_order_is_a_permutation_across_ranks(world, N):
+    """Traffic shaping of the data-parallel weight-gradient GEMMs (host arithmetic of the library, no GPU): every rank walks every
+    output tile exactly once; at every position of that walk the `world` ranks store to `world` DIFFERENT owners (NVLink sees a
+    permutation, never N senders into one port); each rank starts with the rows of owner rank + 1 and ends with its own rows."""
+    from thinkdiff_mlre_b200 import _lib as L
+
+    M = 4096
+    f = L.lib().td_scatter_tile_owner
+    tiles = (M // 256) * ((N + 255) // 256)
+    per_rank = []
+    for rank in range(world):
+        owners, coords = [], set()
+        for t in range(tiles):
+            m, n = C.c_int32(-1), C.c_int32(-1)
+            o = f(t, M, N, world, rank, C.byref(m), C.byref(n))
+            assert 0 <= o < world and o == (m.value * 256) // (M // world)
+            owners.append(o)
+            coords.add((m.value, n.value))
+        assert len(coords) == tiles  # a bijection onto the tile grid
+        assert owners[0] == (rank + 1) % world and owners[-1] == rank
+        assert all(owners[i] == owners[i - 1] or owners[i] == (owners[i - 1] + 1) % world for i in range(1, tiles))
+        per_rank.append(owners)
+    for t in range(tiles):
+        assert len({per_rank[r][t] for r in range(world)}) == world
+    # without a rank (rank < 0: the local-output tile order) all callers agree, and bad arguments are rejected
+    assert f(0, M, N, world, -1, None, None) == 0
+    assert f(tiles, M, N, world, 0, None, None) == -1 and f(0, M, N, 3, 0, None, None) == -1
+
+
+def test_scattered_gemm_tile_order_small_owner_blocks_keep_the_common_order():
+    """Owner blocks smaller than a 256-row tile (the dims of bench.py's dp_parity check) cannot be rotated tile-wise: every rank
+    keeps the common order, which is also what keeps that check bit-identical to the local-output GEMM."""
+    from thinkdiff_mlre_b200 import _lib as L
+
+    f = L.lib().td_scatter_tile_owner
+    for rank in range(8):
+        m = C.c_int32(-1)
+        assert f(0, 512, 192, 8, rank, C.byref(m), None) == 0 and m.value == 0

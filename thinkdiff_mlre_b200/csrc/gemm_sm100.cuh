@@ -202,12 +202,13 @@ __device__ __forceinline__ void for_each_segment(const GemmParams& p, int unit, 
 }
 
 constexpr int kGroupM = 8;  // rasterise m-blocks in groups so that concurrently running tiles share operands in L2
-__device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& m_blk, int& n_blk) {
+__host__ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& m_blk, int& n_blk) {
   const int nnb = p.num_n_blocks;
   const int G = p.raster_group_m > 0 ? p.raster_group_m : kGroupM;
   const int group = tile / (G * nnb);
   const int first_m = group * G;
-  const int gsize = min(G, p.num_m_blocks - first_m);
+  const int rest_m = p.num_m_blocks - first_m;
+  const int gsize = G < rest_m ? G : rest_m;
   const int in_group = tile - group * G * nnb;
   m_blk = first_m + in_group % gsize;
   n_blk = in_group / gsize;

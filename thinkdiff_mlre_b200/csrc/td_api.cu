@@ -489,6 +489,19 @@ struct BwdExtras {
   float loss_div = 1.f;
 };
 
+// Rows per owner and the NVLink traffic shaping of a row-scattered GEMM (see GemmParams::raster_group_m): tiles are grouped by
+// owner, and rank r starts with the rows of owner r + 1 and ends with its own (local) rows. Only when an owner's rows are whole
+// pair tiles (256 rows).
+void set_scatter_raster(GemmParams& p, int world, int rank) {
+  p.scatter_rows = p.M / world;
+  const int tile_m = 2 * kBlockM;
+  if (rank >= 0 && rank < world && world > 1 && p.scatter_rows % tile_m == 0) {
+    const int per_owner = p.scatter_rows / tile_m;
+    p.raster_group_m = per_owner < kGroupM ? per_owner : kGroupM;
+    p.raster_rot_m = ((rank + 1) % world) * per_owner;
+  }
+}
+
 int launch_dw_gemm(GemmOperand a, GemmOperand b, GemmParams& p, float* const* dst, int world, int rank, void* sk, cudaStream_t st,
                    const char* tag, const ScatterDst* signal_from = nullptr) {
   if (world <= 0) return launch_gemm<2, true, true, EPI_F32>(a, b, p, sk, st, tag);
@@ -498,15 +511,7 @@ int launch_dw_gemm(GemmOperand a, GemmOperand b, GemmParams& p, float* const* ds
   }
   if (p.M % world || (p.M / world) % 32) TD_FAIL(TD_ERR_UNSUPPORTED, "row-scattered GEMM: %d rows over %d ranks must give a multiple of 32 rows per rank", p.M, world);
   for (int o = 0; o < world; ++o) p.scatter_dst[o] = dst[o];
-  p.scatter_rows = p.M / world;
-  // NVLink traffic shaping (see GemmParams::raster_group_m): tiles are grouped by owner, and rank r starts with the rows of
-  // owner r + 1 and ends with its own (local) rows. Only when an owner's rows are whole pair tiles (256 rows).
-  const int tile_m = 2 * kBlockM;
-  if (rank >= 0 && rank < world && world > 1 && p.scatter_rows % tile_m == 0) {
-    const int per_owner = p.scatter_rows / tile_m;
-    p.raster_group_m = per_owner < kGroupM ? per_owner : kGroupM;
-    p.raster_rot_m = ((rank + 1) % world) * per_owner;
-  }
+  set_scatter_raster(p, world, rank);
   return launch_gemm<2, true, true, EPI_F32_SCATTER>(a, b, p, sk, st, tag);
 }
 
@@ -1005,6 +1010,23 @@ int32_t td_adamw_slots_step(float* param, const float* grad_slots, int64_t slot_
   adamw_slots_kernel<<<grid_for_rows(numel / 4, 256, 2), 256, 0, st>>>(a);
   TD_CUDA(cudaGetLastError());
   return TD_OK;
+}
+
+int32_t td_scatter_tile_owner(int32_t tile, int32_t M, int32_t N, int32_t world, int32_t rank, int32_t* m_blk_out, int32_t* n_blk_out) {
+  // host arithmetic only (no device needed): the same tile_coords() the kernel runs, with the raster launch_dw_gemm sets up
+  if (M <= 0 || N <= 0 || world < 1 || world > kMaxPeers || M % world || (M / world) % 32 || rank >= world) return -1;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N;
+  p.num_m_blocks = (M + 2 * kBlockM - 1) / (2 * kBlockM);
+  p.num_n_blocks = (N + kBlockN - 1) / kBlockN;
+  if (tile < 0 || tile >= p.num_m_blocks * p.num_n_blocks) return -1;
+  set_scatter_raster(p, world, rank);
+  int m_blk = 0, n_blk = 0;
+  tile_coords(p, tile, m_blk, n_blk);
+  if (m_blk_out) *m_blk_out = m_blk;
+  if (n_blk_out) *n_blk_out = n_blk;
+  return (m_blk * 2 * kBlockM) / p.scatter_rows;
 }
 
 int32_t td_gemm_tn_scatter(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int32_t N, int64_t K, float alpha,
