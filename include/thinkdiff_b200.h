@@ -229,6 +229,13 @@ int32_t td_aligner_bwd_dh2_scatter(const void* dh2, const void* x, const void* h
                                    int32_t world, int32_t rank /* of the caller; < 0: no traffic shaping */,
                                    const td_peer_fold* fold /*[host] or NULL*/, void* workspace, int64_t workspace_bytes,
                                    int32_t phases, td_stream_t stream);
+/* Host arithmetic only (needs no GPU): the work schedule of one M x N x K GEMM launch on `workers` CTA pairs -- the whole-tile
+ * waves and, with stream_k != 0, the tail whose tiles are cut along K -- as the list of segments the kernel's workers claim, in
+ * claim order: out[8 i ..] = {unit, tile, first k-block, end k-block, kind (0 whole tile or unshared, 1 owner of a shared tile,
+ * 2 contributor), first contributor range, number of contributor ranges, tail range index}. Returns the number of segments (which
+ * may exceed max_segments: only that many are written), -1 on bad arguments. For tests of the scheduler's coverage properties. */
+int32_t td_gemm_schedule(int64_t M, int32_t N, int64_t K, int32_t workers, int32_t stream_k, int32_t* out /*[host]*/,
+                         int32_t max_segments);
 /* Host arithmetic only (needs no GPU): the rank that owns the rows of output tile number `tile` (256 x 256 tiles, in the order
  * the kernel claims them) of a row-scattered M x N weight-gradient GEMM run by `rank` of `world`; the tile's block coordinates
  * go to m_blk / n_blk when those are non-NULL. Documents (and lets a CPU test check) the traffic shaping: for any `tile`, the

@@ -64,6 +64,7 @@ SIGNATURES = {
     "td_sum_slots": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp]),
     "td_adamw_slots_step": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _f32, _vp, _vp]),
     "td_aligner_bwd_dh2_scatter": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i32, _vp]),
+    "td_gemm_schedule": (_i32, [_i64, _i32, _i64, _i32, _i32, _vp, _i32]),
     "td_scatter_tile_owner": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "td_gemm_tn_scatter": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _i64, _f32, _vp, _i32, _i32, _vp, _i64, _vp]),
     "td_loss_workspace_bytes": (_i64, [_i64]),

@@ -161,20 +161,20 @@ struct Segment {
   int kind;           // 0 = whole tile / owner without contributors, 1 = owner with contributors, 2 = contributor
   int contrib0, contrib_n;  // kind 1: workers contrib0 .. contrib0 + contrib_n - 1 hold the rest of the tile
 };
-__device__ __forceinline__ int sk_start(const GemmParams& p, int w) { return w * p.tail_q + min(w, p.tail_r); }
-__device__ __forceinline__ int sk_worker_of(const GemmParams& p, int u) {
+__host__ __device__ __forceinline__ int sk_start(const GemmParams& p, int w) { return w * p.tail_q + (w < p.tail_r ? w : p.tail_r); }
+__host__ __device__ __forceinline__ int sk_worker_of(const GemmParams& p, int u) {
   const int big = p.tail_r * (p.tail_q + 1);
   return u < big ? u / (p.tail_q + 1) : p.tail_r + (u - big) / p.tail_q;
 }
 // Units: [0, F) = whole tiles (F = full_waves * workers, or every tile when there is no stream-K workspace), then the tail
 // ranges in descending order. Calls f(segment, range) for every segment of `unit`, in execution order (a range that straddles a
 // tile boundary is a contributor part followed by an owner part).
-__device__ __forceinline__ int num_units(const GemmParams& p) {
+__host__ __device__ __forceinline__ int num_units(const GemmParams& p) {
   const int whole = p.tail_workers == 0 ? p.num_m_blocks * p.num_n_blocks : p.full_waves * p.workers;
   return whole + p.tail_workers;
 }
 template <class F>
-__device__ __forceinline__ void for_each_segment(const GemmParams& p, int unit, F&& f) {
+__host__ __device__ __forceinline__ void for_each_segment(const GemmParams& p, int unit, F&& f) {
   const int KB = p.num_k_blocks;
   const int whole = p.tail_workers == 0 ? p.num_m_blocks * p.num_n_blocks : p.full_waves * p.workers;
   if (unit < whole) {
@@ -187,7 +187,7 @@ __device__ __forceinline__ void for_each_segment(const GemmParams& p, int unit, 
   while (u < u_end) {
     const int tt = u / KB;
     const int kb0 = u - tt * KB;
-    const int kb1 = min(KB, kb0 + (u_end - u));
+    const int kb1 = (kb0 + (u_end - u)) < KB ? (kb0 + (u_end - u)) : KB;
     Segment s{whole + tt, kb0, kb1, 0, 0, 0};
     if (kb0 > 0) {
       s.kind = 2;

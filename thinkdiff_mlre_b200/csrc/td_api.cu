@@ -1012,6 +1012,37 @@ int32_t td_adamw_slots_step(float* param, const float* grad_slots, int64_t slot_
   return TD_OK;
 }
 
+}  // extern "C"
+namespace {
+struct SegmentRecorder {  // (a functor rather than a lambda: for_each_segment is __host__ __device__)
+  int32_t* out; int max; int* n; int unit;
+  __host__ __device__ void operator()(const Segment& s, int range) const {
+    if (*n < max) {
+      int32_t* o = out + 8 * *n;
+      o[0] = unit; o[1] = s.tile; o[2] = s.kb0; o[3] = s.kb1; o[4] = s.kind; o[5] = s.contrib0; o[6] = s.contrib_n; o[7] = range;
+    }
+    ++*n;
+  }
+};
+}  // namespace
+extern "C" {
+
+int32_t td_gemm_schedule(int64_t M, int32_t N, int64_t K, int32_t workers, int32_t stream_k, int32_t* out, int32_t max_segments) {
+  // host arithmetic only: plan_schedule() + for_each_segment(), the code the launch and the kernel run
+  if (M <= 0 || N <= 0 || K <= 0 || workers < 1 || M > 0x7fffffffll || K > 0x7fffffffll || (max_segments > 0 && !out)) return -1;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = int(M); p.N = N; p.K = int(K);
+  p.num_m_blocks = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);
+  p.num_n_blocks = (p.N + kBlockN - 1) / kBlockN;
+  p.num_k_blocks = (p.K + kBlockK - 1) / kBlockK;
+  plan_schedule(p, workers, stream_k != 0);
+  int n = 0;
+  const int units = num_units(p);
+  for (int u = 0; u < units; ++u) for_each_segment(p, u, SegmentRecorder{out, max_segments, &n, u});
+  return n;
+}
+
 int32_t td_scatter_tile_owner(int32_t tile, int32_t M, int32_t N, int32_t world, int32_t rank, int32_t* m_blk_out, int32_t* n_blk_out) {
   // host arithmetic only (no device needed): the same tile_coords() the kernel runs, with the raster launch_dw_gemm sets up
   if (M <= 0 || N <= 0 || world < 1 || world > kMaxPeers || M % world || (M / world) % 32 || rank >= world) return -1;
