@@ -46,14 +46,18 @@ def main():
             buf = io.BytesIO()
             torch.save(e.clone(), buf)
             pickles.append((buf.getvalue(), ids))
-    r = td.EmbedShardReader(path)
-    r.batch(0, B, bi, pin_memory=False)  # touch the pages
-    random.seed(0)
-    t0 = time.perf_counter()
-    rows = 0
-    for fb in r.batches(B, bi, pin_memory=False):
-        rows += fb.flat.shape[0]
-    t_flat = (time.perf_counter() - t0) / args.batches
+    by_threads = {}
+    for threads in (1, 2, 4, 8):
+        r = td.EmbedShardReader(path, copy_threads=threads)
+        r.batch(0, B, bi, pin_memory=False)  # touch the pages
+        random.seed(0)
+        t0 = time.perf_counter()
+        rows = 0
+        for fb in r.batches(B, bi, pin_memory=False):
+            rows += fb.flat.shape[0]
+        by_threads[threads] = (time.perf_counter() - t0) / args.batches
+        r.close()
+    t_flat = by_threads[1]
     random.seed(0)
     t0 = time.perf_counter()
     for b in range(args.batches):
@@ -67,7 +71,8 @@ def main():
     mb = rows / args.batches * C * 2 / 1e6
     res = {"batch": B, "width": C, "mean_source_MB_per_batch": mb, "flat_shard_ms_per_batch": t_flat * 1e3,
            "flat_shard_GBps": mb / 1e3 / t_flat, "reference_style_ms_per_batch": t_ref * 1e3, "speedup": t_ref / t_flat,
-           "cores_used": 1}
+           "cores_used": 1, "flat_shard_ms_per_batch_by_copy_threads": {str(k): v * 1e3 for k, v in by_threads.items()},
+           "host_cpus": len(os.sched_getaffinity(0))}
     print(json.dumps(res))
     if args.out:
         json.dump(res, open(args.out, "w"), indent=1)

@@ -102,3 +102,24 @@ def test_prefetched_batches_equal_plain_batches_in_order(tmp_path):
     with pytest.raises(KeyError):  # a broken build_info fails in the thread and is re-raised here
         list(r.batches_prefetched(4, {"random_split_output_embed": 1}, pin_memory=False))
     r.close()
+
+
+def test_threaded_slab_copy_is_bit_exact(tmp_path):
+    """A slab of >= 8 MB is copied by several threads over disjoint row ranges: same bytes as the single-threaded copy, for the
+    whole shard and for an unaligned sub-range."""
+    rng = np.random.RandomState(5)
+    path = str(tmp_path / "big.tdemb")
+    width, n = 1024, 40
+    with td.EmbedShardWriter(path, width=width) as w:
+        for i in range(n):
+            L = int(rng.randint(100, 200))
+            bits = rng.randint(0, 65536, size=(L, width)).astype(np.uint16)
+            w.add(torch.from_numpy(bits.view(np.int16)).view(torch.bfloat16), [i] * L)
+    bi = dict(use_output_embed=1, use_input_embed=0, random_split_output_embed=0, output_embed_max_len=1 << 30, input_embed_max_len=1 << 30)
+    one, many = td.EmbedShardReader(path, copy_threads=1), td.EmbedShardReader(path, copy_threads=5)
+    assert one.total_rows * width * 2 >= (8 << 20)
+    for lo, hi in ((0, n), (3, n - 2)):
+        a, b = one.batch(lo, hi, bi, pin_memory=False), many.batch(lo, hi, bi, pin_memory=False)
+        assert torch.equal(a.flat.view(torch.int16), b.flat.view(torch.int16)) and a.lens.tolist() == b.lens.tolist()
+    assert many._pool is not None and one._pool is None
+    one.close(), many.close()

@@ -94,7 +94,19 @@ class EmbedShardReader:
     """mmap view of a shard. ``batch(lo, hi, build_info)`` -> FlatBatch for samples [lo, hi) with the reference's kept-length
     rule (random split / fixed max; seed Python's ``random`` to replay the reference's split points)."""
 
-    def __init__(self, path: str):
+    def __init__(self, path: str, copy_threads: int | None = None):
+        """``copy_threads``: threads that share one batch's slab copy (default: up to 8, the CPUs this process may run on). One
+        core moves about 8 GB/s from the page cache into pinned memory -- 20 ms for a 160 MB batch, seven times the GPU step it
+        feeds; the copy is a plain memcpy of disjoint row ranges, which numpy runs without the GIL."""
+        import os
+
+        if copy_threads is None:
+            try:
+                copy_threads = min(8, len(os.sched_getaffinity(0)))
+            except (AttributeError, OSError):
+                copy_threads = min(8, os.cpu_count() or 1)
+        self.copy_threads = max(1, int(copy_threads))
+        self._pool = None
         self._f = open(path, "rb")
         self._mm = mmap.mmap(self._f.fileno(), 0, access=mmap.ACCESS_READ)
         for advice in (getattr(mmap, "MADV_POPULATE_READ", 22), getattr(mmap, "MADV_WILLNEED", 3)):
@@ -127,6 +139,23 @@ class EmbedShardReader:
         a = np.array(self.rows[self.row_start[i] : self.row_start[i + 1]])
         return torch.from_numpy(a.view(np.int16)).view(torch.bfloat16)
 
+    def _slab_copy(self, dst: np.ndarray, r0: int, r1: int):
+        """dst[:] = rows[r0:r1], split by rows over the reader's threads when the slab is large enough to pay for it."""
+        n = r1 - r0
+        t = self.copy_threads if n * self.width * 2 >= (8 << 20) else 1
+        if t <= 1:
+            dst[:] = self.rows[r0:r1]
+            return
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+
+            self._pool = ThreadPoolExecutor(max_workers=self.copy_threads, thread_name_prefix="td-shard-copy")
+        step = -(-n // t)
+        futs = [self._pool.submit(np.copyto, dst[a : min(n, a + step)], self.rows[r0 + a : r0 + min(n, a + step)])
+                for a in range(0, n, step)]
+        for f in futs:
+            f.result()
+
     def batch(self, lo: int, hi: int, build_info: dict, pin_memory: bool = True) -> FlatBatch:
         r0, r1 = int(self.row_start[lo]), int(self.row_start[hi])
         full_lens = self.lens[lo:hi].tolist()
@@ -151,13 +180,15 @@ class EmbedShardReader:
             if buf is None or buf.shape[0] < r1 - r0:
                 buf = self._pinned[slot] = torch.empty((max(r1 - r0, 1), self.width), dtype=torch.bfloat16).pin_memory()
             flat = buf[: r1 - r0]
-            flat.view(torch.int16).numpy().view(np.uint16)[:] = self.rows[r0:r1]  # one slab copy, page cache -> pinned
+            self._slab_copy(flat.view(torch.int16).numpy().view(np.uint16), r0, r1)  # one slab, page cache -> pinned
             self._reported[slot] = False
 
             def slot_cb(events, _slot=slot):
                 self._slot_events[_slot], self._reported[_slot] = list(events), True
         else:
-            flat = torch.from_numpy(np.array(self.rows[r0:r1]).view(np.int16)).view(torch.bfloat16)
+            host = np.empty((r1 - r0, self.width), dtype=np.uint16)
+            self._slab_copy(host, r0, r1)
+            flat = torch.from_numpy(host.view(np.int16)).view(torch.bfloat16)
         start = torch.from_numpy((self.row_start[lo:hi] - r0).astype(np.int64))
         if build_info.get("random_split_output_embed"):
             out_ids = [self.token_ids(i)[n:].tolist() for i, n in zip(range(lo, hi), lens)]
@@ -222,6 +253,9 @@ class EmbedShardReader:
             th.join(timeout=5)
 
     def close(self):
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
         self.rows = self.lens = self.ids_index = self.ids = None
         try:
             self._mm.close()
