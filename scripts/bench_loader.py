@@ -46,16 +46,28 @@ def main():
             buf = io.BytesIO()
             torch.save(e.clone(), buf)
             pickles.append((buf.getvalue(), ids))
-    by_threads = {}
-    for threads in (1, 2, 4, 8):
-        r = td.EmbedShardReader(path, copy_threads=threads)
+    by_threads, slab_prefaulted = {}, {}
+    for threads, bound in ((1, True), (2, True), (4, True), (8, True), (8, False)):
+        r = td.EmbedShardReader(path, copy_threads=threads, pin_copy_threads=bound)
         r.batch(0, B, bi, pin_memory=False)  # touch the pages
-        random.seed(0)
-        t0 = time.perf_counter()
-        rows = 0
-        for fb in r.batches(B, bi, pin_memory=False):
-            rows += fb.flat.shape[0]
-        by_threads[threads] = (time.perf_counter() - t0) / args.batches
+        if bound:
+            random.seed(0)
+            t0 = time.perf_counter()
+            rows = 0
+            for fb in r.batches(B, bi, pin_memory=False):
+                rows += fb.flat.shape[0]
+            by_threads[threads] = (time.perf_counter() - t0) / args.batches
+        # the slab copy alone into a PRE-FAULTED destination -- what the pinned ring of the GPU path is (batches() above
+        # allocates a fresh pageable buffer per batch, so its time includes ~14 k first-touch faults per batch)
+        r1 = int(r.row_start[B])
+        dst = np.empty((r1, C), dtype=np.uint16)
+        dst[:] = 0
+        ts = []
+        for _ in range(12):
+            t0 = time.perf_counter()
+            r._slab_copy(dst, 0, r1)
+            ts.append(time.perf_counter() - t0)
+        slab_prefaulted[f"{threads}{'' if bound else '_unbound'}"] = {"first_ms": ts[0] * 1e3, "median_ms": sorted(ts)[len(ts) // 2] * 1e3}
         r.close()
     t_flat = by_threads[1]
     random.seed(0)
@@ -72,6 +84,7 @@ def main():
     res = {"batch": B, "width": C, "mean_source_MB_per_batch": mb, "flat_shard_ms_per_batch": t_flat * 1e3,
            "flat_shard_GBps": mb / 1e3 / t_flat, "reference_style_ms_per_batch": t_ref * 1e3, "speedup": t_ref / t_flat,
            "cores_used": 1, "flat_shard_ms_per_batch_by_copy_threads": {str(k): v * 1e3 for k, v in by_threads.items()},
+           "slab_copy_into_prefaulted_buffer_by_copy_threads": slab_prefaulted,
            "host_cpus": len(os.sched_getaffinity(0))}
     print(json.dumps(res))
     if args.out:

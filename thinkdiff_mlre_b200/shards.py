@@ -23,6 +23,7 @@ from __future__ import annotations
 import json
 import mmap
 import struct
+import threading
 
 import numpy as np
 import torch
@@ -94,19 +95,26 @@ class EmbedShardReader:
     """mmap view of a shard. ``batch(lo, hi, build_info)`` -> FlatBatch for samples [lo, hi) with the reference's kept-length
     rule (random split / fixed max; seed Python's ``random`` to replay the reference's split points)."""
 
-    def __init__(self, path: str, copy_threads: int | None = None):
-        """``copy_threads``: threads that share one batch's slab copy (default: up to 8, the CPUs this process may run on). One
-        core moves about 8 GB/s from the page cache into pinned memory -- 20 ms for a 160 MB batch, seven times the GPU step it
-        feeds; the copy is a plain memcpy of disjoint row ranges, which numpy runs without the GIL."""
+    def __init__(self, path: str, copy_threads: int | None = None, pin_copy_threads: bool = True):
+        """``copy_threads``: threads that share one batch's slab copy (default: up to 8 of the CPUs this process may run on). One
+        core moves 5-8 GB/s from the page cache into pinned memory -- 20 ms for a 140 MB batch, many times the GPU step it
+        feeds; the copy is a plain memcpy of disjoint row ranges, which numpy runs without the GIL.
+        ``pin_copy_threads``: bind every copy thread to its own CPU. Left to the scheduler, threads woken by the same waker for
+        a few milliseconds of work stay stacked on the waker's CPU and the threaded copy runs at one core's speed (measured: 140 MB
+        into a pre-faulted buffer, 8 threads: 22-26 ms unbound for the first ~50 calls, 3-4 ms bound from the first call; on a
+        B200 box the unbound pool was no faster than one thread -- profiles/r02_bench_n1_from_shards_threaded_copy.json)."""
         import os
 
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            cpus = list(range(os.cpu_count() or 1))
         if copy_threads is None:
-            try:
-                copy_threads = min(8, len(os.sched_getaffinity(0)))
-            except (AttributeError, OSError):
-                copy_threads = min(8, os.cpu_count() or 1)
+            copy_threads = min(8, len(cpus))
         self.copy_threads = max(1, int(copy_threads))
-        self._pool = None
+        # evenly spaced over the allowed CPUs (neighbouring numbers are often SMT siblings of one core)
+        self._copy_cpus = [cpus[(i * len(cpus)) // self.copy_threads] for i in range(self.copy_threads)] if pin_copy_threads and len(cpus) >= self.copy_threads else None
+        self._pool, self._bound, self._bind_lock = None, 0, threading.Lock()
         self._f = open(path, "rb")
         self._mm = mmap.mmap(self._f.fileno(), 0, access=mmap.ACCESS_READ)
         for advice in (getattr(mmap, "MADV_POPULATE_READ", 22), getattr(mmap, "MADV_WILLNEED", 3)):
@@ -139,6 +147,19 @@ class EmbedShardReader:
         a = np.array(self.rows[self.row_start[i] : self.row_start[i + 1]])
         return torch.from_numpy(a.view(np.int16)).view(torch.bfloat16)
 
+    def _bind_copy_thread(self):
+        """Initializer of a copy-pool thread: take the next CPU of ``_copy_cpus`` for this thread alone."""
+        import os
+
+        if self._copy_cpus is None:
+            return
+        with self._bind_lock:
+            i, self._bound = self._bound, self._bound + 1
+        try:
+            os.sched_setaffinity(threading.get_native_id(), {self._copy_cpus[i % len(self._copy_cpus)]})
+        except (AttributeError, OSError):  # not Linux / CPU taken away meanwhile: the thread stays where the scheduler puts it
+            pass
+
     def _slab_copy(self, dst: np.ndarray, r0: int, r1: int):
         """dst[:] = rows[r0:r1], split by rows over the reader's threads when the slab is large enough to pay for it."""
         n = r1 - r0
@@ -149,7 +170,7 @@ class EmbedShardReader:
         if self._pool is None:
             from concurrent.futures import ThreadPoolExecutor
 
-            self._pool = ThreadPoolExecutor(max_workers=self.copy_threads, thread_name_prefix="td-shard-copy")
+            self._pool = ThreadPoolExecutor(max_workers=self.copy_threads, thread_name_prefix="td-shard-copy", initializer=self._bind_copy_thread)
         step = -(-n // t)
         futs = [self._pool.submit(np.copyto, dst[a : min(n, a + step)], self.rows[r0 + a : r0 + min(n, a + step)])
                 for a in range(0, n, step)]
@@ -216,7 +237,6 @@ class EmbedShardReader:
         the only caller of ``random`` while it runs). ``depth`` stays below the pinned ring's three slots, so a slot is never
         refilled while the consumer may still hold the batch that lives in it."""
         import queue
-        import threading
 
         depth = max(1, min(int(depth), 2))
         q: queue.Queue = queue.Queue(maxsize=depth)
