@@ -123,3 +123,104 @@ def test_threaded_slab_copy_is_bit_exact(tmp_path):
         assert torch.equal(a.flat.view(torch.int16), b.flat.view(torch.int16)) and a.lens.tolist() == b.lens.tolist()
     assert many._pool is not None and one._pool is None
     one.close(), many.close()
+
+
+def _write_wds_tar(path, samples, with_image=True):
+    """A shard as the reference's pre-compute task writes it through wds.ShardWriter (image_text_process_data.py:104-118): per
+    sample the members <key>.jpg, <key>.json and one <key>.<flattened name>.pth per tensor, each tensor pickled by torch.save."""
+    import io
+    import json
+    import tarfile
+
+    with tarfile.open(path, "w") as tf:
+        for s in samples:
+            fields = {}
+            if with_image:
+                fields["jpg"] = b"\xff\xd8not a real jpeg\xff\xd9"  # never decoded by the converter
+            fields["json"] = json.dumps(s["json"]).encode("utf-8")
+            for k, v in s.items():
+                if k.endswith(".pth"):
+                    buf = io.BytesIO()
+                    torch.save(v.clone(), buf)
+                    fields[k] = buf.getvalue()
+            for ext, blob in fields.items():
+                ti = tarfile.TarInfo(f"{s['__key__']}.{ext}")
+                ti.size = len(blob)
+                tf.addfile(ti, io.BytesIO(blob))
+
+
+@pytest.mark.parametrize("name", ["collater_random_split.npz", "collater_fixed_max.npz"])
+def test_converted_webdataset_shards_reproduce_the_reference_collater(tmp_path, name):
+    """Reference tar shards -> convert_webdataset_shards -> EmbedShardReader.batch == the reference collater's golden output on
+    the same samples, for both embed streams; the samples are spread over two tars and carry the pass-through json fields."""
+    g = load_golden(name)
+    samples = _golden_samples(g)
+    for i, s in enumerate(samples):
+        s["json"]["gpt"] = f"gpt {i}"
+        s["json"]["revised_generated_text"] = f"revised {i}"
+        s["model.norm.input_embed.pth"] = s["model.norm.input_embed.pth"][: max(1, s["model.norm.input_embed.pth"].shape[0] // 2)].clone()
+        s["__key__"] = f"train/{i:06d}"
+    half = len(samples) // 2
+    tars = [str(tmp_path / "00000.tar"), str(tmp_path / "00001.tar")]
+    _write_wds_tar(tars[0], samples[:half])
+    _write_wds_tar(tars[1], samples[half:], with_image=False)
+    decoded = list(td.iter_webdataset_samples(tars))
+    assert [d["__key__"] for d in decoded] == [s["__key__"] for s in samples]
+    assert all("jpg" not in d and d["json"] == s["json"] for d, s in zip(decoded, samples))
+    paths = td.convert_webdataset_shards(tars, str(tmp_path / "flat"))
+    assert sorted(paths) == ["input", "output"]
+    bi = {k[3:]: int(v) for k, v in g.items() if k.startswith("bi_")}
+    r = td.EmbedShardReader(paths["output"])
+    random.seed(int(g["seed"]))
+    fb = r.batch(0, len(samples), bi, pin_memory=False)
+    bits = fb.flat.view(torch.int16).numpy().view(np.uint16)
+    packed, cu = pack_ref.pack_from_flat(bits, fb.src_row_start.tolist(), fb.lens.tolist())
+    padded, mask = pack_ref.unpack_padded(packed, cu, fb.l_max)
+    np.testing.assert_array_equal(padded, g["out_embed_bits"])
+    np.testing.assert_array_equal(mask, g["out_mask"])
+    assert fb.extras["llava_gpts"] == [f"gpt {i}" for i in range(len(samples))]
+    assert fb.extras["revised_generated_texts"] == [f"revised {i}" for i in range(len(samples))]
+    assert r._meta["keys"] == [s["__key__"] for s in samples]
+    r.close()
+    ri = td.EmbedShardReader(paths["input"])
+    for i, s in enumerate(samples):
+        assert torch.equal(ri.embedding(i).view(torch.int16), s["model.norm.input_embed.pth"].view(torch.int16))
+    ri.close()
+    # the same batch through the worker-side collater on the decoded dicts (the other way into the device pack)
+    random.seed(int(g["seed"]))
+    fc = td.FlatCollater(dict(bi, use_output_embed=1, use_input_embed=0), pin_memory=False, which="output")(decoded)
+    assert fc.lens.tolist() == fb.lens.tolist() and torch.equal(fc.flat.view(torch.int16), fb.flat.view(torch.int16))
+
+
+def test_converter_errors_and_passthrough_rule(tmp_path):
+    e = torch.zeros((3, 8), dtype=torch.bfloat16)
+    mk = lambda i, **js: {"__key__": f"k{i}", "json": dict({"generated_text": "t", "output_token_ids": [1, 2, 3]}, **js),  # noqa: E731
+                          "model.norm.output_embed.pth": e}
+    bi = dict(use_output_embed=1, use_input_embed=0, random_split_output_embed=0, output_embed_max_len=8, input_embed_max_len=8)
+    # the pass-through keys follow the batch's FIRST sample, as in the reference: absent there -> absent; present there but
+    # missing later -> KeyError (the reference indexes json["gpt"] of every sample)
+    tar = str(tmp_path / "a.tar")
+    _write_wds_tar(tar, [mk(0), mk(1, gpt="g1"), mk(2, gpt="g2")])
+    r = td.EmbedShardReader(td.convert_webdataset_shards(tar, str(tmp_path / "a"))["output"])
+    assert "llava_gpts" not in r.batch(0, 2, bi, pin_memory=False).extras
+    assert r.batch(1, 3, bi, pin_memory=False).extras["llava_gpts"] == ["g1", "g2"]
+    r.close()
+    _write_wds_tar(tar, [mk(0, gpt="g0"), mk(1)])
+    r = td.EmbedShardReader(td.convert_webdataset_shards(tar, str(tmp_path / "b"))["output"])
+    with pytest.raises(KeyError):
+        r.batch(0, 2, bi, pin_memory=False)
+    r.close()
+    # a stream that appears or disappears mid-way, a non-bf16 tensor, a tar without embeddings
+    s1 = mk(1)
+    s1["model.norm.input_embed.pth"] = e
+    _write_wds_tar(tar, [mk(0), s1])
+    with pytest.raises(ValueError, match="first one with a input_embed"):
+        td.convert_webdataset_shards(tar, str(tmp_path / "c"))
+    s0 = mk(0)
+    s0["model.norm.output_embed.pth"] = e.float()
+    _write_wds_tar(tar, [s0])
+    with pytest.raises(ValueError, match="bfloat16"):
+        td.convert_webdataset_shards(tar, str(tmp_path / "d"))
+    _write_wds_tar(tar, [{"__key__": "x", "json": {"generated_text": "", "output_token_ids": []}}])
+    with pytest.raises(ValueError, match="no sample"):
+        td.convert_webdataset_shards(tar, str(tmp_path / "e"))

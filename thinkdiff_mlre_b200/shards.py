@@ -15,7 +15,8 @@ slab of rows: ``EmbedShardReader.batch()`` copies it once into pinned memory and
     lens       int32 [n_samples]      full length L_i of every sample (rows)
     ids_index  int64 [n_samples + 1]  prefix offsets into ids
     ids        int32 [...]            output_token_ids of every sample, back to back
-    meta       u64 length + UTF-8 JSON {"generated_text": [...], "keys": [...]}
+    meta       u64 length + UTF-8 JSON {"generated_text": [...], "keys": [...]} (+ "gpt" / "revised_generated_text": [...] when the
+               samples carry those pass-through fields of the reference json, llava_instruct_dataset_mllama_embed_2.py:38-46)
     rows       bf16  [total_rows, width]
 """
 from __future__ import annotations
@@ -31,6 +32,8 @@ import torch
 from .pack import FlatBatch, kept_lengths
 
 MAGIC = b"TDEMB1\0\0"
+# json fields the reference collater passes through when the batch's first sample has them -> key of the collated dict
+PASSTHROUGH_JSON_KEYS = {"gpt": "llava_gpts", "revised_generated_text": "revised_generated_texts"}
 _HEADER = struct.Struct("<8sIIIIQQQQQQ")
 _ALIGN = 4096
 
@@ -45,8 +48,10 @@ class EmbedShardWriter:
     def __init__(self, path: str, width: int):
         self.path, self.width = path, int(width)
         self._rows, self._lens, self._ids, self._texts, self._keys = [], [], [], [], []
+        self._passthrough = {k: [] for k in PASSTHROUGH_JSON_KEYS}
 
-    def add(self, embed: torch.Tensor, token_ids, generated_text: str = "", key: str = ""):
+    def add(self, embed: torch.Tensor, token_ids, generated_text: str = "", key: str = "", passthrough: dict | None = None):
+        """``passthrough``: the sample's ``gpt`` / ``revised_generated_text`` json fields, when it has them (kept as they are)."""
         if embed.dtype != torch.bfloat16 or embed.dim() != 2 or embed.shape[1] != self.width:
             raise ValueError(f"expected a bfloat16 [L, {self.width}] embedding, got {embed.dtype} {tuple(embed.shape)}")
         self._rows.append(embed.contiguous().view(torch.int16).numpy().view(np.uint16))
@@ -54,12 +59,15 @@ class EmbedShardWriter:
         self._ids.append(np.asarray(token_ids, dtype=np.int32))
         self._texts.append(generated_text)
         self._keys.append(key)
+        for k, col in self._passthrough.items():
+            col.append((passthrough or {}).get(k))
 
     def add_reference_sample(self, sample: dict, which: str = "output"):
         """A sample dict as the reference's webdataset pipeline yields it (keys ``json``, ``*.{which}_embed.pth``)."""
         k = [k for k in sample if f"{which}_embed" in k][0]
         js = sample["json"]
-        self.add(sample[k], js["output_token_ids"], js.get("generated_text", ""), sample.get("__key__", ""))
+        self.add(sample[k], js["output_token_ids"], js.get("generated_text", ""), sample.get("__key__", ""),
+                 {p: js[p] for p in PASSTHROUGH_JSON_KEYS if p in js})
 
     def close(self):
         n = len(self._lens)
@@ -67,7 +75,9 @@ class EmbedShardWriter:
         ids_index = np.zeros(n + 1, dtype=np.int64)
         ids_index[1:] = np.cumsum([len(i) for i in self._ids])
         ids = np.concatenate(self._ids) if n else np.zeros(0, np.int32)
-        meta = json.dumps({"generated_text": self._texts, "keys": self._keys}).encode("utf-8")
+        meta = {"generated_text": self._texts, "keys": self._keys}
+        meta.update({k: col for k, col in self._passthrough.items() if any(v is not None for v in col)})
+        meta = json.dumps(meta).encode("utf-8")
         off_lens = _HEADER.size
         off_idx = off_lens + lens.nbytes
         off_ids = off_idx + ids_index.nbytes
@@ -218,6 +228,12 @@ class EmbedShardReader:
                        for i, L in zip(range(lo, hi), full_lens)]
         extras = {"generated_texts": self._meta["generated_text"][lo:hi], "output_token_ids": out_ids,
                   "embed_key": "model.norm.output_embed", "mask_key": "output_embed_mask"}
+        for k, out_key in PASSTHROUGH_JSON_KEYS.items():  # present iff the batch's FIRST sample has the field (reference :38-46)
+            col = self._meta.get(k)
+            if col is not None and col[lo] is not None:
+                if any(v is None for v in col[lo:hi]):
+                    raise KeyError(k)  # the reference indexes json[k] of every sample once the first one has it (:64-68)
+                extras[out_key] = col[lo:hi]
         if slot_cb is not None:
             extras["_h2d_enqueued"] = slot_cb
         return FlatBatch(flat, start, torch.tensor(lens, dtype=torch.int32), l_max, extras)
@@ -282,3 +298,103 @@ class EmbedShardReader:
         except BufferError:  # numpy views still alive somewhere; the OS reclaims the mapping at exit
             pass
         self._f.close()
+
+
+# ------------------------------------------------------------------------------------------ migration from the reference format
+def _split_wds_name(name: str):
+    """WebDataset's member-name rule: the sample key is the path up to the FIRST dot of the last path component, the field name
+    is everything after it (``dir/000123.model.norm.output_embed.pth`` -> ``("dir/000123", "model.norm.output_embed.pth")``)."""
+    head, _, tail = name.rpartition("/")
+    base, dot, ext = tail.partition(".")
+    if not dot or not base:
+        return None, None
+    return (head + "/" if head else "") + base, ext
+
+
+def iter_webdataset_samples(tar_paths, decode_images: bool = False):
+    """The samples of the reference's pre-computed shards, in file order, as the dicts its dataset yields: tar members grouped by
+    key (consecutive members of one sample, as ``wds.ShardWriter`` writes them, thinkdiff/tasks/image_text_process_data.py
+    :104-118), ``json`` decoded, every ``*.pth`` field ``torch.load``-ed. The ``jpg`` field is skipped unless ``decode_images``
+    (then left as raw bytes): the aligner path never looks at the image. Standard library ``tarfile`` only -- neither
+    ``webdataset`` nor PIL is needed to migrate."""
+    import io
+    import tarfile
+
+    def decode(key, fields):
+        out = {"__key__": key}
+        for ext, blob in fields.items():
+            if ext == "json":
+                out["json"] = json.loads(blob.decode("utf-8"))
+            elif ext.endswith(".pth") or ext == "pth":
+                out[ext] = torch.load(io.BytesIO(blob), map_location="cpu", weights_only=True)
+            else:
+                out[ext] = blob
+        return out
+
+    for path in ([tar_paths] if isinstance(tar_paths, (str, bytes)) or hasattr(tar_paths, "__fspath__") else tar_paths):
+        with tarfile.open(path, "r|*") as tf:  # streamed: shards are 500 MB and may be compressed
+            cur, fields = None, {}
+            for m in tf:
+                if not m.isfile():
+                    continue
+                key, ext = _split_wds_name(m.name)
+                if key is None:
+                    continue
+                if key != cur:
+                    if cur is not None:
+                        yield decode(cur, fields)
+                    cur, fields = key, {}
+                if ext.lower() in ("jpg", "jpeg", "png") and not decode_images:
+                    continue
+                fields[ext] = tf.extractfile(m).read()
+            if cur is not None:
+                yield decode(cur, fields)
+
+
+def convert_webdataset_shards(tar_paths, out_prefix: str, streams=("output", "input"), max_samples: int | None = None) -> dict:
+    """Rewrite the reference's WebDataset tar shards (per-sample pickled ``torch.save`` tensors + json,
+    thinkdiff/tasks/image_text_process_data.py:94-118) as flat shards: one ``<out_prefix>.<stream>.tdemb`` per embed stream
+    (``output`` = ``*output_embed*``, ``input`` = ``*input_embed*``; a stream no sample has is skipped). Embeddings are copied bit
+    for bit (they must be bfloat16 ``[L, C]``, as vLLM's hidden states are saved); token ids, generated text, the sample key and
+    the ``gpt`` / ``revised_generated_text`` fields travel in the shard's metadata. Returns ``{stream: path}``."""
+    writers, paths, n = {}, {}, 0
+    for sample in iter_webdataset_samples(tar_paths):
+        if max_samples is not None and n >= max_samples:
+            break
+        if "json" not in sample:
+            raise ValueError(f"sample {sample['__key__']!r} has no json member")
+        for which in streams:
+            ks = [k for k in sample if f"{which}_embed" in k]
+            if not ks:
+                if which in writers:
+                    raise ValueError(f"sample {sample['__key__']!r} lacks the {which}_embed field the earlier samples have")
+                continue
+            if which not in writers:
+                if n:
+                    raise ValueError(f"sample {sample['__key__']!r} is the first one with a {which}_embed field")
+                paths[which] = f"{out_prefix}.{which}.tdemb"
+                writers[which] = EmbedShardWriter(paths[which], int(sample[ks[0]].shape[-1]))
+            writers[which].add_reference_sample(sample, which)
+        n += 1
+    if not writers:
+        raise ValueError("no sample with an input_embed / output_embed field found")
+    for w in writers.values():
+        w.close()
+    return paths
+
+
+def _main(argv=None):
+    import argparse
+
+    ap = argparse.ArgumentParser(prog="scripts/convert_shards.py",
+                                 description="convert the reference's WebDataset embedding shards (.tar) to flat .tdemb shards")
+    ap.add_argument("tars", nargs="+")
+    ap.add_argument("--out", required=True, help="output prefix: writes <out>.output.tdemb and / or <out>.input.tdemb")
+    ap.add_argument("--streams", default="output,input")
+    ap.add_argument("--max-samples", type=int, default=None)
+    a = ap.parse_args(argv)
+    for which, path in convert_webdataset_shards(a.tars, a.out, tuple(x for x in a.streams.split(",") if x), a.max_samples).items():
+        r = EmbedShardReader(path)
+        print(f"{which}: {path}: {len(r)} samples, {r.total_rows} rows x {r.width}")
+        r.close()
+
