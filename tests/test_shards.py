@@ -122,6 +122,12 @@ def test_threaded_slab_copy_is_bit_exact(tmp_path):
         a, b = one.batch(lo, hi, bi, pin_memory=False), many.batch(lo, hi, bi, pin_memory=False)
         assert torch.equal(a.flat.view(torch.int16), b.flat.view(torch.int16)) and a.lens.tolist() == b.lens.tolist()
     assert many._pool is not None and one._pool is None
+    ids = rng.permutation(n).tolist()  # a shuffled batch: one row-range copy per sample, shared by the threads in runs of samples
+    for trunc in (False, True):
+        a, b = one.batch_indices(ids, dict(bi, output_embed_max_len=150), pin_memory=False, truncate_on_host=trunc), \
+            many.batch_indices(ids, dict(bi, output_embed_max_len=150), pin_memory=False, truncate_on_host=trunc)
+        assert a.flat.shape[0] * width * 2 >= (8 << 20)
+        assert torch.equal(a.flat.view(torch.int16), b.flat.view(torch.int16)) and a.src_row_start.tolist() == b.src_row_start.tolist()
     one.close(), many.close()
 
 
@@ -224,3 +230,163 @@ def test_converter_errors_and_passthrough_rule(tmp_path):
     _write_wds_tar(tar, [{"__key__": "x", "json": {"generated_text": "", "output_token_ids": []}}])
     with pytest.raises(ValueError, match="no sample"):
         td.convert_webdataset_shards(tar, str(tmp_path / "e"))
+
+
+def _small_shard(tmp_path, n=12, width=32, seed=9):
+    rng = np.random.RandomState(seed)
+    path = str(tmp_path / f"s{seed}.tdemb")
+    embeds = []
+    with td.EmbedShardWriter(path, width=width) as w:
+        for i in range(n):
+            L = int(rng.randint(3, 30))
+            bits = rng.randint(0, 65536, size=(L, width)).astype(np.uint16)
+            e = torch.from_numpy(bits.view(np.int16)).view(torch.bfloat16)
+            embeds.append(e)
+            w.add(e, list(range(100 * i, 100 * i + L)), f"t{i}", f"k{i}")
+    return path, embeds
+
+
+def test_batch_indices_any_order_and_truncate_on_host(tmp_path):
+    path, embeds = _small_shard(tmp_path)
+    r = td.EmbedShardReader(path)
+    bi = dict(use_output_embed=1, use_input_embed=0, random_split_output_embed=1, output_embed_max_split_len=10, output_embed_max_len=64,
+              input_embed_max_len=64)
+    ids = [7, 2, 2, 11, 0]
+    random.seed(5)
+    fb = r.batch_indices(ids, bi, pin_memory=False)
+    random.seed(5)
+    want_lens = [random.randint(1, min(embeds[i].shape[0] - 1, 10)) for i in ids]  # the reference's draw, in batch order
+    assert fb.lens.tolist() == want_lens and fb.l_max == max(want_lens) and fb.extras["sample_ids"] == ids
+    assert fb.extras["generated_texts"] == [f"t{i}" for i in ids]
+    assert fb.extras["output_token_ids"] == [list(range(100 * i + n, 100 * i + embeds[i].shape[0])) for i, n in zip(ids, want_lens)]
+    for j, i in enumerate(ids):
+        s0 = int(fb.src_row_start[j])
+        assert torch.equal(fb.flat[s0 : s0 + embeds[i].shape[0]].view(torch.int16), embeds[i].view(torch.int16))
+    # truncate_on_host: only the kept rows travel; packing either batch gives the same rows
+    random.seed(5)
+    ft = r.batch_indices(ids, bi, pin_memory=False, truncate_on_host=True)
+    assert ft.lens.tolist() == want_lens and ft.flat.shape[0] == sum(want_lens)
+    pa, _ = pack_ref.pack_from_flat(fb.flat.view(torch.int16).numpy(), fb.src_row_start.tolist(), fb.lens.tolist())
+    pb, _ = pack_ref.pack_from_flat(ft.flat.view(torch.int16).numpy(), ft.src_row_start.tolist(), ft.lens.tolist())
+    np.testing.assert_array_equal(pa, pb)
+    np.testing.assert_array_equal(pb, ft.flat.view(torch.int16).numpy())  # already packed
+    # a consecutive run equals batch(lo, hi)
+    fixed = dict(bi, random_split_output_embed=0, output_embed_max_len=12)
+    a, b = r.batch(3, 8, fixed, pin_memory=False), r.batch_indices([3, 4, 5, 6, 7], fixed, pin_memory=False)
+    assert torch.equal(a.flat.view(torch.int16), b.flat.view(torch.int16)) and a.lens.tolist() == b.lens.tolist() == [min(embeds[i].shape[0], 12) for i in range(3, 8)]
+    with pytest.raises(IndexError):
+        r.batch_indices([0, 12], bi, pin_memory=False)
+    with pytest.raises(ValueError):
+        r.batch_indices([], bi, pin_memory=False)
+    r.close()
+
+
+def test_pinned_ring_recycles_slots_only_after_their_h2d_events(tmp_path, monkeypatch):
+    """The pinned staging ring of the GPU path, driven on the CPU with stand-ins for pinning and CUDA events: a slot is refilled
+    only after the events its consumer reported have been waited for; a slot whose consumer never reported is dropped, not
+    overwritten; a reported slot keeps its buffer."""
+    path, embeds = _small_shard(tmp_path, n=16)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    r = td.EmbedShardReader(path)
+    bi = dict(use_output_embed=1, use_input_embed=0, random_split_output_embed=0, output_embed_max_len=64, input_embed_max_len=64)
+    waited = []
+
+    class Ev:
+        def __init__(self, tag):
+            self.tag = tag
+
+        def synchronize(self):
+            waited.append(self.tag)
+
+    seen = []
+    for j in range(7):
+        fb = r.batch(2 * j, 2 * j + 2, bi)
+        want = torch.cat([embeds[2 * j], embeds[2 * j + 1]])
+        assert torch.equal(fb.flat.view(torch.int16), want.view(torch.int16))
+        seen.append((fb.flat.data_ptr(), fb))  # keep every batch alive: a dropped buffer must not be recycled by the allocator
+        if j != 1:
+            fb.extras["_h2d_enqueued"]([Ev(j)])  # batch 1's consumer never reports
+        # slot of batch j is reused by batch j + 3: the events of batch j are waited for exactly then
+        assert waited == [k for k in range(j - 2) if k != 1], (j, waited)
+    ptr = [p for p, _ in seen]
+    assert ptr[3] == ptr[0] and ptr[6] == ptr[0]  # reported slot: same pinned buffer again
+    assert ptr[4] != ptr[1]                        # unreported slot: a fresh buffer, the old one left to its tensor
+    assert torch.equal(seen[1][1].flat.view(torch.int16), torch.cat([embeds[2], embeds[3]]).view(torch.int16))  # ... and intact
+    r.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_shard_set_epoch_plan_is_a_rank_partition_with_equal_batch_counts(tmp_path, world):
+    paths = [_small_shard(tmp_path, n=n, seed=s)[0] for n, s in ((37, 1), (16, 2), (64, 3))]
+    ss = td.EmbedShardSet(paths)
+    assert len(ss) == 117
+    bs = 2
+    plans = [ss.plan(bs, seed=7, epoch=3, rank=r, world=world) for r in range(world)]
+    assert len({len(p) for p in plans}) == 1                       # no rank runs dry before the others
+    assert [[si for si, _ in p] for p in plans] == [[si for si, _ in plans[0]]] * world  # same shard at the same step on all ranks
+    used = [(si, i) for p in plans for si, ids in p for i in ids]
+    assert len(used) == len(set(used))                             # a sample is used at most once per epoch, by one rank
+    assert all(len(ids) == bs for p in plans for _, ids in p)
+    per_shard = {si: len(ss.readers[si]) // world // bs * bs * world for si in range(3)}
+    assert len(used) == sum(per_shard.values())                    # only the remainders (< world * bs per shard) are dropped
+    assert ss.plan(bs, 7, 3, 0, world) == plans[0] and ss.plan(bs, 7, 4, 0, world) != plans[0]  # f(seed, epoch)
+    seq = [ss.plan(bs, rank=r, world=world, shuffle=False) for r in range(world)]
+    assert all(ids == list(range(ids[0], ids[0] + bs)) for p in seq for _, ids in p)  # unshuffled: consecutive ids (slab copies)
+    with pytest.raises(ValueError):
+        ss.plan(bs, rank=world, world=world)
+    ss.close()
+
+
+def test_shard_set_batches_are_bit_exact(tmp_path):
+    shards = [_small_shard(tmp_path, n=n, seed=s) for n, s in ((10, 4), (9, 5))]
+    ss = td.EmbedShardSet([p for p, _ in shards])
+    bi = dict(use_output_embed=1, use_input_embed=0, random_split_output_embed=0, output_embed_max_len=20, input_embed_max_len=20)
+    n = 0
+    for fb in ss.batches(3, bi, seed=1, epoch=0, rank=1, world=2, pin_memory=False, truncate_on_host=True):
+        embeds = shards[[p for p, _ in shards].index(fb.extras["shard"])][1]
+        for j, i in enumerate(fb.extras["sample_ids"]):
+            s0, k = int(fb.src_row_start[j]), int(fb.lens[j])
+            assert k == min(embeds[i].shape[0], fb.l_max) and torch.equal(fb.flat[s0 : s0 + k].view(torch.int16), embeds[i][:k].view(torch.int16))
+        n += 1
+    assert n == len(ss.plan(3, 1, 0, 1, 2)) == 2
+    ss.close()
+    w = td.EmbedShardWriter(str(tmp_path / "w8.tdemb"), width=8)
+    w.add(torch.zeros((2, 8), dtype=torch.bfloat16), [1, 2])
+    w.close()
+    with pytest.raises(ValueError, match="widths"):
+        td.EmbedShardSet([shards[0][0], str(tmp_path / "w8.tdemb")])
+
+
+def test_prefetch_ring_has_a_slot_for_every_live_batch(tmp_path, monkeypatch):
+    """batches_prefetched(depth=2) on the (mocked) pinned path: the consumer's batch, two queued ones and the one being filled
+    are four different ring slots -- the batch in the consumer's hands is never overwritten, and with every consumer reporting
+    its H2D events no slot is ever dropped (exactly depth + 2 buffers over the whole epoch)."""
+    import time
+
+    width, L, n = 16, 5, 40
+    path = str(tmp_path / "eq.tdemb")
+    rng = np.random.RandomState(0)
+    embeds = []
+    with td.EmbedShardWriter(path, width=width) as w:
+        for i in range(n):
+            e = torch.from_numpy(rng.randint(0, 65536, size=(L, width)).astype(np.uint16).view(np.int16)).view(torch.bfloat16)
+            embeds.append(e)
+            w.add(e, [i] * L)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+
+    class Ev:
+        def synchronize(self):
+            pass
+
+    bi = dict(use_output_embed=1, use_input_embed=0, random_split_output_embed=0, output_embed_max_len=64, input_embed_max_len=64)
+    ss = td.EmbedShardSet([path])
+    ptrs = set()
+    for j, fb in enumerate(ss.batches_prefetched(2, bi, depth=2, shuffle=False)):
+        fb.extras["_h2d_enqueued"]([Ev()])
+        ptrs.add(fb.flat.data_ptr())
+        time.sleep(0.002)  # let the producer run as far ahead as it is allowed to
+        assert torch.equal(fb.flat.view(torch.int16), torch.cat(embeds[2 * j : 2 * j + 2]).view(torch.int16)), j
+    assert j == n // 2 - 1 and len(ptrs) == 4
+    ss.close()

@@ -14,12 +14,12 @@ from .loss import frozen_linear, lm_head_cross_entropy, masked_cross_entropy, ma
 from .pack import FlatBatch, FlatCollater, PackedBatch, compose_image_text, kept_lengths, pack_batch, pack_device  # noqa: E402
 from .train_step import AlignerTrainStep, synthetic_lvlm_batch  # noqa: E402
 from .optim import DeviceGradScaler, FusedAdamW  # noqa: E402
-from .shards import EmbedShardReader, EmbedShardWriter, convert_webdataset_shards, iter_webdataset_samples  # noqa: E402
+from .shards import EmbedShardReader, EmbedShardSet, EmbedShardWriter, convert_webdataset_shards, iter_webdataset_samples  # noqa: E402
 from .lr_schedule import LinearWarmupCosineLRScheduler, LinearWarmupStepLRScheduler, get_lr_scheduler_class  # noqa: E402
 
 __all__ = [
     "ops", "ThinkDiffAligner", "build_vision_projector", "FUSED_TYPE", "masked_mse", "masked_cross_entropy", "lm_head_cross_entropy", "frozen_linear",
     "FlatBatch", "FlatCollater", "PackedBatch", "kept_lengths", "pack_batch", "pack_device", "compose_image_text", "AlignerTrainStep",
-    "synthetic_lvlm_batch", "FusedAdamW", "DeviceGradScaler", "EmbedShardReader", "EmbedShardWriter", "convert_webdataset_shards", "iter_webdataset_samples", "LinearWarmupCosineLRScheduler",
+    "synthetic_lvlm_batch", "FusedAdamW", "DeviceGradScaler", "EmbedShardReader", "EmbedShardSet", "EmbedShardWriter", "convert_webdataset_shards", "iter_webdataset_samples", "LinearWarmupCosineLRScheduler",
     "LinearWarmupStepLRScheduler", "get_lr_scheduler_class",
 ]

@@ -145,7 +145,7 @@ class EmbedShardReader:
         self.rows = np.frombuffer(self._mm, dtype=np.uint16, count=total * width, offset=off_rows).reshape(total, width)
         self.row_start = np.zeros(n + 1, dtype=np.int64)
         self.row_start[1:] = np.cumsum(self.lens)
-        self._pinned = None
+        self._pinned, self._nslots = None, 3
 
     def __len__(self):
         return self.n_samples
@@ -187,19 +187,51 @@ class EmbedShardReader:
         for f in futs:
             f.result()
 
-    def batch(self, lo: int, hi: int, build_info: dict, pin_memory: bool = True) -> FlatBatch:
-        r0, r1 = int(self.row_start[lo]), int(self.row_start[hi])
-        full_lens = self.lens[lo:hi].tolist()
-        lens, l_max = kept_lengths(full_lens, build_info, "output")
-        slot_cb = None
+    def _gather_copy(self, dst: np.ndarray, segs):
+        """dst[o : o + n] = rows[r : r + n] for every (o, r, n) of ``segs`` (disjoint), shared by the copy threads in runs of
+        consecutive segments with about equal row counts when there is enough to move."""
+        total = sum(n for _, _, n in segs)
+        t = self.copy_threads if total * self.width * 2 >= (8 << 20) else 1
+        if t <= 1 or len(segs) < 2:
+            if len(segs) == 1:
+                o, r, n = segs[0]
+                return self._slab_copy(dst[o : o + n], r, r + n)
+            for o, r, n in segs:
+                dst[o : o + n] = self.rows[r : r + n]
+            return
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+
+            self._pool = ThreadPoolExecutor(max_workers=self.copy_threads, thread_name_prefix="td-shard-copy", initializer=self._bind_copy_thread)
+
+        def run(group):
+            for o, r, n in group:
+                np.copyto(dst[o : o + n], self.rows[r : r + n])
+
+        groups, cur, acc, per = [], [], 0, -(-total // t)
+        for sg in segs:
+            cur.append(sg)
+            acc += sg[2]
+            if acc >= per:
+                groups.append(cur)
+                cur, acc = [], 0
+        if cur:
+            groups.append(cur)
+        for f in [self._pool.submit(run, g) for g in groups]:
+            f.result()
+
+    def _staging(self, rows: int, pin_memory: bool):
+        """Destination of one batch: (bf16 tensor [rows, width], its uint16 numpy view, callback for the H2D events or None)."""
         if pin_memory and torch.cuda.is_available():
-            # ring of 3 pinned staging buffers. A slot is refilled only after the H2D copies that read it have finished: whoever
+            # ring of pinned staging buffers (3, or prefetch depth + 2). A slot is refilled only after the H2D copies that read it have finished: whoever
             # enqueues those copies hands their CUDA events back through extras["_h2d_enqueued"] (AlignerTrainStep.prefetch /
             # step_host do), and the next use of the slot waits for them on the host. Without events (a consumer that never
             # reports) the slot's previous buffer is dropped instead of being overwritten.
             if self._pinned is None:
-                self._pinned, self._slot_events, self._reported, self._ring = [None, None, None], [None, None, None], [True, True, True], 0
-            self._ring = (self._ring + 1) % 3
+                self._pinned, self._slot_events, self._reported, self._ring = [], [], [], 0
+            while len(self._pinned) < self._nslots:  # (grown by batches_prefetched: depth + 2 batches are alive at once)
+                self._pinned.append(None), self._slot_events.append(None), self._reported.append(True)
+            self._ring = (self._ring + 1) % len(self._pinned)
             slot = self._ring
             if self._slot_events[slot] is not None:
                 for ev in self._slot_events[slot]:
@@ -208,35 +240,61 @@ class EmbedShardReader:
             elif not self._reported[slot]:
                 self._pinned[slot] = None  # copies of unknown state may still read the old buffer: leave it to its tensor
             buf = self._pinned[slot]
-            if buf is None or buf.shape[0] < r1 - r0:
-                buf = self._pinned[slot] = torch.empty((max(r1 - r0, 1), self.width), dtype=torch.bfloat16).pin_memory()
-            flat = buf[: r1 - r0]
-            self._slab_copy(flat.view(torch.int16).numpy().view(np.uint16), r0, r1)  # one slab, page cache -> pinned
+            if buf is None or buf.shape[0] < rows:
+                buf = self._pinned[slot] = torch.empty((max(rows, 1), self.width), dtype=torch.bfloat16).pin_memory()
+            flat = buf[:rows]
             self._reported[slot] = False
 
             def slot_cb(events, _slot=slot):
                 self._slot_events[_slot], self._reported[_slot] = list(events), True
+
+            return flat, flat.view(torch.int16).numpy().view(np.uint16), slot_cb
+        host = np.empty((rows, self.width), dtype=np.uint16)
+        return torch.from_numpy(host.view(np.int16)).view(torch.bfloat16), host, None
+
+    def batch(self, lo: int, hi: int, build_info: dict, pin_memory: bool = True, truncate_on_host: bool = False) -> FlatBatch:
+        """Samples [lo, hi): one contiguous slab of the shard."""
+        return self.batch_indices(range(lo, hi), build_info, pin_memory, truncate_on_host)
+
+    def batch_indices(self, ids, build_info: dict, pin_memory: bool = True, truncate_on_host: bool = False) -> FlatBatch:
+        """The batch made of samples ``ids`` in that order (any order, e.g. a shuffled sampler's): consecutive ids are one slab
+        copy, anything else one row-range copy per sample -- still no unpickling and no padding. ``truncate_on_host``: copy only
+        the rows the reference's rule keeps (``FlatCollater(truncate_on_host=True)``): fewer bytes into pinned memory and over
+        PCIe, the device pack then degenerates to a copy."""
+        ids = [int(i) for i in ids]
+        if not ids:
+            raise ValueError("empty batch")
+        if min(ids) < 0 or max(ids) >= self.n_samples:
+            raise IndexError(f"sample index outside [0, {self.n_samples})")
+        full_lens = [int(self.lens[i]) for i in ids]
+        lens, l_max = kept_lengths(full_lens, build_info, "output")  # draws the split points in batch order, like the reference
+        src_lens = lens if truncate_on_host else full_lens
+        contiguous = not truncate_on_host and all(b == a + 1 for a, b in zip(ids, ids[1:]))
+        start = np.zeros(len(ids), dtype=np.int64)
+        start[1:] = np.cumsum(src_lens[:-1])
+        rows = int(start[-1]) + src_lens[-1]
+        flat, dst, slot_cb = self._staging(rows, pin_memory)
+        if contiguous:
+            self._slab_copy(dst, int(self.row_start[ids[0]]), int(self.row_start[ids[-1] + 1]))  # one slab, page cache -> staging
         else:
-            host = np.empty((r1 - r0, self.width), dtype=np.uint16)
-            self._slab_copy(host, r0, r1)
-            flat = torch.from_numpy(host.view(np.int16)).view(torch.bfloat16)
-        start = torch.from_numpy((self.row_start[lo:hi] - r0).astype(np.int64))
+            self._gather_copy(dst, [(int(o), int(self.row_start[i]), int(n)) for o, i, n in zip(start, ids, src_lens) if n])
         if build_info.get("random_split_output_embed"):
-            out_ids = [self.token_ids(i)[n:].tolist() for i, n in zip(range(lo, hi), lens)]
+            out_ids = [self.token_ids(i)[n:].tolist() for i, n in zip(ids, lens)]
         else:
-            out_ids = [self.token_ids(i)[:l_max].tolist() if L > l_max else self.token_ids(i).tolist()
-                       for i, L in zip(range(lo, hi), full_lens)]
-        extras = {"generated_texts": self._meta["generated_text"][lo:hi], "output_token_ids": out_ids,
-                  "embed_key": "model.norm.output_embed", "mask_key": "output_embed_mask"}
+            out_ids = [self.token_ids(i)[:l_max].tolist() if L > l_max else self.token_ids(i).tolist() for i, L in zip(ids, full_lens)]
+        texts = self._meta["generated_text"]
+        extras = {"generated_texts": [texts[i] for i in ids], "output_token_ids": out_ids,
+                  "embed_key": "model.norm.output_embed", "mask_key": "output_embed_mask", "sample_ids": ids}
         for k, out_key in PASSTHROUGH_JSON_KEYS.items():  # present iff the batch's FIRST sample has the field (reference :38-46)
             col = self._meta.get(k)
-            if col is not None and col[lo] is not None:
-                if any(v is None for v in col[lo:hi]):
+            if col is not None and col[ids[0]] is not None:
+                vals = [col[i] for i in ids]
+                if any(v is None for v in vals):
                     raise KeyError(k)  # the reference indexes json[k] of every sample once the first one has it (:64-68)
-                extras[out_key] = col[lo:hi]
+                extras[out_key] = vals
         if slot_cb is not None:
             extras["_h2d_enqueued"] = slot_cb
-        return FlatBatch(flat, start, torch.tensor(lens, dtype=torch.int32), l_max, extras)
+        return FlatBatch(flat, torch.from_numpy(start), torch.tensor(lens, dtype=torch.int32), l_max, extras)
 
     def batches(self, batch_size: int, build_info: dict, drop_last: bool = True, pin_memory: bool = True):
         for lo in range(0, self.n_samples, batch_size):
@@ -250,43 +308,11 @@ class EmbedShardReader:
         page-cache -> pinned-memory memcpy of batch i+1 (numpy releases the GIL for it) overlaps the H2D and the training step of
         batch i -- what the reference gets from DataLoader workers + PrefetchLoader (thinkdiff/datasets/datasets/dataloader_utils.py
         :45-118), without worker processes or pickling. Same batches, same order, same split points as ``batches()`` (the thread is
-        the only caller of ``random`` while it runs). ``depth`` stays below the pinned ring's three slots, so a slot is never
-        refilled while the consumer may still hold the batch that lives in it."""
-        import queue
-
+        the only caller of ``random`` while it runs). The pinned ring is grown to ``depth + 2`` slots -- the batch the consumer
+        holds, ``depth`` queued ones and the one the thread is filling -- so a slot is never refilled while its batch is alive."""
         depth = max(1, min(int(depth), 2))
-        q: queue.Queue = queue.Queue(maxsize=depth)
-        stop = threading.Event()
-        done = object()
-
-        def produce():
-            try:
-                for b in self.batches(batch_size, build_info, drop_last, pin_memory):
-                    while not stop.is_set():
-                        try:
-                            q.put(b, timeout=0.1)
-                            break
-                        except queue.Full:
-                            continue
-                    if stop.is_set():
-                        return
-                q.put(done)
-            except BaseException as e:  # noqa: BLE001  (re-raised in the consumer)
-                q.put(e)
-
-        th = threading.Thread(target=produce, name="td-shard-prefetch", daemon=True)
-        th.start()
-        try:
-            while True:
-                item = q.get()
-                if item is done:
-                    return
-                if isinstance(item, BaseException):
-                    raise item
-                yield item
-        finally:
-            stop.set()
-            th.join(timeout=5)
+        self._nslots = max(self._nslots, depth + 2)
+        return _prefetched(lambda: self.batches(batch_size, build_info, drop_last, pin_memory), depth)
 
     def close(self):
         if self._pool is not None:
@@ -298,6 +324,104 @@ class EmbedShardReader:
         except BufferError:  # numpy views still alive somewhere; the OS reclaims the mapping at exit
             pass
         self._f.close()
+
+
+def _prefetched(make_iter, depth: int):
+    """Run ``make_iter()`` on a background thread, at most ``depth`` items ahead of the consumer. The thread stops when the
+    consumer abandons the generator; an exception inside it is re-raised in the consumer."""
+    import queue
+
+    q: queue.Queue = queue.Queue(maxsize=depth)
+    stop = threading.Event()
+    done = object()
+
+    def produce():
+        try:
+            for b in make_iter():
+                while not stop.is_set():
+                    try:
+                        q.put(b, timeout=0.1)
+                        break
+                    except queue.Full:
+                        continue
+                if stop.is_set():
+                    return
+            q.put(done)
+        except BaseException as e:  # noqa: BLE001  (re-raised in the consumer)
+            q.put(e)
+
+    th = threading.Thread(target=produce, name="td-shard-prefetch", daemon=True)
+    th.start()
+    try:
+        while True:
+            item = q.get()
+            if item is done:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+    finally:
+        stop.set()
+        th.join(timeout=5)
+
+
+class EmbedShardSet:
+    """Several flat shards as one training set: shuffled, rank-partitioned batches for data-parallel training.
+
+    Reference being replaced: ``wds.ResampledShards`` + ``wds.shuffle(1000)`` feeding a DataLoader with the dataset's collater
+    (thinkdiff/datasets/datasets/llava_instruct_dataset_mllama_embed_2.py:15-22, thinkdiff/runners/runner_clip_t5.py:71-79) --
+    shards drawn at random, samples mixed inside a 1000-sample buffer, every rank drawing on its own. Here an epoch is a
+    deterministic function of ``(seed, epoch)``: the shards are visited in a shuffled order, the samples of a shard are permuted,
+    and rank ``r`` of ``world`` takes every ``world``-th sample of that permutation, cut to the same count on every rank. Every
+    batch comes from one shard (the mixing radius of a 1000-sample buffer over 500 MB shards), every sample is used at most once
+    per epoch, and **all ranks yield the same number of batches** -- synchronous data parallel (and the peer exchange, which
+    needs every rank to keep stepping) never sees a rank run dry. ``shuffle=False`` walks the shards in order (consecutive
+    samples: one slab copy per batch)."""
+
+    def __init__(self, paths, copy_threads: int | None = None):
+        self.paths = [paths] if isinstance(paths, (str, bytes)) or hasattr(paths, "__fspath__") else list(paths)
+        if not self.paths:
+            raise ValueError("no shards")
+        self.readers = [EmbedShardReader(p, copy_threads) for p in self.paths]
+        if len({r.width for r in self.readers}) != 1:
+            raise ValueError("shards of different embedding widths: " + ", ".join(f"{p}: {r.width}" for p, r in zip(self.paths, self.readers)))
+        self.width = self.readers[0].width
+
+    def __len__(self):
+        return sum(len(r) for r in self.readers)
+
+    def plan(self, batch_size: int, seed: int = 0, epoch: int = 0, rank: int = 0, world: int = 1, shuffle: bool = True):
+        """[(shard index, [sample ids])] of one epoch for ``rank`` -- pure index arithmetic, identical code on every rank."""
+        if not 0 <= rank < world:
+            raise ValueError(f"rank {rank} outside world {world}")
+        rng = np.random.RandomState((int(seed) * 1000003 + int(epoch)) % (2**32))
+        order = rng.permutation(len(self.readers)) if shuffle else np.arange(len(self.readers))
+        out = []
+        for si in order.tolist():
+            n = len(self.readers[si])
+            perm = rng.permutation(n) if shuffle else np.arange(n)  # drawn on every rank: the streams stay in step
+            per_rank = n // world // batch_size * batch_size        # same count everywhere, whole batches only
+            mine = perm[rank::world][:per_rank] if shuffle else perm[rank * per_rank : (rank + 1) * per_rank]
+            out += [(si, mine[b : b + batch_size].tolist()) for b in range(0, per_rank, batch_size)]
+        return out
+
+    def batches(self, batch_size: int, build_info: dict, seed: int = 0, epoch: int = 0, rank: int = 0, world: int = 1,
+                shuffle: bool = True, pin_memory: bool = True, truncate_on_host: bool = False):
+        for si, ids in self.plan(batch_size, seed, epoch, rank, world, shuffle):
+            fb = self.readers[si].batch_indices(ids, build_info, pin_memory, truncate_on_host)
+            fb.extras["shard"] = self.paths[si]
+            yield fb
+
+    def batches_prefetched(self, batch_size: int, build_info: dict, depth: int = 2, **kw):
+        """``batches(...)`` produced by a background thread, ``depth`` (1 or 2) batches ahead (see EmbedShardReader.batches_prefetched)."""
+        depth = max(1, min(int(depth), 2))
+        for r in self.readers:
+            r._nslots = max(r._nslots, depth + 2)
+        return _prefetched(lambda: self.batches(batch_size, build_info, **kw), depth)
+
+    def close(self):
+        for r in self.readers:
+            r.close()
 
 
 # ------------------------------------------------------------------------------------------ migration from the reference format
