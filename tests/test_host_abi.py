@@ -216,3 +216,54 @@ def test_peer_fold_struct_matches_the_header_layout():
     assert C.sizeof(L.PeerFold) == 40
     assert L.PeerFold.signal_slot.offset == 8 and L.PeerFold.small_dst.offset == 16 and L.PeerFold.small_numel.offset == 32
 
+
+
+HOST_ONLY = {"td_last_error", "td_version", "td_device_check", "td_profile_enable", "td_profile_report", "td_profile_timeline",
+             "td_gemm_schedule", "td_scatter_tile_owner", "td_step_ctl_bytes", "td_gemm_workspace_bytes", "td_peer_free", "td_peer_close"}
+
+
+def test_every_device_entry_point_refuses_cleanly_without_a_gpu():
+    """No CPU path behind the C ABI: on a host without an sm_100 device every entry point that would enqueue device work returns
+    a negative status and leaves a message in td_last_error() -- with all-zero arguments, i.e. before touching a single pointer."""
+    import ctypes as C
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.lib()
+    called = 0
+    for name, (res, args) in _lib.SIGNATURES.items():
+        if name in HOST_ONLY or name.endswith("_bytes"):
+            continue
+        zero = []
+        for a in args:
+            if a in (C.c_void_p, C.c_char_p) or (isinstance(a, type) and issubclass(a, C._Pointer)):
+                zero.append(None)
+            elif a is C.c_float:
+                zero.append(0.0)
+            else:
+                zero.append(0)
+        rc = getattr(lib, name)(*zero)
+        assert rc < 0, f"{name} returned {rc} on a host without a GPU"
+        assert _lib.last_error(), name
+        called += 1
+    assert called >= 30
+
+
+def test_workspace_size_functions_are_pure_and_consistent():
+    """The *_bytes entry points are host arithmetic (callable anywhere): 256-byte aligned, monotone in M, and ordered the way the
+    calls nest (the fused MSE forward carves the plain forward's workspace plus its y buffer; the lm_head call carves a loss
+    workspace plus a GEMM workspace)."""
+    lib = _lib.lib()
+    din, d = 3584, 4096
+    prev = None
+    for m in (1, 255, 256, 8451, 65536):
+        f, b, mse = lib.td_aligner_fwd_workspace_bytes(m, din, d), lib.td_aligner_bwd_workspace_bytes(m, din, d), lib.td_aligner_mse_fwd_workspace_bytes(m, din, d)
+        assert f > 0 and b > 0 and f % 256 == 0 and b % 256 == 0
+        assert mse >= f + 2 * m * d
+        assert lib.td_rmsnorm_bwd_workspace_bytes(m, d) > 0 and lib.td_loss_workspace_bytes(m) > 0
+        assert lib.td_lm_head_ce_workspace_bytes(m) >= lib.td_loss_workspace_bytes(m) + lib.td_gemm_workspace_bytes()
+        assert lib.td_aligner_norm_partials_bytes(m, d) >= 2 * 4 * d  # at least one fp32 [dg | db2] partial row
+        if prev is not None:
+            assert f >= prev[0] and b >= prev[1] and mse >= prev[2]
+        prev = (f, b, mse)
+    assert lib.td_gemm_workspace_bytes() % 256 == 0 and lib.td_step_ctl_bytes() >= 32 and _lib.STEP_CTL_SCALE_OFFSET < lib.td_step_ctl_bytes()
