@@ -281,10 +281,7 @@ class FusedAdamW(torch.optim.Optimizer):
                     dist.all_gather_into_tensor(buf, st[k].contiguous(), group=dp.group)
                     full[k] = buf
                 st["_full"] = full
-        try:
-            sd = super().state_dict()
-        finally:
-            pass
+        sd = super().state_dict()
         # super() packed the per-parameter dicts by index: patch in full-shape moments, tensor steps, drop private keys
         packed = sd["state"]
         index = {}
