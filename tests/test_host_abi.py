@@ -267,3 +267,34 @@ def test_workspace_size_functions_are_pure_and_consistent():
             assert f >= prev[0] and b >= prev[1] and mse >= prev[2]
         prev = (f, b, mse)
     assert lib.td_gemm_workspace_bytes() % 256 == 0 and lib.td_step_ctl_bytes() >= 32 and _lib.STEP_CTL_SCALE_OFFSET < lib.td_step_ctl_bytes()
+
+
+class _ListDataset(torch.utils.data.Dataset):
+    def __init__(self, samples):
+        self.samples = samples
+
+    def __len__(self):
+        return len(self.samples)
+
+    def __getitem__(self, i):
+        return self.samples[i]
+
+
+def test_flat_collater_as_collate_fn_of_a_multiprocess_dataloader():
+    """The collater's seat in the reference (DataLoader(..., collate_fn=dataset.collater), runner_clip_t5.py:71-79): FlatCollater
+    runs inside worker PROCESSES (it never touches CUDA or the library's device calls) and its FlatBatch travels back to the
+    trainer intact -- same tensors, lengths and pass-through lists as collating in the main process."""
+    g = load_golden("collater_fixed_max.npz")
+    bi = {k[3:]: int(v) for k, v in g.items() if k.startswith("bi_")}
+    samples = _samples_from_golden(g)
+    for i, s in enumerate(samples):
+        s["json"]["gpt"] = f"g{i}"
+    coll = td.FlatCollater(bi, pin_memory=False, truncate_on_host=True)
+    want = [coll(samples[i : i + 3]) for i in range(0, len(samples) - len(samples) % 3, 3)]
+    loader = torch.utils.data.DataLoader(_ListDataset(samples), batch_size=3, shuffle=False, drop_last=True, num_workers=2, collate_fn=coll)
+    got = list(loader)
+    assert len(got) == len(want) >= 2
+    for a, b in zip(want, got):
+        assert isinstance(b, td.FlatBatch) and b.l_max == a.l_max and b.lens.tolist() == a.lens.tolist()
+        assert torch.equal(a.flat.view(torch.int16), b.flat.view(torch.int16)) and torch.equal(a.src_row_start, b.src_row_start)
+        assert a.extras["output_token_ids"] == b.extras["output_token_ids"] and a.extras["llava_gpts"] == b.extras["llava_gpts"]
