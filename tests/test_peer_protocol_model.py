@@ -198,7 +198,7 @@ def simulate(world, steps, seed, compute=compute_stream, update=update_stream):
     return mem
 
 
-@pytest.mark.parametrize("world", [1, 2, 3, 4])
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
 def test_no_hazard_and_no_deadlock_under_random_interleavings(world):
     for seed in range(150):
         mem = simulate(world, steps=4, seed=seed)
