@@ -97,3 +97,68 @@ def test_collater_fixed_max_equals_reference():
         padded_i, mask_i, _ = pack_ref.collate_padded(embeds, "fixed_max", max_len=cap - 2)
         assert np.array_equal(out["a.input_embed"].view(torch.int16).numpy().view(np.uint16), padded_i)
         assert np.array_equal(out["input_embed_mask"].numpy(), mask_i)
+
+
+@pytest.mark.parametrize("case", range(24))
+def test_product_collater_and_shard_reader_equal_the_live_reference_collater(case, tmp_path):
+    """Fuzz of the PRODUCT's host side of a-1 / f-2 against the reference collater executed live: random batch sizes, lengths,
+    widths and build_info (random split / fixed max, capped or not, one or both embed streams, pass-through json fields), through
+    FlatCollater (with and without host-side truncation) and through a flat shard + EmbedShardReader. The device pack is stood
+    in for by the numpy pack oracle (the GPU tests check the kernel against that same oracle bit for bit)."""
+    import thinkdiff_mlre_b200 as td
+
+    collater = ref_loader.load_collater()
+    rng = np.random.RandomState(1000 + case)
+    B, C = int(rng.randint(1, 9)), int(rng.choice([8, 24, 64]))
+    split = bool(case % 2)
+    lens = [int(v) for v in rng.randint(2, 70, size=B)]
+    both = case % 3 == 0
+    with_gpt, with_rev = bool(rng.randint(2)), bool(rng.randint(2))
+    samples = []
+    for i, L in enumerate(lens):
+        bits = rng.randint(0, 65536, size=(2, L, C)).astype(np.uint16)
+        bits[(bits & 0x7F80) == 0x7F80] = 0x3F80  # no NaN / inf patterns: the reference pads with F.pad on real bf16 values
+        eo, ei = (torch.from_numpy(b.view(np.int16)).view(torch.bfloat16) for b in bits)
+        js = {"generated_text": f"t{i}", "output_token_ids": [int(v) for v in rng.randint(0, 32000, size=L)]}
+        if with_gpt:
+            js["gpt"] = f"g{i}"
+        if with_rev:
+            js["revised_generated_text"] = f"r{i}"
+        samples.append({"__key__": f"k{i}", "json": js, "m.input_embed.pth": ei, "m.output_embed.pth": eo})
+    bi = dict(use_input_embed=both, use_output_embed=True, random_split_output_embed=split,
+              output_embed_max_split_len=int(rng.randint(1, 40)), output_embed_max_len=int(rng.randint(1, 90)),
+              input_embed_max_len=int(rng.randint(1, 90)))
+    random.seed(case)
+    ref = collater(bi, samples)
+
+    def padded_of(fb):
+        packed, cu = pack_ref.pack_from_flat(fb.flat.view(torch.int16).numpy().view(np.uint16), fb.src_row_start.tolist(), fb.lens.tolist())
+        return pack_ref.unpack_padded(packed, cu, fb.l_max)
+
+    def check(fb, key, mask_key):
+        padded, mask = padded_of(fb)
+        assert np.array_equal(ref[key].view(torch.int16).numpy().view(np.uint16), padded)
+        assert np.array_equal(ref[mask_key].numpy(), mask)
+
+    for trunc in (False, True):
+        random.seed(case)
+        fb = td.FlatCollater(bi, pin_memory=False, truncate_on_host=trunc)(samples)
+        check(fb, "m.output_embed", "output_embed_mask")
+        assert fb.extras["output_token_ids"] == ref["output_token_ids"] and fb.extras["generated_texts"] == ref["generated_texts"]
+        assert fb.extras.get("llava_gpts") == ref.get("llava_gpts") and fb.extras.get("revised_generated_texts") == ref.get("revised_generated_texts")
+        if both:
+            check(fb.extras["input_batch"], "m.input_embed", "input_embed_mask")
+        else:
+            assert "input_batch" not in fb.extras and "m.input_embed" not in ref
+    path = str(tmp_path / "s.tdemb")
+    with td.EmbedShardWriter(path, C) as w:
+        for s in samples:
+            w.add_reference_sample(s, "output")
+    r = td.EmbedShardReader(path)
+    for trunc in (False, True):
+        random.seed(case)
+        fb = r.batch(0, B, bi, pin_memory=False, truncate_on_host=trunc)
+        check(fb, "m.output_embed", "output_embed_mask")
+        assert fb.extras["output_token_ids"] == ref["output_token_ids"] and fb.extras.get("llava_gpts") == ref.get("llava_gpts")
+        assert fb.extras.get("revised_generated_texts") == ref.get("revised_generated_texts")
+    r.close()
