@@ -106,3 +106,28 @@ def load_lr_schedulers() -> dict:
     ns = {"math": math, "registry": _Registry}
     exec(compile(src, _OPTIMS_FILE, "exec"), ns)
     return registered
+
+
+_RUNNER_FILE = "thinkdiff/runners/runner_base.py"
+
+
+def build_reference_optimizer(model, init_lr: float, weight_decay: float, beta2: float | None = None):
+    """The reference runner's ``optimizer`` property (thinkdiff/runners/runner_base.py:98-127), exec'd from the source where it
+    lies against a stub runner holding ``model`` and the three ``run_cfg`` values it reads. Returns the ``torch.optim.AdamW``."""
+    import contextlib
+    import io
+    import logging
+
+    import torch
+
+    class _RunCfg(dict):
+        __getattr__ = dict.__getitem__
+
+    cfg = _RunCfg(init_lr=init_lr, weight_decay=weight_decay)
+    if beta2 is not None:
+        cfg["beta2"] = beta2
+    ns = {"torch": torch, "logging": logging}
+    exec(compile(_extract(_RUNNER_FILE, "optimizer", cls="RunnerBase"), _RUNNER_FILE, "exec"), ns)
+    runner = types.SimpleNamespace(model=model, config=types.SimpleNamespace(run_cfg=cfg), _optimizer=None)
+    with contextlib.redirect_stdout(io.StringIO()):  # the reference prints every parameter name
+        return ns["optimizer"](runner)

@@ -162,3 +162,35 @@ def test_product_collater_and_shard_reader_equal_the_live_reference_collater(cas
         assert fb.extras["output_token_ids"] == ref["output_token_ids"] and fb.extras.get("llava_gpts") == ref.get("llava_gpts")
         assert fb.extras.get("revised_generated_texts") == ref.get("revised_generated_texts")
     r.close()
+
+
+@pytest.mark.parametrize("beta2", [None, 0.98])
+def test_optimizer_groups_and_hyperparameters_equal_the_live_reference_runner(beta2):
+    """FusedAdamW / make_reference_optimizer build the parameter groups of the reference runner's own ``optimizer`` property
+    (runner_base.py:98-127, executed live on a model that holds the aligner as ``mm_projector`` next to a frozen weight):
+    same parameters per group, same weight decay, lr, betas and eps."""
+    import thinkdiff_mlre_b200 as td
+    from thinkdiff_mlre_b200.train_step import reference_param_groups
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.mm_projector = td.ThinkDiffAligner(64, 128)
+            self.frozen = torch.nn.Linear(4, 4)
+            for p in self.frozen.parameters():
+                p.requires_grad_(False)
+
+    model = Model()
+    ref = ref_loader.build_reference_optimizer(model, init_lr=3e-4, weight_decay=0.05, beta2=beta2)
+    assert type(ref) is torch.optim.AdamW
+    kw = {} if beta2 is None else {"betas": (0.9, beta2)}
+    mine = td.FusedAdamW(model.mm_projector, lr=3e-4, weight_decay=0.05, **kw)
+    plain = reference_param_groups(model, 0.05)
+    assert len(ref.param_groups) == len(mine.param_groups) == len(plain) == 2
+    for g_ref, g_mine, g_plain in zip(ref.param_groups, mine.param_groups, plain):
+        ids = [id(p) for p in g_ref["params"]]
+        assert ids == [id(p) for p in g_mine["params"]] == [id(p) for p in g_plain["params"]]
+        assert float(g_ref["weight_decay"]) == float(g_mine["weight_decay"]) == float(g_plain["weight_decay"])
+        for k in ("lr", "betas", "eps"):
+            assert tuple(g_ref[k]) == tuple(g_mine[k]) if k == "betas" else g_ref[k] == g_mine[k]
+    assert not any(id(p) in {id(q) for g in ref.param_groups for q in g["params"]} for p in model.frozen.parameters())
