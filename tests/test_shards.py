@@ -390,3 +390,30 @@ def test_prefetch_ring_has_a_slot_for_every_live_batch(tmp_path, monkeypatch):
         assert torch.equal(fb.flat.view(torch.int16), torch.cat(embeds[2 * j : 2 * j + 2]).view(torch.int16)), j
     assert j == n // 2 - 1 and len(ptrs) == 4
     ss.close()
+
+
+def test_pinned_ring_stops_repinning_on_ragged_batches(tmp_path, monkeypatch):
+    """Pinned buffers are sized for the largest batch seen so far plus 1/8: once every slot has been refilled after the largest
+    batch showed up, nothing is re-pinned any more (a re-pin is a cudaHostAlloc of the whole slab)."""
+    path, embeds = _small_shard(tmp_path, n=24, seed=21)
+    pins = []
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: (pins.append(self.shape[0]), self)[1])
+    r = td.EmbedShardReader(path)
+    bi = dict(use_output_embed=1, use_input_embed=0, random_split_output_embed=0, output_embed_max_len=64, input_embed_max_len=64)
+
+    class Ev:
+        def synchronize(self):
+            pass
+
+    for epoch in range(4):
+        if epoch == 2:
+            early = len(pins)
+        for j in range(8):
+            fb = r.batch(3 * j, 3 * j + 3, bi)
+            assert torch.equal(fb.flat.view(torch.int16), torch.cat(embeds[3 * j : 3 * j + 3]).view(torch.int16))
+            fb.extras["_h2d_enqueued"]([Ev()])
+    biggest = max(sum(e.shape[0] for e in embeds[3 * j : 3 * j + 3]) for j in range(8))
+    assert len(pins) == early <= 6                # every slot pinned at most twice, none of it after the slots have met the maximum
+    assert max(pins) <= biggest + (biggest >> 3)  # and never more than 1/8 above the largest batch
+    r.close()

@@ -145,7 +145,7 @@ class EmbedShardReader:
         self.rows = np.frombuffer(self._mm, dtype=np.uint16, count=total * width, offset=off_rows).reshape(total, width)
         self.row_start = np.zeros(n + 1, dtype=np.int64)
         self.row_start[1:] = np.cumsum(self.lens)
-        self._pinned, self._nslots = None, 3
+        self._pinned, self._nslots, self._max_rows = None, 3, 0
 
     def __len__(self):
         return self.n_samples
@@ -240,8 +240,12 @@ class EmbedShardReader:
             elif not self._reported[slot]:
                 self._pinned[slot] = None  # copies of unknown state may still read the old buffer: leave it to its tensor
             buf = self._pinned[slot]
+            self._max_rows = max(self._max_rows, rows, 1)
             if buf is None or buf.shape[0] < rows:
-                buf = self._pinned[slot] = torch.empty((max(rows, 1), self.width), dtype=torch.bfloat16).pin_memory()
+                # pinning is expensive (cudaHostAlloc: tens of ms for a 70 MB slab): size a new buffer for the largest batch any
+                # slot has seen plus 1/8, so that ragged batches stop re-pinning after the first few
+                cap = self._max_rows + (self._max_rows >> 3)
+                buf = self._pinned[slot] = torch.empty((cap, self.width), dtype=torch.bfloat16).pin_memory()
             flat = buf[:rows]
             self._reported[slot] = False
 
