@@ -291,7 +291,8 @@ def test_flat_collater_as_collate_fn_of_a_multiprocess_dataloader():
         s["json"]["gpt"] = f"g{i}"
     coll = td.FlatCollater(bi, pin_memory=False, truncate_on_host=True)
     want = [coll(samples[i : i + 3]) for i in range(0, len(samples) - len(samples) % 3, 3)]
-    loader = torch.utils.data.DataLoader(_ListDataset(samples), batch_size=3, shuffle=False, drop_last=True, num_workers=2, collate_fn=coll)
+    loader = torch.utils.data.DataLoader(_ListDataset(samples), batch_size=3, shuffle=False, drop_last=True, num_workers=2, collate_fn=coll,
+                                         multiprocessing_context="spawn", timeout=120)  # spawn: this process is multi-threaded by now
     got = list(loader)
     assert len(got) == len(want) >= 2
     for a, b in zip(want, got):
