@@ -178,7 +178,10 @@ def cpu_reference_run(steps: int, warmup: int, din: int, seqs: int, max_len: int
     from oracle import aligner_ref, pack_ref
 
     synth = load_synth()
-    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))  # the CPUs this process may actually run on (a cpuset can be narrower than the machine)
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     flat, start, lens_t, target = synth.lvlm_batch_tensors(seqs, max_len, din, D, seed=1234)
     lens, keep = lens_t.tolist(), 0
