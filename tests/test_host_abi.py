@@ -299,3 +299,43 @@ def test_flat_collater_as_collate_fn_of_a_multiprocess_dataloader():
         assert isinstance(b, td.FlatBatch) and b.l_max == a.l_max and b.lens.tolist() == a.lens.tolist()
         assert torch.equal(a.flat.view(torch.int16), b.flat.view(torch.int16)) and torch.equal(a.src_row_start, b.src_row_start)
         assert a.extras["output_token_ids"] == b.extras["output_token_ids"] and a.extras["llava_gpts"] == b.extras["llava_gpts"]
+
+
+def test_header_is_plain_c_and_a_c_program_links_the_library(tmp_path):
+    """The boundary is a C ABI: include/thinkdiff_b200.h compiles as C11 with -Wall -Werror -pedantic (no C++-isms, no torch or CUDA
+    headers), and a C program linked against libthinkdiff_b200.so calls through it -- here the host-only entry points and, without
+    a GPU, the refusal of a device entry point with its message."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "consumer.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "thinkdiff_b200.h"
+int main(void) {
+  int32_t plan[8];
+  td_peer_fold fold;
+  memset(&fold, 0, sizeof fold);
+  if (td_version() != 100) return 1;
+  if (td_aligner_fwd_workspace_bytes(8451, 3584, 4096) <= 0) return 2;
+  if (td_gemm_schedule(-1, 4096, 4096, 74, 1, plan, 8) >= 0) return 3;            /* bad argument: negative status */
+  if (td_scatter_tile_owner(0, 4096, 4096, 8, 0, &plan[0], &plan[1]) != 1) return 4;  /* rank 0 starts at owner 1 */
+  printf("device_check=%d msg=%s fold=%d\n", (int)td_device_check(), td_last_error(), (int)sizeof fold);
+  return 0;
+}
+''')
+    exe = tmp_path / "consumer"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = [gcc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", libdir, "-l:libthinkdiff_b200.so", f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "fold=" in r.stdout
+    if not torch.cuda.is_available():
+        assert "device_check=-" in r.stdout and ("sm_100" in r.stdout or "CUDA" in r.stdout)
