@@ -141,3 +141,68 @@ def test_bench_resolves_the_nvml_handle_by_uuid_not_by_index():
         assert bench.nvml_handle(fake, 3) == "H-index"
     finally:
         torch.cuda.get_device_properties = real
+
+
+def _sharded_checkpoint_worker(rank, world, init, ret):
+    dist.init_process_group("gloo", init_method=init, rank=rank, world_size=world)
+    try:
+        import thinkdiff_mlre_b200 as td
+
+        torch.manual_seed(0)
+        m = td.ThinkDiffAligner(DIN, D)
+        m.enable_data_parallel(defer_wait=True, sharded=True)
+        opt = td.FusedAdamW(m, lr=1e-3)
+        g = torch.Generator().manual_seed(5)  # the GLOBAL moments, identical on every rank; each rank keeps only its rows
+        full = {}
+        for name, p in m.named_parameters():
+            full[name] = (torch.randn(p.shape, generator=g), torch.rand(p.shape, generator=g))
+            ea, es = full[name]
+            if p.dim() == 2:
+                lo, hi = m._dp.shard_rows(p.shape[0])
+                opt.state[p] = {"exp_avg": ea[lo:hi].clone(), "exp_avg_sq": es[lo:hi].clone(), "shard_rows": (lo, hi), "step": 9}
+            else:
+                opt.state[p] = {"exp_avg": ea.clone(), "exp_avg_sq": es.clone(), "step": 9}
+        opt._t = 9
+        sd = opt.state_dict()  # collective: the row blocks are all-gathered
+        names = [n for n, _ in m.named_parameters()]
+        index = {id(p): i for i, p in enumerate(q for grp in opt.param_groups for q in grp["params"])}
+        gathered_ok = all(torch.equal(sd["state"][index[id(p)]]["exp_avg"], full[n][0]) and torch.equal(sd["state"][index[id(p)]]["exp_avg_sq"], full[n][1])
+                          and "shard_rows" not in sd["state"][index[id(p)]] for n, p in m.named_parameters())
+        still_sharded = all(opt.state[p]["exp_avg"].shape[0] == p.shape[0] // world for p in m.parameters() if p.dim() == 2)
+        # torch.optim.AdamW accepts it (what a single-GPU resume of the checkpoint would do)
+        plain = dict(sd)
+        plain.pop("fused_adamw_step")
+        from thinkdiff_mlre_b200.train_step import reference_param_groups
+
+        torch.optim.AdamW(reference_param_groups(m, 0.05), lr=1e-3).load_state_dict(plain)
+        # rank 0's checkpoint restored on EVERY rank (runner_base.py:662): each rank must end up with ITS rows, not rank 0's
+        box = [sd if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        m2 = td.ThinkDiffAligner(DIN, D)
+        m2.enable_data_parallel(defer_wait=True, sharded=True)
+        opt2 = td.FusedAdamW(m2, lr=1e-3)
+        opt2.load_state_dict(box[0])
+        resliced_ok = opt2._t == 9
+        for (n, p) in m2.named_parameters():
+            st = opt2.state[p]
+            if p.dim() == 2:
+                lo, hi = m2._dp.shard_rows(p.shape[0])
+                resliced_ok = resliced_ok and st["shard_rows"] == (lo, hi) and torch.equal(st["exp_avg"], full[n][0][lo:hi]) and torch.equal(st["exp_avg_sq"], full[n][1][lo:hi])
+            else:
+                resliced_ok = resliced_ok and torch.equal(st["exp_avg"], full[n][0])
+            resliced_ok = resliced_ok and st["step"] == 9
+        ret.put((rank, gathered_ok, still_sharded, resliced_ok, names))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_optimizer_checkpoint_gathers_full_moments_and_reslices_per_rank():
+    """in the sharded / peer modes a rank holds the AdamW moments of its own weight rows only. state_dict()
+    must return full-shape moments on every rank (collective all-gather) in torch.optim.AdamW's format, and rank 0's checkpoint
+    loaded on every rank (the reference's resume, runner_base.py:613 / :662) must leave each rank with the moments of ITS rows and
+    the step counter of the checkpoint."""
+    got = sorted(spawn_ranks(_sharded_checkpoint_worker, 2))
+    assert [g[0] for g in got] == [0, 1]
+    for rank, gathered_ok, still_sharded, resliced_ok, names in got:
+        assert gathered_ok and still_sharded and resliced_ok, (rank, gathered_ok, still_sharded, resliced_ok)
+        assert names == ["0.weight", "0.bias", "2.weight", "2.bias", "3.weight"]
