@@ -206,3 +206,33 @@ def test_sharded_optimizer_checkpoint_gathers_full_moments_and_reslices_per_rank
     for rank, gathered_ok, still_sharded, resliced_ok, names in got:
         assert gathered_ok and still_sharded and resliced_ok, (rank, gathered_ok, still_sharded, resliced_ok)
         assert names == ["0.weight", "0.bias", "2.weight", "2.bias", "3.weight"]
+
+
+def _row_gather_worker(rank, world, init, ret):
+    dist.init_process_group("gloo", init_method=init, rank=rank, world_size=world)
+    try:
+        import thinkdiff_mlre_b200 as td
+
+        torch.manual_seed(0)
+        m = td.ThinkDiffAligner(DIN, D)
+        m.enable_data_parallel(defer_wait=True, sharded=True)
+        want = {k: v.clone() for k, v in m.state_dict().items()}
+        # every rank is current on ITS rows only (what the row-sharded AdamW leaves behind); the other rows are stale
+        for w in (m[0].weight.data, m[2].weight.data):
+            lo, hi = m._dp.shard_rows(w.shape[0])
+            stale = torch.full_like(w, float("nan"))
+            stale[lo:hi] = w[lo:hi]
+            w.copy_(stale)
+        m.sync_parameters()  # collective, in place
+        ok = all(torch.equal(v, want[k]) for k, v in m.state_dict().items())
+        ret.put((rank, ok, m._dp.shard_rows(D)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sync_parameters_all_gathers_the_master_rows_in_place():
+    """Sharded data parallel: after the row-sharded updates each rank holds current fp32 master rows for its own block only;
+    sync_parameters() (called by AlignerTrainStep.flush() before a checkpoint) must rebuild the full matrices on every rank."""
+    got = sorted(spawn_ranks(_row_gather_worker, 2))
+    assert [(g[0], g[1]) for g in got] == [(0, True), (1, True)]
+    assert [g[2] for g in got] == [(0, D // 2), (D // 2, D)]
