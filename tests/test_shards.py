@@ -328,7 +328,7 @@ def test_shard_set_epoch_plan_is_a_rank_partition_with_equal_batch_counts(tmp_pa
     used = [(si, i) for p in plans for si, ids in p for i in ids]
     assert len(used) == len(set(used))                             # a sample is used at most once per epoch, by one rank
     assert all(len(ids) == bs for p in plans for _, ids in p)
-    per_shard = {si: len(ss.readers[si]) // world // bs * bs * world for si in range(3)}
+    per_shard = {si: ss.counts[si] // world // bs * bs * world for si in range(3)}
     assert len(used) == sum(per_shard.values())                    # only the remainders (< world * bs per shard) are dropped
     assert ss.plan(bs, 7, 3, 0, world) == plans[0] and ss.plan(bs, 7, 4, 0, world) != plans[0]  # f(seed, epoch)
     seq = [ss.plan(bs, rank=r, world=world, shuffle=False) for r in range(world)]
@@ -351,6 +351,15 @@ def test_shard_set_batches_are_bit_exact(tmp_path):
         n += 1
     assert n == len(ss.plan(3, 1, 0, 1, 2)) == 2
     ss.close()
+    # shards are opened on demand and at most max_open stay mapped; all of them stage through one pinned ring
+    lazy = td.EmbedShardSet([p for p, _ in shards], max_open=1)
+    assert lazy._open == {} and len(lazy) == 19
+    r0 = lazy.reader(0)
+    assert list(lazy._open) == [0] and lazy.reader(0) is r0
+    r1 = lazy.reader(1)
+    assert list(lazy._open) == [1] and r0.rows is None and r1._ring is lazy._ring  # shard 0 closed, same ring handed on
+    lazy.close()
+    assert lazy._open == {}
     w = td.EmbedShardWriter(str(tmp_path / "w8.tdemb"), width=8)
     w.add(torch.zeros((2, 8), dtype=torch.bfloat16), [1, 2])
     w.close()
@@ -418,3 +427,26 @@ def test_pinned_ring_stops_repinning_on_ragged_batches(tmp_path, monkeypatch):
     assert pins == sorted(pins)
     assert max(pins) <= biggest + (biggest >> 3)  # and never more than 1/8 above the largest batch
     r.close()
+
+
+def test_shard_set_opens_the_next_shard_ahead_and_keeps_two_open(tmp_path):
+    shards = [_small_shard(tmp_path, n=8, seed=30 + k) for k in range(4)]
+    ss = td.EmbedShardSet([p for p, _ in shards])
+    bi = dict(use_output_embed=1, use_input_embed=0, random_split_output_embed=0, output_embed_max_len=64, input_embed_max_len=64)
+    plan = ss.plan(4, seed=2, epoch=0)
+    order = [si for k, (si, _) in enumerate(plan) if k == 0 or plan[k - 1][0] != si]
+    assert sorted(order) == [0, 1, 2, 3]
+    seen = []
+    for k, fb in enumerate(ss.batches(4, bi, seed=2, epoch=0, pin_memory=False)):
+        si = plan[k][0]
+        embeds = shards[si][1]
+        for j, i in enumerate(fb.extras["sample_ids"]):
+            s0 = int(fb.src_row_start[j])
+            assert torch.equal(fb.flat[s0 : s0 + embeds[i].shape[0]].view(torch.int16), embeds[i].view(torch.int16))
+        ss._lookahead and ss._lookahead.join()
+        pos = order.index(si)
+        # this shard and the next one are open (after the last shard: its predecessor is simply not evicted), never more than two
+        assert set(order[pos : pos + 2]) <= set(ss._open) <= set(order[max(pos - 1, 0) : pos + 2]) and len(ss._open) <= 2, (k, list(ss._open))
+        seen.append(si)
+    assert len(seen) == len(plan) == 8
+    ss.close()

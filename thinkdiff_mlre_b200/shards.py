@@ -101,11 +101,49 @@ class EmbedShardWriter:
             self.close()
 
 
+class _PinnedRing:
+    """Ring of pinned staging buffers ``[rows, width]`` bf16 (3 slots, or prefetch depth + 2). A slot is refilled only after the H2D
+    copies that read it have finished: whoever enqueues those copies hands their CUDA events back through
+    ``extras["_h2d_enqueued"]`` (``AlignerTrainStep.prefetch`` / ``step_host`` / ``pack_batch`` do), and the next use of the slot
+    waits for them on the host. Without events (a consumer that never reports) the slot's previous buffer is dropped instead of
+    being overwritten. One ring can serve several readers of the same width (``EmbedShardSet``): switching shards re-pins nothing."""
+
+    def __init__(self, width: int, slots: int = 3):
+        self.width, self.nslots, self.max_rows = int(width), int(slots), 0
+        self.bufs, self.events, self.reported, self.pos = [], [], [], 0
+
+    def take(self, rows: int):
+        """(bf16 tensor [rows, width] in the next slot, callback that receives the H2D events of its consumer)."""
+        while len(self.bufs) < self.nslots:  # (grown by batches_prefetched: depth + 2 batches are alive at once)
+            self.bufs.append(None), self.events.append(None), self.reported.append(True)
+        self.pos = (self.pos + 1) % len(self.bufs)
+        slot = self.pos
+        if self.events[slot] is not None:
+            for ev in self.events[slot]:
+                ev.synchronize()
+            self.events[slot] = None
+        elif not self.reported[slot]:
+            self.bufs[slot] = None  # copies of unknown state may still read the old buffer: leave it to its tensor
+        buf = self.bufs[slot]
+        self.max_rows = max(self.max_rows, rows, 1)
+        if buf is None or buf.shape[0] < rows:
+            # pinning is expensive (cudaHostAlloc: tens of ms for a 70 MB slab): size a new buffer for the largest batch any
+            # slot has seen plus 1/8, so that ragged batches stop re-pinning after the first few
+            cap = self.max_rows + (self.max_rows >> 3)
+            buf = self.bufs[slot] = torch.empty((cap, self.width), dtype=torch.bfloat16).pin_memory()
+        self.reported[slot] = False
+
+        def slot_cb(events, _slot=slot):
+            self.events[_slot], self.reported[_slot] = list(events), True
+
+        return buf[:rows], slot_cb
+
+
 class EmbedShardReader:
     """mmap view of a shard. ``batch(lo, hi, build_info)`` -> FlatBatch for samples [lo, hi) with the reference's kept-length
     rule (random split / fixed max; seed Python's ``random`` to replay the reference's split points)."""
 
-    def __init__(self, path: str, copy_threads: int | None = None, pin_copy_threads: bool = True):
+    def __init__(self, path: str, copy_threads: int | None = None, pin_copy_threads: bool = True, ring: "_PinnedRing | None" = None):
         """``copy_threads``: threads that share one batch's slab copy (default: up to 8 of the CPUs this process may run on). One
         core moves 5-8 GB/s from the page cache into pinned memory -- 20 ms for a 140 MB batch, many times the GPU step it
         feeds; the copy is a plain memcpy of disjoint row ranges, which numpy runs without the GIL.
@@ -145,7 +183,7 @@ class EmbedShardReader:
         self.rows = np.frombuffer(self._mm, dtype=np.uint16, count=total * width, offset=off_rows).reshape(total, width)
         self.row_start = np.zeros(n + 1, dtype=np.int64)
         self.row_start[1:] = np.cumsum(self.lens)
-        self._pinned, self._nslots, self._max_rows = None, 3, 0
+        self._ring = ring  # pinned staging ring (created on first use; an EmbedShardSet shares one among its readers)
 
     def __len__(self):
         return self.n_samples
@@ -223,35 +261,9 @@ class EmbedShardReader:
     def _staging(self, rows: int, pin_memory: bool):
         """Destination of one batch: (bf16 tensor [rows, width], its uint16 numpy view, callback for the H2D events or None)."""
         if pin_memory and torch.cuda.is_available():
-            # ring of pinned staging buffers (3, or prefetch depth + 2). A slot is refilled only after the H2D copies that read it have finished: whoever
-            # enqueues those copies hands their CUDA events back through extras["_h2d_enqueued"] (AlignerTrainStep.prefetch /
-            # step_host do), and the next use of the slot waits for them on the host. Without events (a consumer that never
-            # reports) the slot's previous buffer is dropped instead of being overwritten.
-            if self._pinned is None:
-                self._pinned, self._slot_events, self._reported, self._ring = [], [], [], 0
-            while len(self._pinned) < self._nslots:  # (grown by batches_prefetched: depth + 2 batches are alive at once)
-                self._pinned.append(None), self._slot_events.append(None), self._reported.append(True)
-            self._ring = (self._ring + 1) % len(self._pinned)
-            slot = self._ring
-            if self._slot_events[slot] is not None:
-                for ev in self._slot_events[slot]:
-                    ev.synchronize()
-                self._slot_events[slot] = None
-            elif not self._reported[slot]:
-                self._pinned[slot] = None  # copies of unknown state may still read the old buffer: leave it to its tensor
-            buf = self._pinned[slot]
-            self._max_rows = max(self._max_rows, rows, 1)
-            if buf is None or buf.shape[0] < rows:
-                # pinning is expensive (cudaHostAlloc: tens of ms for a 70 MB slab): size a new buffer for the largest batch any
-                # slot has seen plus 1/8, so that ragged batches stop re-pinning after the first few
-                cap = self._max_rows + (self._max_rows >> 3)
-                buf = self._pinned[slot] = torch.empty((cap, self.width), dtype=torch.bfloat16).pin_memory()
-            flat = buf[:rows]
-            self._reported[slot] = False
-
-            def slot_cb(events, _slot=slot):
-                self._slot_events[_slot], self._reported[_slot] = list(events), True
-
+            if self._ring is None:
+                self._ring = _PinnedRing(self.width)
+            flat, slot_cb = self._ring.take(rows)
             return flat, flat.view(torch.int16).numpy().view(np.uint16), slot_cb
         host = np.empty((rows, self.width), dtype=np.uint16)
         return torch.from_numpy(host.view(np.int16)).view(torch.bfloat16), host, None
@@ -315,7 +327,9 @@ class EmbedShardReader:
         the only caller of ``random`` while it runs). The pinned ring is grown to ``depth + 2`` slots -- the batch the consumer
         holds, ``depth`` queued ones and the one the thread is filling -- so a slot is never refilled while its batch is alive."""
         depth = max(1, min(int(depth), 2))
-        self._nslots = max(self._nslots, depth + 2)
+        if self._ring is None:
+            self._ring = _PinnedRing(self.width)
+        self._ring.nslots = max(self._ring.nslots, depth + 2)
         return _prefetched(lambda: self.batches(batch_size, build_info, drop_last, pin_memory), depth)
 
     def close(self):
@@ -382,27 +396,54 @@ class EmbedShardSet:
     needs every rank to keep stepping) never sees a rank run dry. ``shuffle=False`` walks the shards in order (consecutive
     samples: one slab copy per batch)."""
 
-    def __init__(self, paths, copy_threads: int | None = None):
+    def __init__(self, paths, copy_threads: int | None = None, max_open: int = 2):
+        """Only the 64-byte headers are read here. A shard is opened (mmap + page-table pre-fault) when its first batch is built
+        and at most ``max_open`` shards stay open; all of them stage through ONE pinned ring, so walking through hundreds of
+        shards neither maps them all nor re-pins a buffer per shard."""
         self.paths = [paths] if isinstance(paths, (str, bytes)) or hasattr(paths, "__fspath__") else list(paths)
         if not self.paths:
             raise ValueError("no shards")
-        self.readers = [EmbedShardReader(p, copy_threads) for p in self.paths]
-        if len({r.width for r in self.readers}) != 1:
-            raise ValueError("shards of different embedding widths: " + ", ".join(f"{p}: {r.width}" for p, r in zip(self.paths, self.readers)))
-        self.width = self.readers[0].width
+        self.copy_threads, self.max_open = copy_threads, max(1, int(max_open))
+        self.counts, widths = [], []
+        for path in self.paths:
+            with open(path, "rb") as f:
+                head = f.read(_HEADER.size)
+            if len(head) < _HEADER.size:
+                raise ValueError(f"{path}: not a TDEMB1 bf16 shard")
+            magic, ver, dtype, width, n = _HEADER.unpack(head)[:5]
+            if magic != MAGIC or ver != 1 or dtype != 1:
+                raise ValueError(f"{path}: not a TDEMB1 bf16 shard")
+            self.counts.append(int(n)), widths.append(int(width))
+        if len(set(widths)) != 1:
+            raise ValueError("shards of different embedding widths: " + ", ".join(f"{p}: {w}" for p, w in zip(self.paths, widths)))
+        self.width = widths[0]
+        self._ring = _PinnedRing(self.width)
+        self._open = {}  # shard index -> reader, in least-recently-used order
+        self._lock, self._lookahead = threading.Lock(), None
 
     def __len__(self):
-        return sum(len(r) for r in self.readers)
+        return sum(self.counts)
+
+    def reader(self, si: int) -> EmbedShardReader:
+        """The (lazily opened) reader of shard ``si``; the least recently used one is closed when more than ``max_open`` are open."""
+        with self._lock:
+            r = self._open.pop(si, None)
+            if r is None:
+                while len(self._open) >= self.max_open:
+                    self._open.pop(next(iter(self._open))).close()
+                r = EmbedShardReader(self.paths[si], self.copy_threads, ring=self._ring)
+            self._open[si] = r
+            return r
 
     def plan(self, batch_size: int, seed: int = 0, epoch: int = 0, rank: int = 0, world: int = 1, shuffle: bool = True):
         """[(shard index, [sample ids])] of one epoch for ``rank`` -- pure index arithmetic, identical code on every rank."""
         if not 0 <= rank < world:
             raise ValueError(f"rank {rank} outside world {world}")
         rng = np.random.RandomState((int(seed) * 1000003 + int(epoch)) % (2**32))
-        order = rng.permutation(len(self.readers)) if shuffle else np.arange(len(self.readers))
+        order = rng.permutation(len(self.paths)) if shuffle else np.arange(len(self.paths))
         out = []
         for si in order.tolist():
-            n = len(self.readers[si])
+            n = self.counts[si]
             perm = rng.permutation(n) if shuffle else np.arange(n)  # drawn on every rank: the streams stay in step
             per_rank = n // world // batch_size * batch_size        # same count everywhere, whole batches only
             mine = perm[rank::world][:per_rank] if shuffle else perm[rank * per_rank : (rank + 1) * per_rank]
@@ -411,21 +452,38 @@ class EmbedShardSet:
 
     def batches(self, batch_size: int, build_info: dict, seed: int = 0, epoch: int = 0, rank: int = 0, world: int = 1,
                 shuffle: bool = True, pin_memory: bool = True, truncate_on_host: bool = False):
-        for si, ids in self.plan(batch_size, seed, epoch, rank, world, shuffle):
-            fb = self.readers[si].batch_indices(ids, build_info, pin_memory, truncate_on_host)
+        plan = self.plan(batch_size, seed, epoch, rank, world, shuffle)
+        shards = [si for k, (si, _) in enumerate(plan) if k == 0 or plan[k - 1][0] != si]  # in visiting order
+        cur = None
+        for si, ids in plan:
+            if si != cur:
+                cur = si
+                if self._lookahead is not None:
+                    self._lookahead.join()
+                r = self.reader(si)
+                nxt = shards[shards.index(si) + 1 : shards.index(si) + 2]
+                if nxt and self.max_open >= 2:
+                    # open (mmap + pre-fault = read from disk) the next shard while this one is being consumed
+                    self._lookahead = threading.Thread(target=self.reader, args=(nxt[0],), name="td-shard-open", daemon=True)
+                    self._lookahead.start()
+            fb = r.batch_indices(ids, build_info, pin_memory, truncate_on_host)
             fb.extras["shard"] = self.paths[si]
             yield fb
 
     def batches_prefetched(self, batch_size: int, build_info: dict, depth: int = 2, **kw):
         """``batches(...)`` produced by a background thread, ``depth`` (1 or 2) batches ahead (see EmbedShardReader.batches_prefetched)."""
         depth = max(1, min(int(depth), 2))
-        for r in self.readers:
-            r._nslots = max(r._nslots, depth + 2)
+        self._ring.nslots = max(self._ring.nslots, depth + 2)
         return _prefetched(lambda: self.batches(batch_size, build_info, **kw), depth)
 
     def close(self):
-        for r in self.readers:
-            r.close()
+        if self._lookahead is not None:
+            self._lookahead.join()
+            self._lookahead = None
+        with self._lock:
+            for r in self._open.values():
+                r.close()
+            self._open = {}
 
 
 # ------------------------------------------------------------------------------------------ migration from the reference format
