@@ -69,6 +69,17 @@ def main():
             ts.append(time.perf_counter() - t0)
         slab_prefaulted[f"{threads}{'' if bound else '_unbound'}"] = {"first_ms": ts[0] * 1e3, "median_ms": sorted(ts)[len(ts) // 2] * 1e3}
         r.close()
+    # shuffled epochs through EmbedShardSet: batches of arbitrary samples (one row-range copy per sample), with and without
+    # host-side truncation to the kept rows, into a pre-faulted buffer is not possible through the public API on a CPU-only host,
+    # so these include the fresh pageable destination like by_threads above
+    ss = td.EmbedShardSet([path])
+    shuffled = {}
+    for trunc in (False, True):
+        random.seed(0)
+        t0 = time.perf_counter()
+        nb = sum(1 for _ in ss.batches(B, bi, seed=1, epoch=0, pin_memory=False, truncate_on_host=trunc))
+        shuffled["kept_rows_only" if trunc else "full_samples"] = (time.perf_counter() - t0) / nb * 1e3
+    ss.close()
     t_flat = by_threads[1]
     random.seed(0)
     t0 = time.perf_counter()
@@ -85,6 +96,7 @@ def main():
            "flat_shard_GBps": mb / 1e3 / t_flat, "reference_style_ms_per_batch": t_ref * 1e3, "speedup": t_ref / t_flat,
            "cores_used": 1, "flat_shard_ms_per_batch_by_copy_threads": {str(k): v * 1e3 for k, v in by_threads.items()},
            "slab_copy_into_prefaulted_buffer_by_copy_threads": slab_prefaulted,
+           "shuffled_epoch_ms_per_batch": shuffled,
            "host_cpus": len(os.sched_getaffinity(0))}
     print(json.dumps(res))
     if args.out:
