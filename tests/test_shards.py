@@ -230,6 +230,23 @@ def test_converter_errors_and_passthrough_rule(tmp_path):
     _write_wds_tar(tar, [{"__key__": "x", "json": {"generated_text": "", "output_token_ids": []}}])
     with pytest.raises(ValueError, match="no sample"):
         td.convert_webdataset_shards(tar, str(tmp_path / "e"))
+    # a failed conversion leaves neither a half-written shard nor the writer's temporary rows file
+    import os
+
+    left = sorted(f for f in os.listdir(tmp_path) if f.startswith(("c.", "d.", "e.")) or f.endswith(".rows.tmp"))
+    assert left == [], left
+    # the writer as a context manager: an exception inside drops the shard, a closed writer refuses more samples
+    with pytest.raises(RuntimeError):
+        with td.EmbedShardWriter(str(tmp_path / "f.tdemb"), 8) as w:
+            w.add(e, [1, 2, 3])
+            raise RuntimeError("producer failed")
+    assert not os.path.exists(tmp_path / "f.tdemb") and not os.path.exists(str(tmp_path / "f.tdemb") + ".rows.tmp")
+    w = td.EmbedShardWriter(str(tmp_path / "g.tdemb"), 8)
+    w.add(e, [1, 2, 3])
+    w.close()
+    assert not os.path.exists(str(tmp_path / "g.tdemb") + ".rows.tmp") and w.close() == str(tmp_path / "g.tdemb")
+    with pytest.raises(ValueError, match="closed"):
+        w.add(e, [1, 2, 3])
 
 
 def _small_shard(tmp_path, n=12, width=32, seed=9):

@@ -43,18 +43,24 @@ def _align(n: int) -> int:
 
 
 class EmbedShardWriter:
-    """``add()`` samples, ``close()`` writes the shard. Embeddings are kept as raw 16-bit words (bit-exact)."""
+    """``add()`` samples, ``close()`` finishes the shard. Embeddings are kept as raw 16-bit words (bit-exact). The rows are
+    streamed to ``<path>.rows.tmp`` as they arrive (a 500 MB shard never sits in memory); ``close()`` writes the header, the
+    index and the metadata -- whose sizes are only known then -- and appends the rows behind them."""
 
     def __init__(self, path: str, width: int):
         self.path, self.width = path, int(width)
-        self._rows, self._lens, self._ids, self._texts, self._keys = [], [], [], [], []
+        self._lens, self._ids, self._texts, self._keys = [], [], [], []
         self._passthrough = {k: [] for k in PASSTHROUGH_JSON_KEYS}
+        self._rows_path = path + ".rows.tmp"
+        self._rows_file = open(self._rows_path, "wb")
 
     def add(self, embed: torch.Tensor, token_ids, generated_text: str = "", key: str = "", passthrough: dict | None = None):
         """``passthrough``: the sample's ``gpt`` / ``revised_generated_text`` json fields, when it has them (kept as they are)."""
         if embed.dtype != torch.bfloat16 or embed.dim() != 2 or embed.shape[1] != self.width:
             raise ValueError(f"expected a bfloat16 [L, {self.width}] embedding, got {embed.dtype} {tuple(embed.shape)}")
-        self._rows.append(embed.contiguous().view(torch.int16).numpy().view(np.uint16))
+        if self._rows_file is None:
+            raise ValueError("shard already closed")
+        self._rows_file.write(embed.contiguous().view(torch.int16).numpy().tobytes())
         self._lens.append(int(embed.shape[0]))
         self._ids.append(np.asarray(token_ids, dtype=np.int32))
         self._texts.append(generated_text)
@@ -84,14 +90,33 @@ class EmbedShardWriter:
         off_meta = off_ids + ids.nbytes
         off_rows = _align(off_meta + 8 + len(meta))
         total_rows = int(lens.sum())
-        with open(self.path, "wb") as f:
-            f.write(_HEADER.pack(MAGIC, 1, 1, self.width, n, total_rows, off_lens, off_idx, off_ids, off_meta, off_rows))
-            f.write(lens.tobytes()), f.write(ids_index.tobytes()), f.write(ids.tobytes())
-            f.write(struct.pack("<Q", len(meta))), f.write(meta)
-            f.write(b"\0" * (off_rows - f.tell()))
-            for r in self._rows:
-                f.write(r.tobytes())
+        if self._rows_file is None:
+            return self.path
+        self._rows_file.close()
+        self._rows_file = None
+        import os
+        import shutil
+
+        try:
+            with open(self.path, "wb") as f:
+                f.write(_HEADER.pack(MAGIC, 1, 1, self.width, n, total_rows, off_lens, off_idx, off_ids, off_meta, off_rows))
+                f.write(lens.tobytes()), f.write(ids_index.tobytes()), f.write(ids.tobytes())
+                f.write(struct.pack("<Q", len(meta))), f.write(meta)
+                f.write(b"\0" * (off_rows - f.tell()))
+                with open(self._rows_path, "rb") as rows:
+                    shutil.copyfileobj(rows, f, 16 << 20)
+        finally:
+            os.remove(self._rows_path)
         return self.path
+
+    def abort(self):
+        """Drop the partly written shard (the temporary rows file); nothing is left at ``path``."""
+        import os
+
+        if self._rows_file is not None:
+            self._rows_file.close()
+            self._rows_file = None
+            os.remove(self._rows_path)
 
     def __enter__(self):
         return self
@@ -99,6 +124,8 @@ class EmbedShardWriter:
     def __exit__(self, *exc):
         if exc[0] is None:
             self.close()
+        else:
+            self.abort()
 
 
 class _PinnedRing:
@@ -544,26 +571,31 @@ def convert_webdataset_shards(tar_paths, out_prefix: str, streams=("output", "in
     for bit (they must be bfloat16 ``[L, C]``, as vLLM's hidden states are saved); token ids, generated text, the sample key and
     the ``gpt`` / ``revised_generated_text`` fields travel in the shard's metadata. Returns ``{stream: path}``."""
     writers, paths, n = {}, {}, 0
-    for sample in iter_webdataset_samples(tar_paths):
-        if max_samples is not None and n >= max_samples:
-            break
-        if "json" not in sample:
-            raise ValueError(f"sample {sample['__key__']!r} has no json member")
-        for which in streams:
-            ks = [k for k in sample if f"{which}_embed" in k]
-            if not ks:
-                if which in writers:
-                    raise ValueError(f"sample {sample['__key__']!r} lacks the {which}_embed field the earlier samples have")
-                continue
-            if which not in writers:
-                if n:
-                    raise ValueError(f"sample {sample['__key__']!r} is the first one with a {which}_embed field")
-                paths[which] = f"{out_prefix}.{which}.tdemb"
-                writers[which] = EmbedShardWriter(paths[which], int(sample[ks[0]].shape[-1]))
-            writers[which].add_reference_sample(sample, which)
-        n += 1
-    if not writers:
-        raise ValueError("no sample with an input_embed / output_embed field found")
+    try:
+        for sample in iter_webdataset_samples(tar_paths):
+            if max_samples is not None and n >= max_samples:
+                break
+            if "json" not in sample:
+                raise ValueError(f"sample {sample['__key__']!r} has no json member")
+            for which in streams:
+                ks = [k for k in sample if f"{which}_embed" in k]
+                if not ks:
+                    if which in writers:
+                        raise ValueError(f"sample {sample['__key__']!r} lacks the {which}_embed field the earlier samples have")
+                    continue
+                if which not in writers:
+                    if n:
+                        raise ValueError(f"sample {sample['__key__']!r} is the first one with a {which}_embed field")
+                    paths[which] = f"{out_prefix}.{which}.tdemb"
+                    writers[which] = EmbedShardWriter(paths[which], int(sample[ks[0]].shape[-1]))
+                writers[which].add_reference_sample(sample, which)
+            n += 1
+        if not writers:
+            raise ValueError("no sample with an input_embed / output_embed field found")
+    except BaseException:
+        for w in writers.values():
+            w.abort()  # no half-written shard and no temporary rows file is left behind
+        raise
     for w in writers.values():
         w.close()
     return paths
