@@ -435,8 +435,9 @@ def e2e_from_shards(td, stepper, host_t, seqs, din, dev, steps, sync_all, max_ov
     """The host-fed step with its batches coming from disk: the synthetic samples are written once as two flat shards (features
     [*, din] and T5-space targets [*, D]; the on-disk format of thinkdiff_mlre_b200/shards.py that replaces the reference's
     pickled tensors in tar shards, thinkdiff/tasks/image_text_process_data.py:94-118), then every step reads its batch with
-    EmbedShardReader (one slab copy page cache -> pinned ring buffer), ships it and trains on it. The reader runs on this
-    process's main thread, so this number is bounded by one core's memcpy -- it is here to exercise the loader on the GPU path."""
+    EmbedShardReader (one slab copy page cache -> pinned ring buffer, shared by the reader's CPU-bound copy threads), ships it and
+    trains on it. The reader is called from this process's main thread between two steps (no background prefetch), so the loader's
+    time adds to the step -- it is here to exercise the loader on the GPU path, not to show its best case."""
     import tempfile
 
     import torch
@@ -488,7 +489,8 @@ def e2e_from_shards(td, stepper, host_t, seqs, din, dev, steps, sync_all, max_ov
     os.rmdir(tmp)
     return {"value": tokens / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "loader_ms_per_batch": load_s / max(steps - 1, 1) * 1e3,
             "wall_ms_per_step": (time.perf_counter() - t0) / steps * 1e3,
-            "note": "batches read from flat on-disk shards by EmbedShardReader on the main thread (one slab memcpy per tensor into a pinned ring, recycled on CUDA events)"}
+            "copy_threads": rf.copy_threads,
+            "note": "batches read from flat on-disk shards by EmbedShardReader, called from the main thread between steps (one slab copy per tensor into a pinned ring recycled on CUDA events, shared by `copy_threads` CPU-bound threads)"}
 
 
 # ----------------------------------------------------------------------------------------------- B200 arm
