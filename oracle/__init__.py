@@ -14,6 +14,10 @@ Contents
                  (reference: thinkdiff/datasets/datasets/llava_instruct_dataset_mllama_embed_2.py:34-185).
 ``loss_ref``     CrossEntropyLoss(ignore_index=-100) as used at ...embed_decoder_2.py:241-246, and the
                  masked MSE that BASELINE.json's north_star adds (not in the reference).
+``t5_head_ref``  frozen T5 output head + CE and the frozen bias-free Linear (...embed_decoder_2.py:231-246), f-1 first slice.
+``t5_decoder_ref`` the frozen T5 v1.1 decoder stack (third-party: transformers==4.46.1 modeling_t5.py) restated on PACKED
+                 aligner rows -- varlen cross-attention, relative position bias, gated GELU; pinned live against the installed
+                 transformers in tests/test_t5_decoder_oracle.py. No kernel consumes it yet (f-1 groundwork).
 ``ref_loader``   ast-extracts and exec's the reference's OWN functions from /root/reference (dev container only).
 ``make_golden``  regenerates tests/golden/*.npz by running the reference's own code (dev container only).
 
