@@ -535,6 +535,20 @@ def main():
         print(json.dumps(obj), flush=True)
         os.dup2(2, 1)
 
+    # Watchdog: a stream that waits on a peer counter (cuStreamWaitValue32 has no timeout) or a collective whose partner died would
+    # otherwise sit there until the launcher's own limit. No run of this script takes anywhere near this long.
+    limit = float(os.environ.get("TD_BENCH_WATCHDOG_S", "1800"))
+    if limit > 0:
+        def _abort():
+            try:
+                os.write(2, f"bench.py watchdog: no result after {limit:.0f} s (rank {os.environ.get('RANK', '0')}): hung peer wait / collective? aborting\n".encode())
+            finally:
+                os._exit(4)
+
+        watchdog = threading.Timer(limit, _abort)
+        watchdog.daemon = True
+        watchdog.start()
+
     if args.impl == "reference":
         return run_reference_arm(args, emit)
 

@@ -30,3 +30,17 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
 def test_reference_arm_nonzero_rank_is_silent():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_watchdog_aborts_a_run_that_does_not_finish():
+    """bench.py arms a timer before any work (a hung peer wait or collective has no timeout of its own): when it fires the process
+    says so on stderr and exits with status 4 instead of sitting there until the launcher's limit. Disabled with 0."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TD_BENCH_WATCHDOG_S="0.5")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "8", "--warmup", "2"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 4 and "bench.py watchdog" in r.stderr and r.stdout.strip() == ""
