@@ -18,6 +18,13 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
 
+    # no test may hang the box: a stuck stream wait / collective sits in a C call that no signal interrupts, so the limit is
+    # enforced from a watchdog thread (pytest-timeout's "thread" method: dump the stacks, end the process)
+    if config.pluginmanager.hasplugin("timeout"):
+        for item in items:
+            if item.get_closest_marker("timeout") is None:
+                item.add_marker(pytest.mark.timeout(900, method="thread"))
+
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason="no CUDA device")
